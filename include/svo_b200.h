@@ -1,0 +1,163 @@
+/*
+ * svo_b200.h -- C ABI of libsvo_b200.so: the B200 (sm_100a) replacement for
+ * the reference renderer's GPU dispatch boundary for ONE path, the sparse
+ * voxel octree trace (src/shaders/svotrace.comp) and its beam pre-pass
+ * (src/shaders/svobeam.comp).
+ *
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the reference repo root).  Plain pointers and sizes only; no C++ or
+ * torch types.  All functions return 0 on success and a non-zero CUresult-
+ * style code otherwise (never abort the host VM); svo_last_error() gives the
+ * text.  The library is called from one host thread at a time, like the
+ * reference's GL context (Main.java runs everything on the GLFW thread).
+ *
+ * There is no CPU fallback: every call fails with SVO_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ */
+#ifndef SVO_B200_H
+#define SVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_ABI_VERSION 1
+#define SVO_NO_HIT 0xFFFFFFFFu
+
+enum svo_status {
+  SVO_OK = 0,
+  SVO_ERR_INVALID = 1,    /* bad argument (mirrors CUDA_ERROR_INVALID_VALUE) */
+  SVO_ERR_OOM = 2,        /* CUDA_ERROR_OUT_OF_MEMORY */
+  SVO_ERR_NO_DEVICE = 100,/* CUDA_ERROR_NO_DEVICE: no fallback exists */
+  SVO_ERR_CUDA = 999,     /* any other CUDA failure; text in svo_last_error */
+  SVO_ERR_FORMAT = 1000,  /* node stream is not a tree this path can walk */
+  SVO_ERR_NO_SCENE = 1001 /* render/cast before svo_upload */
+};
+
+typedef struct svo_ctx svo_ctx;
+
+/* Per-frame parameters.  Replaces the uniforms written at
+ * src/engine/Main.java:269-283 (locations 8 camPos; 1-4 l1,l2,r1,r2; 5
+ * frameNumber; 6 renderMode; 11 useBeamOptimization; location 9 bufferEnd
+ * is the upload length and lives in svo_upload).  The last four members
+ * expose what the shader hard-codes: MAX_DEPTH 13 (svotrace.comp:40), the
+ * bounce-loop count 2 (:444), the cone LOD cut 11 (:275-277) and the
+ * commented-out mirror material (:500-504; 0 = off = as shipped). */
+typedef struct svo_frame {
+  float camPos[3];
+  float l1[3], l2[3], r1[3], r2[3];
+  int32_t frameNumber;
+  int32_t renderMode;
+  int32_t useBeam;
+  int32_t maxDepth;
+  int32_t casts;
+  int32_t coneDepth;
+  int32_t mirrorValue;
+  int32_t flags; /* reserved, must be 0 */
+} svo_frame;
+
+/* ray-stream records (new capability, BASELINE.json configs[3]) */
+typedef struct svo_ray { float o[3]; float d[3]; } svo_ray;
+typedef struct svo_hit { uint32_t id; float t; uint32_t value; uint32_t iter; } svo_hit;
+
+/* output planes, all width*height elements, row-major, row 0 = gl row 0 */
+enum svo_plane {
+  SVO_PLANE_COLOR_RGBA8 = 0, /* framebufferImage, image unit 0 (Main.java:66-70) */
+  SVO_PLANE_DEPTH = 1,       /* depthbufferImage, image unit 1 (Main.java:73-77) */
+  SVO_PLANE_BEAM = 2,        /* beambufferImage (W/4 x H/4), image unit 2 (Main.java:79-86) */
+  SVO_PLANE_HIT_ID = 3,      /* new: primary res.pointer (svotrace.comp:294,381; store commented out at :728) */
+  SVO_PLANE_ITER = 4,        /* new: primary loop iterations (render mode 1 shows it as a heat map, :428) */
+  SVO_PLANE_PRIMARY_T = 5,   /* new: primary res.t */
+  SVO_PLANE_RADIANCE = 6     /* new: finalcolor before the rgba8 store, float4 */
+};
+
+enum svo_option {
+  SVO_OPT_AUX_PLANES = 1,  /* 0/1: also write planes 3..6 (validation outputs); default 0 */
+  SVO_OPT_FAST_MATH = 2,   /* 0: --fmad=false validation kernels (default, bit-exact contract); 1: fma-contracted build */
+  SVO_OPT_KERNEL = 3,      /* traversal kernel variant; default 0 = best measured */
+  SVO_OPT_L2_PERSIST = 4,  /* 0/1: pin the upper octree levels with an L2 access-policy window; default 1 */
+  SVO_OPT_RAY_SORT = 5     /* 0/1: bin ray streams by octant/direction before tracing; default 1 */
+};
+
+/* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and
+ *    Renderer.addShader (Renderer.java:43-54) ------------------------------- */
+int svo_abi_version(void);
+int svo_device_count(int *count);
+int svo_create(svo_ctx **out, int device, int width, int height);
+void svo_destroy(svo_ctx *ctx);
+const char *svo_last_error(const svo_ctx *ctx); /* ctx may be NULL (creation errors) */
+int svo_set_option(svo_ctx *ctx, int option, int64_t value);
+int svo_get_option(const svo_ctx *ctx, int option, int64_t *value);
+/* Run on a caller-owned CUDA stream (cudaStream_t / CUstream as void*); NULL
+ * restores the context's own stream. */
+int svo_set_stream(svo_ctx *ctx, void *cuda_stream);
+
+/* -- octree upload: replaces Renderer.addSSBO(7, ByteBuffer)
+ *    (Renderer.java:123-129, Main.java:122).  `nodes` is the engine's node
+ *    buffer (Octree.java:63-67), valid bytes [0, nbytes) with nbytes =
+ *    Octree.memOffset.  The library copies; the caller keeps ownership. */
+int svo_upload(svo_ctx *ctx, const uint8_t *nodes, uint64_t nbytes);
+/* replaces Renderer.updateSSBO(7, buf, start, end) (Renderer.java:136-146,
+ * Main.java:349-350): `nodes` is the base of the whole buffer, bytes
+ * [start,end) changed.  end may exceed the previous length (appended nodes). */
+int svo_upload_range(svo_ctx *ctx, const uint8_t *nodes, uint64_t start, uint64_t end);
+/* counts after upload: info[0] node-stream bytes, [1] interior descriptors,
+ * [2] octree levels, [3] device bytes used by the scene */
+int svo_scene_info(const svo_ctx *ctx, uint64_t info[4]);
+
+/* -- dispatch: replaces Renderer.dispatchCompute(traceShader, 240, 135, 1) +
+ *    glMemoryBarrier (Renderer.java:118-121, Main.java:285).  Asynchronous. */
+int svo_render(svo_ctx *ctx, const svo_frame *frame);
+/* rows [y0,y1) only: the image-tile partition for multi-GPU */
+int svo_render_rows(svo_ctx *ctx, const svo_frame *frame, int y0, int y1);
+/* replaces dispatchCompute(beamShader, W/8/4, H/8/4, 1) (Main.java:257-266) */
+int svo_beam(svo_ctx *ctx, const svo_frame *frame);
+int svo_sync(svo_ctx *ctx);
+
+/* -- readback: replaces glGetTexImage(depth) every frame (Main.java:132-146).
+ *    dst is host memory (pinned or pageable), width*height elements. */
+int svo_read_plane(svo_ctx *ctx, int plane, void *dst, uint64_t dst_bytes);
+int svo_read_plane_rows(svo_ctx *ctx, int plane, int y0, int y1, void *dst, uint64_t dst_bytes);
+int svo_read_color_rgba8(svo_ctx *ctx, uint8_t *dst);
+int svo_read_depth(svo_ctx *ctx, float *dst);
+int svo_read_depth_at(svo_ctx *ctx, int x, int y, float *dst); /* the crosshair pick, Main.java:144-146 */
+int svo_read_hit_id(svo_ctx *ctx, uint32_t *dst);
+int svo_read_iter(svo_ctx *ctx, uint32_t *dst);
+int svo_read_primary_t(svo_ctx *ctx, float *dst);
+int svo_read_radiance_f32(svo_ctx *ctx, float *dst);
+/* device address of a plane (for CUDA/NCCL/peer interop); NULL if absent */
+void *svo_device_ptr(svo_ctx *ctx, int plane);
+/* redirect a plane to caller-owned device memory (e.g. a peer GPU's frame
+ * buffer mapped over NVLink); NULL restores the context's own allocation */
+int svo_bind_plane(svo_ctx *ctx, int plane, void *device_ptr);
+
+/* -- ray streams (new): n independent intersectOctree calls.
+ *    svo_cast: host buffers in/out.  svo_cast_device: device buffers. */
+int svo_cast(svo_ctx *ctx, const svo_ray *rays, uint64_t n, svo_hit *out, int maxDepth);
+int svo_cast_device(svo_ctx *ctx, const void *d_rays, uint64_t n, void *d_out, int maxDepth);
+
+/* -- measurement: CUDA events on the stream the kernels run on */
+int svo_timer_begin(svo_ctx *ctx);
+int svo_timer_end(svo_ctx *ctx, float *elapsed_ms); /* synchronises */
+/* kernels launched by this context since creation (for bench.py gpu_launches) */
+int svo_launch_count(const svo_ctx *ctx, uint64_t *count);
+
+/* -- device-side deterministic math probe (tests only: compares the kernel's
+ *    sin/cos/acos/exp/rand with the oracle bit for bit).  fn: 0 sin, 1 cos,
+ *    2 acos, 3 exp, 4 rand(x, y). */
+int svo_math_probe(svo_ctx *ctx, int fn, const float *x, const float *y, float *out, uint64_t n);
+
+/* -- world generation (replaces Octree.constructCompleteOctree,
+ *    Octree.java:192-353, for heightmap worlds).  Host-side, multi-threaded,
+ *    byte-identical to the reference builder's stream.  height: n*n u16 (row =
+ *    z), mat: n*n u8.  Returns bytes needed via *out_bytes; call with out=NULL
+ *    to size.  chunk = CHUNK_SIZE (reference 1024). */
+int svo_build_terrain(const uint16_t *height, const uint8_t *mat, int n, int chunk, uint8_t *out,
+                      uint64_t cap, uint64_t *out_bytes, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H */

@@ -1,0 +1,520 @@
+// svo_capi.cu -- the C ABI declared in include/svo_b200.h.
+//
+// This is the replacement for the reference's GL dispatch boundary,
+// src/engine/Renderer.java (addShader :43-54, addSSBO :123-129, updateSSBO
+// :136-146, dispatchCompute :118-121) plus the raw GL43C calls in
+// src/engine/Main.java (image setup :62-86, uniforms :269-283, depth readback
+// :132-146).  No CPU fallback exists: without a CUDA device every call fails.
+#include "../../include/svo_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "svo_kernels.h"
+#include "svo_transcode.h"
+
+using namespace svo;
+
+static_assert(sizeof(svo_frame) == sizeof(FrameParams), "svo_frame and FrameParams must have one layout");
+static_assert(sizeof(svo_ray) == 24 && sizeof(svo_hit) == 16, "ray-stream records are packed");
+
+static thread_local std::string g_error;
+
+struct svo_ctx {
+  int device = 0;
+  int W = 0, H = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  // scene
+  uint8_t *d_raw = nullptr;
+  uint64_t raw_cap = 0, nbytes = 0;
+  uint2 *d_desc = nullptr;
+  uint32_t *d_refbase = nullptr;
+  uint64_t desc_cap = 0;
+  uint32_t ndesc = 0, nlevels = 0;
+  uint32_t first_word_zero = 1;
+  bool have_scene = false;
+  std::vector<uint8_t> h_raw;  // host shadow of the stream (range updates re-transcode from it)
+  // planes
+  void *own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void *bound[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // ray-stream scratch
+  void *d_rays = nullptr, *d_hits = nullptr;
+  uint64_t cast_cap = 0;
+  // options
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(svo_ctx *c, int code, const std::string &msg) {
+  g_error = msg;
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(svo_ctx *c, cudaError_t e, const char *what) {
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();  // clear sticky-less errors
+  if (e == cudaErrorMemoryAllocation) return fail(c, SVO_ERR_OOM, m);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return fail(c, SVO_ERR_NO_DEVICE, m);
+  return fail(c, SVO_ERR_CUDA, m);
+}
+#define SVO_CUDA(c, call)                                   \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return cuda_fail((c), e_, #call); \
+  } while (0)
+
+size_t plane_elem_bytes(int plane) {
+  switch (plane) {
+    case SVO_PLANE_COLOR_RGBA8: return 4;
+    case SVO_PLANE_RADIANCE: return 16;
+    default: return 4;
+  }
+}
+size_t plane_elems(const svo_ctx *c, int plane) {
+  if (plane == SVO_PLANE_BEAM) return (size_t)(c->W / 4) * (size_t)(c->H / 4);
+  return (size_t)c->W * (size_t)c->H;
+}
+void *plane_ptr(const svo_ctx *c, int plane) { return c->bound[plane] ? c->bound[plane] : c->own[plane]; }
+
+int ensure_aux(svo_ctx *c) {
+  for (int p = SVO_PLANE_HIT_ID; p <= SVO_PLANE_RADIANCE; p++) {
+    if (!c->own[p]) {
+      size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
+      SVO_CUDA(c, cudaMalloc(&c->own[p], bytes ? bytes : 16));
+      SVO_CUDA(c, cudaMemsetAsync(c->own[p], 0, bytes, c->stream));
+    }
+  }
+  return SVO_OK;
+}
+
+SceneView scene_view(const svo_ctx *c) {
+  SceneView v;
+  v.desc = c->d_desc;
+  v.refbase = c->d_refbase;
+  v.raw = c->d_raw;
+  v.nbytes = c->nbytes;
+  v.ndesc = c->ndesc;
+  v.first_word_zero = c->first_word_zero;
+  return v;
+}
+LaunchCfg launch_cfg(const svo_ctx *c) {
+  LaunchCfg l;
+  l.fast = c->opt_fast != 0;
+  l.aux = c->opt_aux != 0;
+  l.kernel = c->opt_kernel;
+  l.sm_count = c->sm_count;
+  return l;
+}
+Planes planes_of(const svo_ctx *c) {
+  Planes p;
+  p.rgba8 = (uchar4 *)plane_ptr(c, SVO_PLANE_COLOR_RGBA8);
+  p.depth = (float *)plane_ptr(c, SVO_PLANE_DEPTH);
+  p.beam = (const float *)plane_ptr(c, SVO_PLANE_BEAM);
+  p.hit_id = (uint32_t *)plane_ptr(c, SVO_PLANE_HIT_ID);
+  p.iter = (uint32_t *)plane_ptr(c, SVO_PLANE_ITER);
+  p.primary_t = (float *)plane_ptr(c, SVO_PLANE_PRIMARY_T);
+  p.radiance = (float4 *)plane_ptr(c, SVO_PLANE_RADIANCE);
+  return p;
+}
+
+int check_frame(svo_ctx *c, const svo_frame *f) {
+  if (!f) return fail(c, SVO_ERR_INVALID, "frame is NULL");
+  if (f->maxDepth < 1 || f->maxDepth > 23) return fail(c, SVO_ERR_INVALID, "maxDepth must be in [1,23]");
+  if (f->coneDepth < 1 || f->coneDepth > 23) return fail(c, SVO_ERR_INVALID, "coneDepth must be in [1,23]");
+  if (f->casts < 0 || f->casts > 64) return fail(c, SVO_ERR_INVALID, "casts must be in [0,64]");
+  if (f->flags != 0) return fail(c, SVO_ERR_INVALID, "flags must be 0");
+  return SVO_OK;
+}
+
+// (re)build the device descriptor arrays from the host shadow of the stream
+int retranscode(svo_ctx *c) {
+  Transcoded t;
+  std::string err;
+  if (!transcode_stream(c->h_raw.data(), c->nbytes, t, err)) return fail(c, SVO_ERR_FORMAT, err);
+  const uint64_t nd = t.desc.size();
+  if (nd > c->desc_cap) {
+    if (c->d_desc) cudaFree(c->d_desc);
+    if (c->d_refbase) cudaFree(c->d_refbase);
+    c->d_desc = nullptr;
+    c->d_refbase = nullptr;
+    c->desc_cap = 0;
+    const uint64_t cap = nd + nd / 8 + 64;
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, cap * sizeof(uint2)));
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, cap * sizeof(uint32_t)));
+    c->desc_cap = cap;
+  }
+  // the kernels may still be reading the previous arrays
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  SVO_CUDA(c, cudaMemcpyAsync(c->d_desc, t.desc.data(), nd * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+  SVO_CUDA(c, cudaMemcpyAsync(c->d_refbase, t.refbase.data(), nd * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // t goes out of scope
+  c->ndesc = (uint32_t)nd;
+  c->nlevels = (uint32_t)t.level_start.size();
+  uint32_t w0 = 0;
+  for (uint64_t i = 0; i < 4 && i < c->nbytes; i++) w0 |= c->h_raw[i];
+  c->first_word_zero = (w0 == 0);
+  c->have_scene = true;
+
+  // L2 access-policy window over the hot upper levels (a prefix of the BFS array)
+  if (c->opt_l2) {
+    cudaDeviceProp prop;
+    SVO_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    size_t win = nd * sizeof(uint2);
+    if ((size_t)prop.accessPolicyMaxWindowSize < win) win = (size_t)prop.accessPolicyMaxWindowSize;
+    size_t persist = (size_t)prop.persistingL2CacheMaxSize;
+    if (persist > 0 && win > 0) {
+      if (win > persist) win = persist;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof attr);
+      attr.accessPolicyWindow.base_ptr = c->d_desc;
+      attr.accessPolicyWindow.num_bytes = win;
+      attr.accessPolicyWindow.hitRatio = 1.0f;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
+  return SVO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svo_abi_version(void) { return SVO_ABI_VERSION; }
+
+int svo_device_count(int *count) {
+  if (!count) return fail(nullptr, SVO_ERR_INVALID, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return cuda_fail(nullptr, e, "cudaGetDeviceCount");
+  }
+  *count = n;
+  return SVO_OK;
+}
+
+int svo_create(svo_ctx **out, int device, int width, int height) {
+  if (!out) return fail(nullptr, SVO_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height > (1ull << 31))
+    return fail(nullptr, SVO_ERR_INVALID, "bad image size");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, SVO_ERR_NO_DEVICE,
+                std::string("no CUDA device (this path has no CPU fallback): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices"));
+  if (device < 0 || device >= n) return fail(nullptr, SVO_ERR_INVALID, "device index out of range");
+  svo_ctx *c = new svo_ctx();
+  c->device = device;
+  c->W = width;
+  c->H = height;
+  int rc = SVO_OK;
+  do {
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaSetDevice"); break; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaGetDeviceProperties"); break; }
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
+    c->stream = c->own_stream;
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
+    for (int p = SVO_PLANE_COLOR_RGBA8; p <= SVO_PLANE_BEAM; p++) {
+      size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
+      if ((e = cudaMalloc(&c->own[p], bytes ? bytes : 16)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(plane)"); break; }
+      cudaMemsetAsync(c->own[p], 0, bytes, c->stream);
+    }
+  } while (0);
+  if (rc != SVO_OK) {
+    svo_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SVO_OK;
+}
+
+void svo_destroy(svo_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  for (int p = 0; p < 7; p++)
+    if (c->own[p]) cudaFree(c->own[p]);
+  if (c->d_raw) cudaFree(c->d_raw);
+  if (c->d_desc) cudaFree(c->d_desc);
+  if (c->d_refbase) cudaFree(c->d_refbase);
+  if (c->d_rays) cudaFree(c->d_rays);
+  if (c->d_hits) cudaFree(c->d_hits);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  cudaGetLastError();
+  delete c;
+}
+
+const char *svo_last_error(const svo_ctx *c) { return c ? c->err.c_str() : g_error.c_str(); }
+
+int svo_set_option(svo_ctx *c, int option, int64_t value) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  switch (option) {
+    case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
+    case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
+    case SVO_OPT_KERNEL: c->opt_kernel = (int)value; return SVO_OK;
+    case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
+    case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
+    default: return fail(c, SVO_ERR_INVALID, "unknown option");
+  }
+}
+int svo_get_option(const svo_ctx *c, int option, int64_t *value) {
+  if (!c || !value) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  switch (option) {
+    case SVO_OPT_AUX_PLANES: *value = c->opt_aux; return SVO_OK;
+    case SVO_OPT_FAST_MATH: *value = c->opt_fast; return SVO_OK;
+    case SVO_OPT_KERNEL: *value = c->opt_kernel; return SVO_OK;
+    case SVO_OPT_L2_PERSIST: *value = c->opt_l2; return SVO_OK;
+    case SVO_OPT_RAY_SORT: *value = c->opt_sort; return SVO_OK;
+    default: return fail(const_cast<svo_ctx *>(c), SVO_ERR_INVALID, "unknown option");
+  }
+}
+
+int svo_set_stream(svo_ctx *c, void *cuda_stream) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return SVO_OK;
+}
+
+int svo_upload(svo_ctx *c, const uint8_t *nodes, uint64_t nbytes) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!nodes && nbytes) return fail(c, SVO_ERR_INVALID, "nodes is NULL");
+  if (nbytes >= (1ull << 32)) return fail(c, SVO_ERR_INVALID, "node stream must be < 4 GiB");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (nbytes + 16 > c->raw_cap) {
+    SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_raw) cudaFree(c->d_raw);
+    c->d_raw = nullptr;
+    c->raw_cap = 0;
+    const uint64_t cap = nbytes + nbytes / 16 + 4096;
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_raw, cap));
+    c->raw_cap = cap;
+  }
+  c->h_raw.assign(nodes, nodes + nbytes);
+  c->nbytes = nbytes;
+  if (nbytes) SVO_CUDA(c, cudaMemcpyAsync(c->d_raw, nodes, nbytes, cudaMemcpyHostToDevice, c->stream));
+  return retranscode(c);
+}
+
+int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t end) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_upload_range before svo_upload");
+  // Renderer.updateSSBO prints "Update SSBO error: Invalid parameters." and returns (Renderer.java:137-140)
+  if (!nodes || start >= end) return fail(c, SVO_ERR_INVALID, "Update SSBO error: Invalid parameters.");
+  if (end >= (1ull << 32)) return fail(c, SVO_ERR_INVALID, "node stream must be < 4 GiB");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (end + 16 > c->raw_cap) {  // appended nodes outgrew the allocation: move the stream
+    uint8_t *nr = nullptr;
+    const uint64_t cap = end + end / 4 + 4096;
+    SVO_CUDA(c, cudaMalloc((void **)&nr, cap));
+    SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->nbytes) SVO_CUDA(c, cudaMemcpy(nr, c->d_raw, c->nbytes, cudaMemcpyDeviceToDevice));
+    cudaFree(c->d_raw);
+    c->d_raw = nr;
+    c->raw_cap = cap;
+  }
+  if (end > c->nbytes) {
+    // bytes between the old end and `start` were never uploaded: they are zero on the
+    // host shadow and must be zero on the device too
+    if (start > c->nbytes) SVO_CUDA(c, cudaMemsetAsync(c->d_raw + c->nbytes, 0, start - c->nbytes, c->stream));
+    c->h_raw.resize(end, 0);
+    c->nbytes = end;
+  }
+  memcpy(c->h_raw.data() + start, nodes + start, end - start);
+  SVO_CUDA(c, cudaMemcpyAsync(c->d_raw + start, nodes + start, end - start, cudaMemcpyHostToDevice, c->stream));
+  return retranscode(c);
+}
+
+int svo_scene_info(const svo_ctx *c, uint64_t info[4]) {
+  if (!c || !info) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  info[0] = c->nbytes;
+  info[1] = c->ndesc;
+  info[2] = c->nlevels;
+  info[3] = c->raw_cap + c->desc_cap * (sizeof(uint2) + sizeof(uint32_t));
+  return SVO_OK;
+}
+
+int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_render before svo_upload");
+  int rc = check_frame(c, frame);
+  if (rc) return rc;
+  if (y0 < 0 || y1 > c->H || y0 > y1) return fail(c, SVO_ERR_INVALID, "row range outside the image");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (c->opt_aux && (rc = ensure_aux(c)) != SVO_OK) return rc;
+  FrameParams fp;
+  memcpy(&fp, frame, sizeof fp);
+  SVO_CUDA(c, launch_render(launch_cfg(c), scene_view(c), fp, planes_of(c), c->W, c->H, y0, y1, c->stream));
+  c->launches++;
+  return SVO_OK;
+}
+int svo_render(svo_ctx *c, const svo_frame *frame) { return svo_render_rows(c, frame, 0, c ? c->H : 0); }
+
+int svo_beam(svo_ctx *c, const svo_frame *frame) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_beam before svo_upload");
+  int rc = check_frame(c, frame);
+  if (rc) return rc;
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  FrameParams fp;
+  memcpy(&fp, frame, sizeof fp);
+  SVO_CUDA(c, launch_beam(launch_cfg(c), scene_view(c), fp, (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
+  c->launches++;
+  return SVO_OK;
+}
+
+int svo_sync(svo_ctx *c) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SVO_OK;
+}
+
+int svo_read_plane_rows(svo_ctx *c, int plane, int y0, int y1, void *dst, uint64_t dst_bytes) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (plane < 0 || plane > SVO_PLANE_RADIANCE || !dst) return fail(c, SVO_ERR_INVALID, "bad plane or NULL dst");
+  const int rows = plane == SVO_PLANE_BEAM ? c->H / 4 : c->H, cols = plane == SVO_PLANE_BEAM ? c->W / 4 : c->W;
+  if (y0 < 0 || y1 > rows || y0 > y1) return fail(c, SVO_ERR_INVALID, "row range outside the plane");
+  const void *src = plane_ptr(c, plane);
+  if (!src) return fail(c, SVO_ERR_INVALID, "plane not allocated (enable SVO_OPT_AUX_PLANES before rendering)");
+  const size_t eb = plane_elem_bytes(plane);
+  const size_t bytes = (size_t)(y1 - y0) * (size_t)cols * eb;
+  if (dst_bytes < bytes) return fail(c, SVO_ERR_INVALID, "dst too small");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (bytes) SVO_CUDA(c, cudaMemcpyAsync(dst, (const char *)src + (size_t)y0 * (size_t)cols * eb, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SVO_OK;
+}
+int svo_read_plane(svo_ctx *c, int plane, void *dst, uint64_t dst_bytes) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  return svo_read_plane_rows(c, plane, 0, plane == SVO_PLANE_BEAM ? c->H / 4 : c->H, dst, dst_bytes);
+}
+int svo_read_color_rgba8(svo_ctx *c, uint8_t *dst) { return svo_read_plane(c, SVO_PLANE_COLOR_RGBA8, dst, ~0ull); }
+int svo_read_depth(svo_ctx *c, float *dst) { return svo_read_plane(c, SVO_PLANE_DEPTH, dst, ~0ull); }
+int svo_read_hit_id(svo_ctx *c, uint32_t *dst) { return svo_read_plane(c, SVO_PLANE_HIT_ID, dst, ~0ull); }
+int svo_read_iter(svo_ctx *c, uint32_t *dst) { return svo_read_plane(c, SVO_PLANE_ITER, dst, ~0ull); }
+int svo_read_primary_t(svo_ctx *c, float *dst) { return svo_read_plane(c, SVO_PLANE_PRIMARY_T, dst, ~0ull); }
+int svo_read_radiance_f32(svo_ctx *c, float *dst) { return svo_read_plane(c, SVO_PLANE_RADIANCE, dst, ~0ull); }
+
+int svo_read_depth_at(svo_ctx *c, int x, int y, float *dst) {
+  if (!c || !dst) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (x < 0 || y < 0 || x >= c->W || y >= c->H) return fail(c, SVO_ERR_INVALID, "pixel outside the image");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  const float *src = (const float *)plane_ptr(c, SVO_PLANE_DEPTH) + (size_t)y * (size_t)c->W + (size_t)x;
+  SVO_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SVO_OK;
+}
+
+void *svo_device_ptr(svo_ctx *c, int plane) {
+  if (!c || plane < 0 || plane > SVO_PLANE_RADIANCE) return nullptr;
+  if (plane >= SVO_PLANE_HIT_ID && !c->own[plane] && !c->bound[plane]) {
+    cudaSetDevice(c->device);
+    if (ensure_aux(c) != SVO_OK) return nullptr;
+  }
+  return plane_ptr(c, plane);
+}
+
+int svo_bind_plane(svo_ctx *c, int plane, void *device_ptr) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (plane < 0 || plane > SVO_PLANE_RADIANCE) return fail(c, SVO_ERR_INVALID, "bad plane");
+  c->bound[plane] = device_ptr;
+  return SVO_OK;
+}
+
+int svo_cast_device(svo_ctx *c, const void *d_rays, uint64_t n, void *d_out, int maxDepth) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_cast before svo_upload");
+  if (maxDepth < 1 || maxDepth > 23) return fail(c, SVO_ERR_INVALID, "maxDepth must be in [1,23]");
+  if (n && (!d_rays || !d_out)) return fail(c, SVO_ERR_INVALID, "NULL ray or hit buffer");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, launch_cast(launch_cfg(c), scene_view(c), d_rays, nullptr, n, d_out, maxDepth, c->stream));
+  if (n) c->launches++;
+  return SVO_OK;
+}
+
+int svo_cast(svo_ctx *c, const svo_ray *rays, uint64_t n, svo_hit *out, int maxDepth) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_cast before svo_upload");
+  if (n == 0) return SVO_OK;
+  if (!rays || !out) return fail(c, SVO_ERR_INVALID, "NULL ray or hit buffer");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (n > c->cast_cap) {
+    SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->d_rays) cudaFree(c->d_rays);
+    if (c->d_hits) cudaFree(c->d_hits);
+    c->d_rays = c->d_hits = nullptr;
+    c->cast_cap = 0;
+    SVO_CUDA(c, cudaMalloc(&c->d_rays, n * sizeof(svo_ray)));
+    SVO_CUDA(c, cudaMalloc(&c->d_hits, n * sizeof(svo_hit)));
+    c->cast_cap = n;
+  }
+  SVO_CUDA(c, cudaMemcpyAsync(c->d_rays, rays, n * sizeof(svo_ray), cudaMemcpyHostToDevice, c->stream));
+  int rc = svo_cast_device(c, c->d_rays, n, c->d_hits, maxDepth);
+  if (rc) return rc;
+  SVO_CUDA(c, cudaMemcpyAsync(out, c->d_hits, n * sizeof(svo_hit), cudaMemcpyDeviceToHost, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SVO_OK;
+}
+
+int svo_timer_begin(svo_ctx *c) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  return SVO_OK;
+}
+int svo_timer_end(svo_ctx *c, float *ms) {
+  if (!c || !ms) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  SVO_CUDA(c, cudaEventSynchronize(c->ev1));
+  SVO_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return SVO_OK;
+}
+int svo_launch_count(const svo_ctx *c, uint64_t *count) {
+  if (!c || !count) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  *count = c->launches;
+  return SVO_OK;
+}
+
+int svo_math_probe(svo_ctx *c, int fn, const float *x, const float *y, float *out, uint64_t n) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return SVO_OK;
+  if (!x || !out || (fn == 4 && !y)) return fail(c, SVO_ERR_INVALID, "NULL argument");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  SVO_CUDA(c, cudaMalloc((void **)&dx, n * 4));
+  SVO_CUDA(c, cudaMalloc((void **)&dy, n * 4));
+  SVO_CUDA(c, cudaMalloc((void **)&dout, n * 4));
+  SVO_CUDA(c, cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, c->stream));
+  SVO_CUDA(c, cudaMemcpyAsync(dy, y ? y : x, n * 4, cudaMemcpyHostToDevice, c->stream));
+  SVO_CUDA(c, launch_math_probe(fn, dx, dy, dout, n, c->stream));
+  c->launches++;
+  SVO_CUDA(c, cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dx);
+  cudaFree(dy);
+  cudaFree(dout);
+  return SVO_OK;
+}
+
+}  // extern "C"

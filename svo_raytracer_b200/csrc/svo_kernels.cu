@@ -1,0 +1,138 @@
+// svo_kernels.cu -- __global__ entry points of the SVO trace path (sm_100a).
+// Launch geometry replaces glDispatchCompute(ceil(W/8), ceil(H/8), 1) with
+// local size 8x8 (reference src/engine/Main.java:108-109,285;
+// src/shaders/svotrace.comp:648).
+#include "svo_kernels.h"
+#include "svo_trace.cuh"
+
+namespace svo {
+
+// ---------------------------------------------------------------------------
+// Kernel variant 0: one thread per pixel.  A warp owns an 8x4 pixel tile (so
+// its 32 primary rays share the upper octree levels and its stores fill whole
+// 32-byte sectors); a 128-thread CTA owns 16x8 pixels.
+// ---------------------------------------------------------------------------
+template <bool FAST, bool AUX>
+__global__ void __launch_bounds__(128) k_render_tile(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  if (x >= W || y >= y1) return;
+  shade_pixel<FAST, AUX>(sc, f, pl, W, H, x, y);
+}
+
+// ---------------------------------------------------------------------------
+// Ray streams: n independent intersectOctree calls (coneTrace = false).
+// ---------------------------------------------------------------------------
+struct RayRec { float ox, oy, oz, dx, dy, dz; };
+struct HitRec { uint32_t id; float t; uint32_t value, iter; };
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_cast_stream(SceneView sc, const RayRec *__restrict__ rays, const uint32_t *__restrict__ order,
+                                                     uint64_t n, HitRec *__restrict__ out, int maxDepth) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = order ? (uint64_t)order[i] : i;
+    const RayRec ray = rays[r];
+    CastRes res;
+    res.value = res.pointer = res.iter = res.depth = 0u;
+    res.t = 0.0f; res.scale = 0.0f; res.dbg = 0.0f; res.dbg_init = 0;
+    res.normal = mk3(0.f, 0.f, 0.f); res.voxelPos = mk3(0.f, 0.f, 0.f);
+    uint32_t loops = 0;
+    const bool hit = cast_ray<FAST>(sc, mk3(ray.ox, ray.oy, ray.oz), mk3(ray.dx, ray.dy, ray.dz), maxDepth, false, 11, res, loops);
+    HitRec h;
+    h.id = hit ? res.pointer : kNoHit;
+    h.t = hit ? res.t : 0.0f;
+    h.value = hit ? res.value : 0u;
+    h.iter = loops;
+    out[r] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Beam pre-pass (reference src/shaders/svobeam.comp:617-636): one
+// UN-normalised ray through pixel (4gx, 4gy); stores res.t (0 on miss, where
+// upstream leaves it undefined).
+// ---------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_beam(SceneView sc, FrameParams f, float *__restrict__ beam, int W, int H) {
+  const int bw = W >> 2, bh = H >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  if (gx >= bw || gy >= bh) return;
+  const float fx = fdiv(fadd((float)(gx * 4), 0.5f), (float)W);
+  const float fy = fdiv(fadd((float)(gy * 4), 0.5f), (float)H);
+  vec3 dir;
+  dir.x = mixf(mixf(f.l1[0], f.l2[0], fy), mixf(f.r1[0], f.r2[0], fy), fx);
+  dir.y = mixf(mixf(f.l1[1], f.l2[1], fy), mixf(f.r1[1], f.r2[1], fy), fx);
+  dir.z = mixf(mixf(f.l1[2], f.l2[2], fy), mixf(f.r1[2], f.r2[2], fy), fx);
+  CastRes res;
+  res.value = res.pointer = res.iter = res.depth = 0u;
+  res.t = 0.0f; res.scale = 0.0f; res.dbg = 0.0f; res.dbg_init = 0;
+  res.normal = mk3(0.f, 0.f, 0.f); res.voxelPos = mk3(0.f, 0.f, 0.f);
+  uint32_t loops = 0;
+  const bool hit = cast_ray<FAST>(sc, mk3(f.camPos[0], f.camPos[1], f.camPos[2]), dir, f.maxDepth, false, f.coneDepth, res, loops);
+  beam[(size_t)gy * (size_t)bw + (size_t)gx] = hit ? res.t : 0.0f;
+}
+
+__global__ void k_math_probe(int fn, const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float r;
+  switch (fn) {
+    case 0: r = det_sin(x[i]); break;
+    case 1: r = det_cos(x[i]); break;
+    case 2: r = det_acos(x[i]); break;
+    case 3: r = det_exp(x[i]); break;
+    default: r = det_rand(x[i], y[i]); break;
+  }
+  out[i] = r;
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
+                          int y0, int y1, cudaStream_t stream) {
+  const dim3 block(128);
+  const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
+  if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+  if (cfg.fast) {
+    if (cfg.aux) k_render_tile<true, true><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1);
+    else k_render_tile<true, false><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1);
+  } else {
+    if (cfg.aux) k_render_tile<false, true><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1);
+    else k_render_tile<false, false><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d_rays, const uint32_t *d_order, uint64_t n,
+                        void *d_out, int maxDepth, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int block = 128;
+  uint64_t want = (n + block - 1) / block;
+  const uint64_t cap = (uint64_t)cfg.sm_count * 16u * 8u;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (cfg.fast) k_cast_stream<true><<<grid, block, 0, stream>>>(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
+  else k_cast_stream<false><<<grid, block, 0, stream>>>(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, float *beam, int W, int H,
+                        cudaStream_t stream) {
+  const int bw = W >> 2, bh = H >> 2;
+  if (bw == 0 || bh == 0) return cudaSuccess;
+  const dim3 block(128), grid((bw + 15) / 16, (bh + 7) / 8);
+  if (cfg.fast) k_beam<true><<<grid, block, 0, stream>>>(sc, f, beam, W, H);
+  else k_beam<false><<<grid, block, 0, stream>>>(sc, f, beam, W, H);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_math_probe(int fn, const float *x, const float *y, float *out, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fn, x, y, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace svo

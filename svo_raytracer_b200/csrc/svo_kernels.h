@@ -1,0 +1,48 @@
+// svo_kernels.h -- host-visible types and launchers of the trace kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace svo {
+
+struct SceneView {
+  const uint2 *desc;        // interior-node descriptors, BFS order, [ndesc]
+  const uint32_t *refbase;  // reference byte offset of each node's child block, [ndesc]
+  const uint8_t *raw;       // the reference node stream, [nbytes]
+  uint64_t nbytes;
+  uint32_t ndesc;
+  uint32_t first_word_zero;  // octreeBuffer[0] == 0 (svotrace.comp:696)
+};
+
+struct FrameParams {  // == svo_frame (include/svo_b200.h)
+  float camPos[3];
+  float l1[3], l2[3], r1[3], r2[3];
+  int frameNumber, renderMode, useBeam, maxDepth, casts, coneDepth, mirrorValue, flags;
+};
+
+struct Planes {
+  uchar4 *rgba8;
+  float *depth;
+  const float *beam;
+  uint32_t *hit_id;
+  uint32_t *iter;
+  float *primary_t;
+  float4 *radiance;
+};
+
+struct LaunchCfg {
+  bool fast;     // Ops<true>: fma-contracted t arithmetic
+  bool aux;      // also write hit_id / iter / primary_t / radiance
+  int kernel;    // variant selector (SVO_OPT_KERNEL)
+  int sm_count;
+};
+
+cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
+                          int y0, int y1, cudaStream_t stream);
+cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d_rays, const uint32_t *d_order, uint64_t n,
+                        void *d_out, int maxDepth, cudaStream_t stream);
+cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, float *beam, int W, int H,
+                        cudaStream_t stream);
+cudaError_t launch_math_probe(int fn, const float *x, const float *y, float *out, uint64_t n, cudaStream_t stream);
+
+}  // namespace svo
