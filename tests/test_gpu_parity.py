@@ -1,0 +1,114 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs.  Bit-exact for ids / iteration counts / depth /
+rgba8 (integer and index work, and -- because the arithmetic contract is fixed
+on both sides -- the float planes too)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PLANES = ("rgba8", "depth", "radiance", "hit_id", "iter", "primary_t")
+
+
+def _render_gpu(svo, ctx, frame):
+    ctx.render(frame)
+    return {"rgba8": ctx.read_color_rgba8(), "depth": ctx.read_depth(), "radiance": ctx.read_radiance(),
+            "hit_id": ctx.read_hit_id(), "iter": ctx.read_iter(), "primary_t": ctx.read_primary_t()}
+
+
+def _assert_planes_equal(got, want, what):
+    for k in PLANES:
+        g, w = got[k], want[k]
+        if g.dtype.kind == "f":
+            same = (g.view(np.uint32) == w.view(np.uint32)) | (np.isnan(g) & np.isnan(w))
+        else:
+            same = g == w
+        bad = int((~same).sum())
+        assert bad == 0, "%s: plane %s differs in %d of %d elements" % (what, k, bad, same.size)
+
+
+@pytest.fixture(scope="module")
+def ctx512(svo, terrain512):
+    c = svo.SvoContext(640, 360)
+    c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+    c.upload(terrain512)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("cam", ["A", "B", "C"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_config1_all_modes_bit_exact(svo, oracle, terrain512, ctx512, cam, mode):
+    """BASELINE configs[0]: 512^3 terrain, 640x360, every render mode, cameras A/B/C."""
+    pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+    want, st = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=3, render_mode=mode),
+                             640, 360, nthreads=8)
+    assert st.stale_pops == 0
+    got = _render_gpu(svo, ctx512, svo.camera_frame(cam, frame_number=3, render_mode=mode))
+    _assert_planes_equal(got, want, "cam %s mode %d" % (cam, mode))
+
+
+def test_math_probe_bit_exact(svo, oracle, ctx512):
+    rng = np.random.default_rng(7)
+    L = oracle.lib()
+    cases = {
+        0: np.concatenate([rng.uniform(-7, 7, 20000), rng.uniform(-2e6, 2e6, 20000), [0.0, -0.0, np.inf, np.nan, 1e9, 3e38]]),
+        1: np.concatenate([rng.uniform(-7, 7, 20000), rng.uniform(-2e6, 2e6, 20000), [0.0, -0.0, np.inf, np.nan]]),
+        2: np.concatenate([rng.uniform(-1, 1, 40000), [-1.0, 1.0, 0.5, -0.5, 1.0000001, np.nan]]),
+        3: np.concatenate([rng.uniform(-20, 5, 40000), rng.uniform(-110, 90, 2000), [0.0, np.nan, -np.inf, np.inf]]),
+    }
+    names = {0: "sin", 1: "cos", 2: "acos", 3: "exp"}
+    for fn, x in cases.items():
+        x = x.astype(np.float32)
+        got = ctx512.math_probe(fn, x)
+        f = getattr(L, "svo_oracle_" + names[fn])
+        want = np.array([f(float(v)) for v in x], dtype=np.float32)
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), "%s differs at %s" % (names[fn], x[~same][:5])
+    x = rng.uniform(0, 8192, 20000).astype(np.float32)
+    y = rng.uniform(0, 8192, 20000).astype(np.float32)
+    got = ctx512.math_probe(4, x, y)
+    want = np.array([L.svo_oracle_rand(float(a), float(b)) for a, b in zip(x, y)], dtype=np.float32)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+
+
+def test_ray_stream_bit_exact(svo, oracle, terrain512, ctx512):
+    """Incoherent rays (BASELINE configs[3] in miniature): random origins in/around the cube, random directions,
+    including axis-parallel, zero and NaN directions."""
+    rng = np.random.default_rng(42)
+    n = 200000
+    rays = np.zeros(n, dtype=svo.RAY_DTYPE)
+    rays["o"] = rng.uniform(0.9, 2.1, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["d"][:50, 0] = 0.0          # axis-parallel (t_coef = -inf quirk)
+    rays["d"][50:60] = 0.0           # zero direction
+    rays["d"][60:70] = np.nan        # NaN direction (zero-normal bounce)
+    rays["d"][70:80, 1] = np.nan
+    rays["o"][80:90] = np.nan
+    for depth in (13, 9, 5):
+        want, st = oracle.cast_rays(terrain512, rays, max_depth=depth, nthreads=8)
+        got = ctx512.cast(rays, max_depth=depth)
+        for k in ("id", "value", "iter"):
+            assert (got[k] == want[k]).all(), "depth %d field %s: %d mismatches" % (depth, k, (got[k] != want[k]).sum())
+        assert (got["t"].view(np.uint32) == want["t"].view(np.uint32)).all()
+        assert st.stale_pops == 0
+
+
+def test_multichunk_tree_and_rows(svo, oracle, terrain128):
+    """Fill levels + chunk splices (128^3 world of 64^3 chunks) and the row-band partition."""
+    W, H = 200, 120  # not a multiple of the 16x8 CTA tile
+    with svo.SvoContext(W, H) as c:
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.upload(terrain128)
+        for cam in ("A", "B", "C"):
+            pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+            want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=0, max_depth=7),
+                                    W, H, nthreads=8)
+            f = svo.camera_frame(cam, frame_number=1, render_mode=0, max_depth=7)
+            # render as three uneven bands, as the multi-GPU tile partition does
+            for y0, y1 in ((0, 37), (37, 38), (38, H)):
+                c.render(f, y0, y1)
+            got = {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(),
+                   "hit_id": c.read_hit_id(), "iter": c.read_iter(), "primary_t": c.read_primary_t()}
+            _assert_planes_equal(got, want, "terrain128 cam " + cam)
