@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the SVO trace path (primary + diffuse bounce) on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line on rank 0.  A "step" is one pass of the hot path over one
+frame: render mode 0 of the reference shader (primary cast + one diffuse bounce
+cast where the primary hit, src/shaders/svotrace.comp:443-560) at 1920x1080.
+Rays = intersectOctree calls actually issued.
+
+  value      whole-job Mrays/s with octree and frame parameters resident on the
+             device (kernel launches only in the timed region)
+  e2e        the same through the C ABI with HOST buffers: the frame struct comes
+             from host memory each step and the colour + depth planes are read
+             back into pinned host memory each step (what Main.java does per frame)
+  roofline   algorithmic bytes of the reference layout (7 B root + every child
+             record the reference fetches + 8 B/pixel output) / kernel time,
+             against the measured HBM copy peak; plus the random-sector gather
+             roofline of SURVEY 8d
+  cpu_baseline  the CPU oracle (a port of the reference shader; the reference's
+             own Java/GLSL cannot run here) on the host cores, bounded sample
+
+`--impl reference` times that CPU oracle as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+CAM_CYCLE = ("A", "B", "C")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=int(os.environ.get("SVO_BENCH_SIZE", "8192")), help="world edge in voxels")
+    ap.add_argument("--fast-math", type=int, default=0, help="1: fma-contracted kernels (not bit-exact)")
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def world(size: int):
+    """Synthetic heightmap world, built by the product's own generator (host code)."""
+    import svo_raytracer_b200 as svo
+    t0 = time.time()
+    hm, mm = svo.terrain_inputs(size)
+    nodes = svo.build_terrain(hm, mm, size, min(size, 1024))
+    return nodes, time.time() - t0
+
+
+def frame_for(step: int, size: int):
+    import svo_raytracer_b200 as svo
+    depth = min(13, max(1, int(np.log2(size))))  # MAX_DEPTH = log2 N (13 for the reference's 8192^3, svotrace.comp:40)
+    return svo.camera_frame(CAM_CYCLE[step % len(CAM_CYCLE)], frame_number=step + 1, render_mode=0,
+                            max_depth=depth, casts=2, cone_depth=11)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(nodes, size, steps, warmup, budget_s, cores):
+    """The CPU oracle (port of svotrace.comp) on the host cores; bounded sample of the same workload."""
+    from oracle import oracle as O
+    O.build()
+    # bounded sample: every `stride`-th row block of each frame, sized from a pilot run
+    def run(step, y0, y1):
+        f = frame_for(step, size)
+        of = O.make_frame(list(f.camPos), list(f.l1), list(f.l2), list(f.r1), list(f.r2), frame_number=f.frameNumber,
+                          render_mode=f.renderMode, max_depth=f.maxDepth, casts=f.casts, cone_depth=f.coneDepth)
+        t0 = time.perf_counter()
+        _, st = O.render(nodes, of, W, H, y0=y0, y1=y1, nthreads=cores, planes=("rgba8", "depth"))
+        return st.casts, time.perf_counter() - t0
+    rows = 40
+    pilot_rays, pilot_t = 0, 0.0
+    for s in range(3):
+        r, t = run(s, H // 2 - rows // 2, H // 2 + rows // 2)
+        pilot_rays += r
+        pilot_t += t
+    per_step_budget = budget_s / max(1, steps + warmup)
+    rows = int(max(8, min(H, rows * per_step_budget / max(pilot_t / 3, 1e-6))))
+    y0 = (H - rows) // 2
+    for s in range(warmup):
+        run(s, y0, y0 + rows)
+    rays, secs = 0, 0.0
+    for s in range(steps):
+        r, t = run(warmup + s, y0, y0 + rows)
+        rays += r
+        secs += t
+    return rays / secs / 1e6, "rows [%d,%d) of each 1920x1080 frame, %d steps, cameras A/B/C cycled" % (y0, y0 + rows, steps), secs / steps * 1e3
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode 0 (primary + 1 diffuse bounce), cameras A/B/C cycled" % (a.size, W, H)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        nodes, _ = world(a.size)
+        v, sample, ms = cpu_arm(nodes, a.size, a.steps, a.warmup, 120.0, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "Mrays/s (primary + diffuse bounce)", "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "tree_bytes": int(nodes.size)},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import svo_raytracer_b200 as svo
+    from svo_raytracer_b200 import _lib as L
+
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world_size > 1 else 0
+    torch.cuda.set_device(dev)
+
+    nodes, build_s = world(a.size)
+    ctx = svo.SvoContext(W, H, device=dev)
+    ctx.set_option(L.OPT_FAST_MATH, a.fast_math)
+    ctx.set_option(L.OPT_KERNEL, a.kernel)
+    t0 = time.time()
+    ctx.upload(nodes)
+    upload_s = time.time() - t0
+    info = ctx.scene_info()
+
+    # Units: with N ranks every rank renders its own progressive sample (frameNumber) of the same views --
+    # independent units, no data-path collective (weak scaling); step s on rank r is sample s*N + r.
+    def my_frame(s):
+        f = frame_for(s, a.size)
+        f.frameNumber = s * world_size + rank + 1
+        return f
+
+    total = a.warmup + a.steps
+    frames = [my_frame(s) for s in range(total)]
+
+    # rays per frame and algorithmic bytes (instrumented kernel, outside the timed region)
+    per_cam = {}
+    for ci, cam in enumerate(CAM_CYCLE):
+        per_cam[cam] = ctx.render_stats(frames[ci])
+    rays_per_step = [per_cam[CAM_CYCLE[s % 3]]["casts"] for s in range(total)]
+    # bounce rays depend on the RNG sample only through hit/miss of the PRIMARY cast: casts are identical per camera
+    alg_bytes_per_step = [per_cam[CAM_CYCLE[s % 3]]["record_bytes"] + 8 * W * H for s in range(total)]
+    iters_per_step = [per_cam[CAM_CYCLE[s % 3]]["iters"] for s in range(total)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------
+    for s in range(a.warmup):
+        ctx.render(frames[s])
+    ctx.sync()
+    barrier()
+    clocks = ClockSampler(dev)
+    launches0 = ctx.launch_count()
+    ctx.timer_begin()
+    for s in range(a.warmup, total):
+        ctx.render(frames[s])
+    dev_ms = ctx.timer_end()
+    launches = ctx.launch_count() - launches0
+    barrier()
+    clk = clocks.stop()
+    if dist is not None:
+        t = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_ms = float(t.item())
+        r = torch.tensor([float(sum(rays_per_step[a.warmup:]))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r)
+        all_rays = float(r.item())
+    else:
+        max_ms, all_rays = dev_ms, float(sum(rays_per_step[a.warmup:]))
+    value = all_rays / (max_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers -------------------------
+    color_h = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    depth_h = torch.empty((H, W), dtype=torch.float32).pin_memory()
+    def e2e_step(s):
+        ctx.render(frames[s])  # the 96-byte svo_frame is read from host memory by the call
+        ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
+        ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
+    for s in range(a.warmup):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(a.warmup, total):
+        e2e_step(s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = all_rays / e2e_s / 1e6
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline ----------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    timed = range(a.warmup, total)
+    launch_ms = dev_ms / max(1, launches)
+    alg_bytes = float(np.mean([alg_bytes_per_step[s] for s in timed]))
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    mean_F = sum(iters_per_step[s] for s in timed) / sum(rays_per_step[s] for s in timed)
+    gather = {}
+    try:
+        S = ctx.gather_probe(min(max(info["descriptors"] * 8, 1 << 20), 8 << 30))
+        rays_s = sum(rays_per_step[s] for s in timed) / (dev_ms * 1e-3)
+        gather = {"sectors_per_s": S, "working_set_bytes": info["descriptors"] * 8, "node_fetches_per_ray": mean_F,
+                  "achieved_sector_equiv_per_s": rays_s * mean_F, "frac": rays_s * mean_F / S}
+    except svo.SvoError as e:
+        gather = {"error": str(e)}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "k_render_tile", "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_ms": launch_ms, "gather": gather}
+
+    cpu = None
+    if not a.no_cpu_baseline and world_size == 1:
+        v, sample, _ = cpu_arm(nodes, a.size, 3, 0, a.cpu_seconds, cores)
+        cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}
+
+    out = {
+        "metric": "Mrays/s (primary + diffuse bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "tree_bytes": int(nodes.size), "descriptors": info["descriptors"], "levels": info["levels"],
+                   "l2_policy": "inputs larger than L2 (octree %.2f GB, 3 camera poses cycled); no flush between steps" % (nodes.size / 1e9)
+                   if nodes.size > 126e6 else "octree fits L2; camera poses cycled; no flush",
+                   "fast_math": a.fast_math, "kernel": a.kernel, "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
+                   "world_build_s": round(build_s, 2), "upload_transcode_s": round(upload_s, 2),
+                   "units": "rank r renders progressive sample s*N+r of each view; no data-path collective"},
+        "clocks": clk, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 8,
+                "ms_per_step": e2e_s / a.steps * 1e3},
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

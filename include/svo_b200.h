@@ -143,6 +143,15 @@ int svo_timer_begin(svo_ctx *ctx);
 int svo_timer_end(svo_ctx *ctx, float *elapsed_ms); /* synchronises */
 /* kernels launched by this context since creation (for bench.py gpu_launches) */
 int svo_launch_count(const svo_ctx *ctx, uint64_t *count);
+/* Instrumented render (validation kernels + counters), synchronous.  Writes all
+ * planes like svo_render with SVO_OPT_AUX_PLANES and returns counters[0] =
+ * intersectOctree calls, [1] = loop iterations (= child records the reference
+ * fetches, svotrace.comp:294), [2] = bytes of those records in the reference
+ * layout plus 7 per cast for the root (SURVEY 8d "algorithmic bytes"). */
+int svo_render_stats(svo_ctx *ctx, const svo_frame *frame, uint64_t counters[3]);
+/* Gather roofline: random 32-byte-sector read rate over a working
+ * set of `working_set_bytes`, measured with CUDA events.  Returns sectors/s. */
+int svo_gather_probe(svo_ctx *ctx, uint64_t working_set_bytes, int loads_per_thread, double *sectors_per_s);
 
 /* -- device-side deterministic math probe (tests only: compares the kernel's
  *    sin/cos/acos/exp/rand with the oracle bit for bit).  fn: 0 sin, 1 cos,
@@ -156,6 +165,12 @@ int svo_math_probe(svo_ctx *ctx, int fn, const float *x, const float *y, float *
  *    to size.  chunk = CHUNK_SIZE (reference 1024). */
 int svo_build_terrain(const uint16_t *height, const uint8_t *mat, int n, int chunk, uint8_t *out,
                       uint64_t cap, uint64_t *out_bytes, int nthreads);
+
+/* Deterministic synthetic inputs for benchmarks and tests (the reference's
+ * 8192^2 heightmap / material PNGs are absent upstream): n*n u16 heights with
+ * the value span of assets/heightmaps/nz.png and n*n u8 materials in {1,2,3}.
+ * Host-side, multi-threaded, bit-reproducible for a given (n, seed). */
+int svo_terrain_generate(int n, int seed, uint16_t *height, uint8_t *mat, int nthreads);
 
 #ifdef __cplusplus
 }

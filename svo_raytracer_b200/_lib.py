@@ -71,7 +71,10 @@ SYMBOLS = {
     "svo_timer_begin": (_i, [_vp]),
     "svo_timer_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "svo_launch_count": (_i, [_vp, C.POINTER(_u64)]),
+    "svo_render_stats": (_i, [_vp, C.POINTER(Frame), C.POINTER(_u64 * 3)]),
+    "svo_gather_probe": (_i, [_vp, _u64, _i, C.POINTER(C.c_double)]),
     "svo_math_probe": (_i, [_vp, _i, _vp, _vp, _vp, _u64]),
+    "svo_terrain_generate": (_i, [_i, _i, _vp, _vp, _i]),
     "svo_build_terrain": (_i, [_vp, _vp, _i, _i, _vp, _u64, C.POINTER(_u64), _i]),
 }
 

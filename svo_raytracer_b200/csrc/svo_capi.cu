@@ -496,6 +496,58 @@ int svo_launch_count(const svo_ctx *c, uint64_t *count) {
   return SVO_OK;
 }
 
+int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
+  if (!c || !counters) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_render_stats before svo_upload");
+  int rc = check_frame(c, frame);
+  if (rc) return rc;
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if ((rc = ensure_aux(c)) != SVO_OK) return rc;
+  unsigned long long *d = nullptr;
+  SVO_CUDA(c, cudaMalloc((void **)&d, 3 * sizeof(unsigned long long)));
+  SVO_CUDA(c, cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), c->stream));
+  FrameParams fp;
+  memcpy(&fp, frame, sizeof fp);
+  SVO_CUDA(c, launch_render_stats(scene_view(c), fp, planes_of(c), c->W, c->H, 0, c->H, d, c->stream));
+  c->launches++;
+  unsigned long long h[3];
+  SVO_CUDA(c, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  for (int i = 0; i < 3; i++) counters[i] = h[i];
+  return SVO_OK;
+}
+
+int svo_gather_probe(svo_ctx *c, uint64_t working_set_bytes, int loads_per_thread, double *sectors_per_s) {
+  if (!c || !sectors_per_s) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (working_set_bytes < 4096 || loads_per_thread < 8) return fail(c, SVO_ERR_INVALID, "working set or load count too small");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  const uint64_t words = working_set_bytes / 8;
+  void *buf = nullptr;
+  uint32_t *sink = nullptr;
+  SVO_CUDA(c, cudaMalloc(&buf, words * 8));
+  SVO_CUDA(c, cudaMalloc((void **)&sink, 64));
+  SVO_CUDA(c, cudaMemsetAsync(buf, 1, words * 8, c->stream));
+  const int loads = (loads_per_thread + 7) / 8 * 8;
+  const int blocks = c->sm_count * 8;
+  SVO_CUDA(c, launch_gather_probe(buf, words, loads, blocks, sink, c->stream));  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    SVO_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    SVO_CUDA(c, launch_gather_probe(buf, words, loads, blocks, sink, c->stream));
+    SVO_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    SVO_CUDA(c, cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    SVO_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ms < best) best = ms;
+  }
+  c->launches += 6;
+  cudaFree(buf);
+  cudaFree(sink);
+  *sectors_per_s = (double)blocks * 256.0 * (double)loads / ((double)best * 1e-3);
+  return SVO_OK;
+}
+
 int svo_math_probe(svo_ctx *c, int fn, const float *x, const float *y, float *out, uint64_t n) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (n == 0) return SVO_OK;

@@ -21,6 +21,49 @@ __global__ void __launch_bounds__(128) k_render_tile(SceneView sc, FrameParams f
   shade_pixel<FAST, AUX>(sc, f, pl, W, H, x, y);
 }
 
+// Instrumented build of variant 0: same traversal, plus the oracle's counters
+// (casts, loop iterations, bytes of the reference-layout records the reference
+// would have fetched).  bench.py runs it once, outside the timed region, to get
+// the algorithmic bytes of the workload; tests compare it with the oracle.
+__global__ void __launch_bounds__(128) k_render_stats(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
+                                                      unsigned long long *counters) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  RayStats rs;
+  rs.casts = rs.iters = rs.record_bytes = 0u;
+  if (x < W && y < y1) shade_pixel<false, true, true>(sc, f, pl, W, H, x, y, &rs);
+  const uint32_t c = __reduce_add_sync(0xffffffffu, rs.casts);
+  const uint32_t i = __reduce_add_sync(0xffffffffu, rs.iters);
+  const uint32_t b = __reduce_add_sync(0xffffffffu, rs.record_bytes);
+  if (lane == 0) {
+    atomicAdd(counters + 0, (unsigned long long)c);
+    atomicAdd(counters + 1, (unsigned long long)i);
+    atomicAdd(counters + 2, (unsigned long long)b);
+  }
+}
+
+// Random-sector gather microbenchmark: the "gather roofline" S of SURVEY 8d.
+// Every thread issues `loads` independent 8-byte read-only loads (8 in flight)
+// at hashed offsets of a `words`-long uint2 array, i.e. one random 32-byte
+// sector each -- the access pattern of a PUSH in cast_ray.
+__global__ void __launch_bounds__(256) k_gather_probe(const uint2 *__restrict__ buf, uint64_t words, int loads, uint32_t *__restrict__ sink) {
+  uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  uint32_t acc = 0;
+  for (int i = 0; i < loads; i += 8) {
+    uint2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      const uint64_t idx = __umul64hi(s, words);  // uniform in [0, words)
+      v[j] = __ldg(buf + idx);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc ^= v[j].x + v[j].y;
+  }
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
 // ---------------------------------------------------------------------------
 // Ray streams: n independent intersectOctree calls (coneTrace = false).
 // ---------------------------------------------------------------------------
@@ -104,6 +147,20 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
     if (cfg.aux) k_render_tile<false, true><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1);
     else k_render_tile<false, false><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1,
+                                unsigned long long *d_counters, cudaStream_t stream) {
+  const dim3 block(128);
+  const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
+  if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+  k_render_stats<<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, d_counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int blocks, uint32_t *sink, cudaStream_t stream) {
+  k_gather_probe<<<blocks, 256, 0, stream>>>((const uint2 *)buf, words, loads, sink);
   return cudaGetLastError();
 }
 

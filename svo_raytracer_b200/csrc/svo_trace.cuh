@@ -81,10 +81,14 @@ SVO_DI uint32_t child_offset(uint32_t codes, uint32_t c) {
 SVO_DI float sign_glsl(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
 // intersectOctree (svotrace.comp:211-432).  Returns hit; `loops` = iterations run.
-template <bool FAST>
+struct RayStats {  // per-thread counters of the instrumented build (SVO_OPT_STATS)
+  uint32_t casts, iters, record_bytes;
+};
+
+template <bool FAST, bool STATS = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, vec3 d, int maxDepth,
                                          const bool coneTrace, const int coneDepth, CastRes &res,
-                                         uint32_t &loops) {
+                                         uint32_t &loops, RayStats *rs = nullptr) {
   typedef Ops<FAST> M;
   const float kEps = 3.552713678800501e-15f;  // :31
   res.dbg_init = 1;                            // :213
@@ -138,6 +142,10 @@ __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, vec3
     const float tc_max = fminf(fminf(tx_corner, ty_corner), tz_corner);
 
     child_shift = idx ^ octant_mask;  // :286
+    if (STATS) {  // size of the child record the reference fetches here (extractChild :294)
+      const uint32_t code = (pd.y >> (2u * child_shift)) & 3u;
+      rs->record_bytes += code == 1u ? 3u : (code == 3u ? 1u : 7u);
+    }
     // child.value != 0 (:295) is bit 16+child of the parent's descriptor
     if (((pd.y >> (16u + child_shift)) & 1u) != 0u && t_min <= t_max) {
       if (kMaxScale - scale == maxDepth) { hit = true; break; }  // :300-302
@@ -202,6 +210,11 @@ __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, vec3
     }
   }
   loops = iter;
+  if (STATS) {
+    rs->casts += 1u;
+    rs->record_bytes += 7u;  // extractNode(0) :222
+    rs->iters += iter > (uint32_t)kMaxIterations ? (uint32_t)kMaxIterations : iter;
+  }
 
   if (!hit) {
     if (iter <= (uint32_t)kMaxIterations) {  // :371-377
@@ -264,9 +277,9 @@ SVO_DI vec3 sky(vec3 dir) {  // :449-450, :629-631
 }
 
 // trace (svotrace.comp:435-646)
-template <bool FAST>
+template <bool FAST, bool STATS>
 __device__ __forceinline__ void trace_pixel(const SceneView &sc, const FrameParams &f, float beamDist, vec3 origin,
-                                            vec3 dir, float seed0, float seed1, float seed2, PixelOut &out) {
+                                            vec3 dir, float seed0, float seed1, float seed2, PixelOut &out, RayStats *rs) {
   CastRes res;
   res.value = res.pointer = res.iter = res.depth = 0u;  // uninitialised upstream; zero by contract
   res.t = 2.0f;                                          // :437
@@ -285,7 +298,7 @@ __device__ __forceinline__ void trace_pixel(const SceneView &sc, const FramePara
     const float is3 = fdiv(1.0f, fsqrt(3.0f));
     const vec3 sun_dir = mk3(is3, is3, is3);  // :546
     for (int i = 0; i < f.casts; i++) {
-      const bool intersect = cast_ray<FAST>(sc, origin, dir, f.maxDepth, i != 0, f.coneDepth, res, loops);
+      const bool intersect = cast_ray<FAST, STATS>(sc, origin, dir, f.maxDepth, i != 0, f.coneDepth, res, loops, rs);
       if (i == 0) {
         out.iter = loops;
         out.hit_id = intersect ? res.pointer : kNoHit;
@@ -340,7 +353,7 @@ __device__ __forceinline__ void trace_pixel(const SceneView &sc, const FramePara
   }
 
   if (mode == 1 || mode == 2 || mode == 3) {
-    const bool hit = cast_ray<FAST>(sc, origin, dir, f.maxDepth, false, f.coneDepth, res, loops);
+    const bool hit = cast_ray<FAST, STATS>(sc, origin, dir, f.maxDepth, false, f.coneDepth, res, loops, rs);
     out.iter = loops;
     out.hit_id = hit ? res.pointer : kNoHit;
     out.primary_t = hit ? res.t : 0.0f;
@@ -378,7 +391,7 @@ __device__ __forceinline__ void trace_pixel(const SceneView &sc, const FramePara
     matcolor.y = fadd(fmul(lambdag, matcolor.y), fmul(fsub(1.0f, lambdag), 1.0f));
     matcolor.z = fadd(fmul(lambdab, matcolor.z), fmul(fsub(1.0f, lambdab), 1.0f));
     const vec3 so = res.voxelPos;
-    const bool shit = cast_ray<FAST>(sc, so, sun2, f.maxDepth, false, f.coneDepth, res, loops);  // :607
+    const bool shit = cast_ray<FAST, STATS>(sc, so, sun2, f.maxDepth, false, f.coneDepth, res, loops, rs);  // :607
     if (shit && res.t > fmul(res.scale, 1.73205080757f)) {
       matcolor = mk3(fsub(matcolor.x, 0.2f), fsub(matcolor.y, 0.2f), fsub(matcolor.z, 0.2f));
     } else if (res.iter > 260u) {  // :616-619
@@ -398,9 +411,9 @@ SVO_DI unsigned char quant8(float c) {  // imageStore to rgba8 (:726), DESIGN.md
 }
 
 // main (svotrace.comp:649-729) for pixel (x, y)
-template <bool FAST, bool AUX>
+template <bool FAST, bool AUX, bool STATS = false>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
-                                            int x, int y) {
+                                            int x, int y, RayStats *rs = nullptr) {
   float beamDist = 0.0f;
   if (f.useBeam && pl.beam) beamDist = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));  // :656-658
   const float fx = fdiv(fadd((float)x, 0.5f), (float)W);  // :662
@@ -416,8 +429,8 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
   o.hit_id = kNoHit;
   o.iter = 0;
   o.primary_t = 0.0f;
-  trace_pixel<FAST>(sc, f, beamDist, mk3(f.camPos[0], f.camPos[1], f.camPos[2]), dir, (float)x, (float)y,
-                    (float)f.frameNumber, o);
+  trace_pixel<FAST, STATS>(sc, f, beamDist, mk3(f.camPos[0], f.camPos[1], f.camPos[2]), dir, (float)x, (float)y,
+                           (float)f.frameNumber, o, rs);
   if (x < 10 && y < 10)  // :696-700
     o.color = sc.first_word_zero ? mk3(1.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
   const size_t p = (size_t)y * (size_t)W + (size_t)x;

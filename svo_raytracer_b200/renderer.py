@@ -202,6 +202,18 @@ class SvoContext:
         self._check(self._lib.svo_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def render_stats(self, frame: Frame) -> dict:
+        """Instrumented render: the oracle's counters for this frame (see svo_render_stats)."""
+        cnt = (C.c_uint64 * 3)()
+        self._check(self._lib.svo_render_stats(self._h, C.byref(frame), C.byref(cnt)))
+        return {"casts": int(cnt[0]), "iters": int(cnt[1]), "record_bytes": int(cnt[2])}
+
+    def gather_probe(self, working_set_bytes: int, loads_per_thread: int = 256) -> float:
+        """Random 32-byte-sector gather rate (sectors/s) over a working set: the gather roofline."""
+        v = C.c_double()
+        self._check(self._lib.svo_gather_probe(self._h, int(working_set_bytes), int(loads_per_thread), C.byref(v)))
+        return float(v.value)
+
     def math_probe(self, fn: int, x: np.ndarray, y: Optional[np.ndarray] = None) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = None if y is None else np.ascontiguousarray(y, dtype=np.float32)
