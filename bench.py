@@ -281,7 +281,7 @@ def main():
     except svo.SvoError as e:
         gather = {"error": str(e)}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "k_render_tile", "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src, "kernel": "k_render_persistent" if a.kernel == 1 else "k_render_tile", "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms, "gather": gather}
 
     cpu = None

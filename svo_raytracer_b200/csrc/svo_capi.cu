@@ -48,6 +48,10 @@ struct svo_ctx {
   uint64_t cast_cap = 0;
   // options
   int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 0;
+  unsigned int *d_tile_counter = nullptr;
+  WaveWorkspace ws{};  // wavefront variant, allocated on first use
+  void *ws_block = nullptr;
+  int ctas_per_sm = 8;
   uint64_t launches = 0;
   std::string err;
 };
@@ -96,6 +100,25 @@ int ensure_aux(svo_ctx *c) {
   return SVO_OK;
 }
 
+// one allocation carved into the wavefront planes
+int ensure_wavefront(svo_ctx *c) {
+  if (c->ws_block) return SVO_OK;
+  const uint64_t slots = (uint64_t)((c->W + 7) / 8) * (uint64_t)((c->H + 3) / 4) * 32u;
+  const uint64_t planes = 2 * 2 + 2 + 2 * 6;  // ray A/B x2 queues, hit A/B, state 6 x2 queues
+  const uint64_t bytes = planes * slots * sizeof(uint4) + 4096;
+  SVO_CUDA(c, cudaMalloc(&c->ws_block, bytes));
+  uint4 *p = (uint4 *)c->ws_block;
+  auto take = [&]() { uint4 *r = p; p += slots; return r; };
+  for (int q = 0; q < 2; q++) { c->ws.rayA[q] = take(); c->ws.rayB[q] = take(); }
+  c->ws.hitA = take();
+  c->ws.hitB = take();
+  for (int q = 0; q < 2; q++)
+    for (int k = 0; k < 6; k++) c->ws.state[q][k] = take();
+  c->ws.counters = (unsigned *)p;
+  c->ws.slots = slots;
+  return SVO_OK;
+}
+
 SceneView scene_view(const svo_ctx *c) {
   SceneView v;
   v.desc = c->d_desc;
@@ -112,6 +135,8 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.aux = c->opt_aux != 0;
   l.kernel = c->opt_kernel;
   l.sm_count = c->sm_count;
+  l.ctas_per_sm = c->ctas_per_sm;
+  l.tile_counter = c->d_tile_counter;
   return l;
 }
 Planes planes_of(const svo_ctx *c) {
@@ -230,6 +255,7 @@ int svo_create(svo_ctx **out, int device, int width, int height) {
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
     c->stream = c->own_stream;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
+    if ((e = cudaMalloc((void **)&c->d_tile_counter, 64)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(counter)"); break; }
     for (int p = SVO_PLANE_COLOR_RGBA8; p <= SVO_PLANE_BEAM; p++) {
       size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
       if ((e = cudaMalloc(&c->own[p], bytes ? bytes : 16)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(plane)"); break; }
@@ -255,6 +281,8 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_refbase) cudaFree(c->d_refbase);
   if (c->d_rays) cudaFree(c->d_rays);
   if (c->d_hits) cudaFree(c->d_hits);
+  if (c->d_tile_counter) cudaFree(c->d_tile_counter);
+  if (c->ws_block) cudaFree(c->ws_block);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -363,6 +391,12 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
   if (c->opt_aux && (rc = ensure_aux(c)) != SVO_OK) return rc;
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
+  if (c->opt_kernel == 2) {
+    if ((rc = ensure_wavefront(c)) != SVO_OK) return rc;
+    SVO_CUDA(c, launch_render_wavefront(launch_cfg(c), scene_view(c), fp, planes_of(c), c->W, c->H, y0, y1, c->ws, c->stream));
+    c->launches += (uint64_t)wavefront_launches(fp);
+    return SVO_OK;
+  }
   SVO_CUDA(c, launch_render(launch_cfg(c), scene_view(c), fp, planes_of(c), c->W, c->H, y0, y1, c->stream));
   c->launches++;
   return SVO_OK;

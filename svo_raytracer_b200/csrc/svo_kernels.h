@@ -35,8 +35,25 @@ struct LaunchCfg {
   bool aux;      // also write hit_id / iter / primary_t / radiance
   int kernel;    // variant selector (SVO_OPT_KERNEL)
   int sm_count;
+  int ctas_per_sm;             // persistent grid = sm_count * ctas_per_sm
+  unsigned int *tile_counter;  // device word: the persistent kernel's tile queue head
 };
 
+constexpr int kWaveMaxStages = 64;  // casts per pixel the wavefront path supports (svo_frame.casts <= 64)
+
+// Device workspace of the wavefront path (variant 2): two ray queues, one hit-state buffer,
+// two pixel-state queues (all SoA uint4 planes of `slots` entries) and the stage counters.
+struct WaveWorkspace {
+  uint4 *rayA[2], *rayB[2];
+  uint4 *hitA, *hitB;
+  uint4 *state[2][6];
+  unsigned *counters;  // 2 * (kWaveMaxStages + 1) words
+  uint64_t slots;
+};
+
+cudaError_t launch_render_wavefront(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
+                                    int y0, int y1, const WaveWorkspace &ws, cudaStream_t stream);
+int wavefront_launches(const FrameParams &f);
 cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                           int y0, int y1, cudaStream_t stream);
 cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1,

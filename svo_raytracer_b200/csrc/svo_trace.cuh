@@ -18,6 +18,15 @@
 //    produce value / packed normal; the hit id is the reference's byte offset
 //    (res.pointer), recomputed from refbase[parent] + a popcount prefix of the
 //    type codes.
+//  * The traversal is a resumable state machine (Trav::setup / step / finish)
+//    and so is the per-pixel shading (pixel_begin / pixel_after_cast /
+//    pixel_store): the tile kernel runs them back to back, the persistent
+//    kernel interleaves pixels so that a lane whose ray has finished is
+//    refilled instead of idling until the slowest ray of its warp is done.
+//  * The cube position is kept as the raw IEEE bit pattern of the reference's
+//    `pos` floats: inside [1,2) adding/subtracting scale_exp2 IS setting /
+//    subtracting bit `scale` of the mantissa, so PUSH/ADVANCE/POP are integer
+//    ops and the POP test is "did the subtraction borrow above bit `scale`".
 //  * The control flow (iteration count, PUSH/ADVANCE/POP order, the 1500
 //    iteration cap, the sticky cone LOD cut, every quirk listed in DESIGN.md)
 //    is reproduced exactly; Ops<false> rounds every operation separately
@@ -62,6 +71,16 @@ struct CastRes {
   int dbg_init;  // ... except the (0.3,0.3,0.6) set on entry (:213), kept by the iteration-cap exit
 };
 
+SVO_DI void cast_res_clear(CastRes &r) {  // uninitialised upstream; zero by contract
+  r.value = r.pointer = r.iter = r.depth = 0u;
+  r.t = 0.0f;
+  r.scale = 0.0f;
+  r.normal = mk3(0.0f, 0.0f, 0.0f);
+  r.voxelPos = mk3(0.0f, 0.0f, 0.0f);
+  r.dbg = 0.0f;
+  r.dbg_init = 0;
+}
+
 SVO_DI uint32_t raw_byte(const SceneView &sc, uint32_t p) {  // getByte (:75-79); out of range reads 0
   return ((uint64_t)p < sc.nbytes) ? (uint32_t)__ldg(sc.raw + p) : 0u;
 }
@@ -80,154 +99,41 @@ SVO_DI uint32_t child_offset(uint32_t codes, uint32_t c) {
 
 SVO_DI float sign_glsl(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
-// intersectOctree (svotrace.comp:211-432).  Returns hit; `loops` = iterations run.
-struct RayStats {  // per-thread counters of the instrumented build (SVO_OPT_STATS)
+struct RayStats {  // per-thread counters of the instrumented build (svo_render_stats)
   uint32_t casts, iters, record_bytes;
 };
 
-template <bool FAST, bool STATS = false>
-__device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, vec3 d, int maxDepth,
-                                         const bool coneTrace, const int coneDepth, CastRes &res,
-                                         uint32_t &loops, RayStats *rs = nullptr) {
-  typedef Ops<FAST> M;
-  const float kEps = 3.552713678800501e-15f;  // :31
-  res.dbg_init = 1;                            // :213
+enum { TRAV_CONTINUE = 0, TRAV_HIT = 1, TRAV_MISS = 2 };
 
-  if (fabsf(d.x) < kEps) d.x = fmul(kEps, sign_glsl(d.x));  // :226-228
-  if (fabsf(d.y) < kEps) d.y = fmul(kEps, sign_glsl(d.y));
-  if (fabsf(d.z) < kEps) d.z = fmul(kEps, sign_glsl(d.z));
+// State of one cast when its loop ends: enough to run the code after the loop.
+struct HitState {
+  uint32_t pidx;  // descriptor index of the parent of the hit child
+  uint32_t meta;  // status [0:2) | child_shift [2:5) | octant_mask [5:8) | scale [8:13)
+  uint32_t ipx, ipy, ipz;
+  float t_min;
+  uint32_t iter;
+};
 
-  const float tx_coef = fdiv(1.0f, -fabsf(d.x));  // :230-232
-  const float ty_coef = fdiv(1.0f, -fabsf(d.y));
-  const float tz_coef = fdiv(1.0f, -fabsf(d.z));
-  float tx_bias = M::mul(tx_coef, o.x);  // :234-236
-  float ty_bias = M::mul(ty_coef, o.y);
-  float tz_bias = M::mul(tz_coef, o.z);
-
-  uint32_t octant_mask = 0;  // :238-241
-  if (d.x > 0.0f) { octant_mask ^= 1u; tx_bias = M::msub(3.0f, tx_coef, tx_bias); }
-  if (d.y > 0.0f) { octant_mask ^= 2u; ty_bias = M::msub(3.0f, ty_coef, ty_bias); }
-  if (d.z > 0.0f) { octant_mask ^= 4u; tz_bias = M::msub(3.0f, tz_coef, tz_bias); }
-
-  float t_min = fmaxf(fmaxf(M::msub(2.0f, tx_coef, tx_bias), M::msub(2.0f, ty_coef, ty_bias)),
-                      M::msub(2.0f, tz_coef, tz_bias));                                        // :243
-  float t_max = fminf(fminf(M::sub(tx_coef, tx_bias), M::sub(ty_coef, ty_bias)), M::sub(tz_coef, tz_bias));  // :244
-  t_min = fmaxf(t_min, 0.0f);  // :245
-  float h = t_max;             // :247
-
-  uint32_t idx = 0;
-  float px = 1.0f, py = 1.0f, pz = 1.0f;
-  int scale = kMaxScale - 1;
-  float scale_exp2 = 0.5f;
-  if (M::msub(1.5f, tx_coef, tx_bias) > t_min) { idx ^= 1u; px = 1.5f; }  // :255-257
-  if (M::msub(1.5f, ty_coef, ty_bias) > t_min) { idx ^= 2u; py = 1.5f; }
-  if (M::msub(1.5f, tz_coef, tz_bias) > t_min) { idx ^= 4u; pz = 1.5f; }
-
-  uint32_t pidx = 0;                 // parent = root (:222)
-  uint2 pd = __ldg(sc.desc);         // its descriptor
-  uint32_t stk_idx[kMaxScale + 1];   // octstack (:199-202): parent index + t_max per scale
-  float stk_tmax[kMaxScale + 1];
-  uint32_t iter = 0;
-  uint32_t child_shift = 0;
-  bool hit = false;
-
-  while (scale < kMaxScale) {  // :262
-    iter++;
-    if (iter > (uint32_t)kMaxIterations) break;          // :264-266 (miss, debugColor stays at its entry value)
-    if (t_min > 0.05f && coneTrace) maxDepth = coneDepth;  // :275-277
-
-    const float tx_corner = M::msub(px, tx_coef, tx_bias);  // :280-283
-    const float ty_corner = M::msub(py, ty_coef, ty_bias);
-    const float tz_corner = M::msub(pz, tz_coef, tz_bias);
-    const float tc_max = fminf(fminf(tx_corner, ty_corner), tz_corner);
-
-    child_shift = idx ^ octant_mask;  // :286
-    if (STATS) {  // size of the child record the reference fetches here (extractChild :294)
-      const uint32_t code = (pd.y >> (2u * child_shift)) & 3u;
-      rs->record_bytes += code == 1u ? 3u : (code == 3u ? 1u : 7u);
-    }
-    // child.value != 0 (:295) is bit 16+child of the parent's descriptor
-    if (((pd.y >> (16u + child_shift)) & 1u) != 0u && t_min <= t_max) {
-      if (kMaxScale - scale == maxDepth) { hit = true; break; }  // :300-302
-      const float tv_max = fminf(t_max, tc_max);                 // :304
-      const float half = M::mul(scale_exp2, 0.5f);
-      const float tx_center = M::madd(half, tx_coef, tx_corner);  // :306-308
-      const float ty_center = M::madd(half, ty_coef, ty_corner);
-      const float tz_center = M::madd(half, tz_coef, tz_corner);
-      if (t_min <= tv_max) {  // :310
-        const uint32_t dmask = pd.y >> 24;
-        if (((dmask >> child_shift) & 1u) == 0u) { hit = true; break; }  // child.cp == 0 (:311-313)
-        if (tc_max < h) {  // PUSH :316-319
-          stk_idx[scale] = pidx;
-          stk_tmax[scale] = t_max;
-        }
-        h = tc_max;
-        pidx = pd.x + __popc(dmask & ((1u << child_shift) - 1u));  // parent = child (:322)
-        pd = __ldg(sc.desc + pidx);
-        idx = 0u;
-        --scale;
-        scale_exp2 = half;
-        if (tx_center > t_min) { idx ^= 1u; px = fadd(px, scale_exp2); }  // :328-330 (exact adds)
-        if (ty_center > t_min) { idx ^= 2u; py = fadd(py, scale_exp2); }
-        if (tz_center > t_min) { idx ^= 4u; pz = fadd(pz, scale_exp2); }
-        t_max = tv_max;
-        continue;
-      }
-    }
-    // ADVANCE :337-344
-    uint32_t step_mask = 0u;
-    if (tx_corner <= tc_max) { step_mask ^= 1u; px = fsub(px, scale_exp2); }
-    if (ty_corner <= tc_max) { step_mask ^= 2u; py = fsub(py, scale_exp2); }
-    if (tz_corner <= tc_max) { step_mask ^= 4u; pz = fsub(pz, scale_exp2); }
-    if (step_mask == 0u) {
-      // All three corners are NaN (NaN direction from a zero or 555 normal):
-      // nothing changes any more and the reference spins to the cap (:264).
-      iter = (uint32_t)kMaxIterations + 1u;
-      break;
-    }
-    t_min = tc_max;
-    idx ^= step_mask;
-
-    if ((idx & step_mask) != 0u) {  // POP :347-368
-      uint32_t differing_bits = 0;
-      if (step_mask & 1u) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));
-      if (step_mask & 2u) differing_bits |= __float_as_uint(py) ^ __float_as_uint(fadd(py, scale_exp2));
-      if (step_mask & 4u) differing_bits |= __float_as_uint(pz) ^ __float_as_uint(fadd(pz, scale_exp2));
-      scale = 31 - __clz(differing_bits);  // findMSB
-      if (scale >= kMaxScale) break;       // left the cube: the loop condition fails next (:262)
-      scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);
-      pidx = stk_idx[scale];
-      t_max = stk_tmax[scale];
-      pd = __ldg(sc.desc + pidx);
-      const uint32_t shx = __float_as_uint(px) >> scale;
-      const uint32_t shy = __float_as_uint(py) >> scale;
-      const uint32_t shz = __float_as_uint(pz) >> scale;
-      px = __uint_as_float(shx << scale);
-      py = __uint_as_float(shy << scale);
-      pz = __uint_as_float(shz << scale);
-      idx = (shx & 1u) | ((shy & 1u) << 1) | ((shz & 1u) << 2);
-      h = 0.0f;
-    }
-  }
+// after the loop (svotrace.comp:371-431).  Returns hit; `loops` = iterations run.
+SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uint32_t &loops) {
+  const uint32_t iter = hs.iter;
   loops = iter;
-  if (STATS) {
-    rs->casts += 1u;
-    rs->record_bytes += 7u;  // extractNode(0) :222
-    rs->iters += iter > (uint32_t)kMaxIterations ? (uint32_t)kMaxIterations : iter;
-  }
-
-  if (!hit) {
+  if ((hs.meta & 3u) != (uint32_t)TRAV_HIT) {
     if (iter <= (uint32_t)kMaxIterations) {  // :371-377
       res.dbg = fmul(0.01f, (float)iter);
       res.dbg_init = 0;
+    } else {
+      res.dbg_init = 1;  // :213 survives the cap exit
     }
     return false;
   }
-
   // hit: extractChild again (:381) on the ORIGINAL bytes
-  const uint32_t codes = pd.y & 0xFFFFu;
-  const uint32_t ptr = __ldg(sc.refbase + pidx) + child_offset(codes, child_shift);
-  const uint32_t code = (codes >> (2u * child_shift)) & 3u;
+  const uint32_t cs = (hs.meta >> 2) & 7u, oct = (hs.meta >> 5) & 7u;
+  const int scale = (int)((hs.meta >> 8) & 31u);
+  const float scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);
+  const uint32_t codes = __ldg(sc.desc + hs.pidx).y & 0xFFFFu;
+  const uint32_t ptr = __ldg(sc.refbase + hs.pidx) + child_offset(codes, cs);
+  const uint32_t code = (codes >> (2u * cs)) & 3u;
   const uint32_t value = raw_byte(sc, ptr);
   uint32_t raw16 = 0;  // Node.leafMask of the hit record
   if (code == 1u) raw16 = raw_byte(sc, ptr + 1u) | (raw_byte(sc, ptr + 2u) << 8);        // extractLeaf :103-108
@@ -241,16 +147,16 @@ __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, vec3
     norm = normalize3(mk3(nx, ny, nz));
   }
   res.pointer = ptr;
-  res.t = t_min;  // :403-408
+  res.t = hs.t_min;  // :403-408
   res.value = value;
   res.iter = iter;
   res.normal = norm;
   res.scale = scale_exp2;
   res.depth = (uint32_t)(kMaxScale - scale);
-  float vx = px, vy = py, vz = pz;  // :413-421
-  if (d.x > 0.0f) vx = fsub(fsub(3.0f, vx), scale_exp2);
-  if (d.y > 0.0f) vy = fsub(fsub(3.0f, vy), scale_exp2);
-  if (d.z > 0.0f) vz = fsub(fsub(3.0f, vz), scale_exp2);
+  float vx = __uint_as_float(hs.ipx), vy = __uint_as_float(hs.ipy), vz = __uint_as_float(hs.ipz);  // :413-421
+  if (oct & 1u) vx = fsub(fsub(3.0f, vx), scale_exp2);  // dir.x > 0
+  if (oct & 2u) vy = fsub(fsub(3.0f, vy), scale_exp2);
+  if (oct & 4u) vz = fsub(fsub(3.0f, vz), scale_exp2);
   res.voxelPos.x = fadd(vx, fmul(fmul(fmul(norm.x, scale_exp2), 2.0f), 1.74f));
   res.voxelPos.y = fadd(vy, fmul(fmul(fmul(norm.y, scale_exp2), 2.0f), 1.74f));
   res.voxelPos.z = fadd(vz, fmul(fmul(fmul(norm.z, scale_exp2), 2.0f), 1.74f));
@@ -259,149 +165,378 @@ __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, vec3
   return true;  // :431 (scale < MAX_SCALE && t_min <= t_max both hold at either break)
 }
 
+// One intersectOctree call (svotrace.comp:211-432) as a resumable state machine.
+template <bool FAST, bool STATS = false>
+struct Trav {
+  typedef Ops<FAST> M;
+  float cx, cy, cz;         // t*_coef
+  float bx, by, bz;         // t*_bias
+  float t_min, t_max, h;
+  float px, py, pz;         // pos
+  float scale_exp2;
+  int scale;
+  int stop_scale;           // MAX_SCALE - maxDepth
+  int cone_stop;            // what stop_scale becomes once t_min > 0.05 (== stop_scale when !coneTrace)
+  uint32_t idx, oct, pidx, iter;
+  uint2 pd;
+
+  __device__ __forceinline__ void setup(const SceneView &sc, const vec3 o, vec3 d, int maxDepth, bool coneTrace,
+                                        int coneDepth, RayStats *rs) {
+    const float kEps = 3.552713678800501e-15f;                // :31
+    if (fabsf(d.x) < kEps) d.x = fmul(kEps, sign_glsl(d.x));  // :226-228
+    if (fabsf(d.y) < kEps) d.y = fmul(kEps, sign_glsl(d.y));
+    if (fabsf(d.z) < kEps) d.z = fmul(kEps, sign_glsl(d.z));
+    cx = fdiv(1.0f, -fabsf(d.x));  // :230-232
+    cy = fdiv(1.0f, -fabsf(d.y));
+    cz = fdiv(1.0f, -fabsf(d.z));
+    bx = M::mul(cx, o.x);  // :234-236
+    by = M::mul(cy, o.y);
+    bz = M::mul(cz, o.z);
+    oct = 0;  // :238-241
+    if (d.x > 0.0f) { oct ^= 1u; bx = M::msub(3.0f, cx, bx); }
+    if (d.y > 0.0f) { oct ^= 2u; by = M::msub(3.0f, cy, by); }
+    if (d.z > 0.0f) { oct ^= 4u; bz = M::msub(3.0f, cz, bz); }
+    t_min = fmaxf(fmaxf(M::msub(2.0f, cx, bx), M::msub(2.0f, cy, by)), M::msub(2.0f, cz, bz));  // :243
+    t_max = fminf(fminf(M::sub(cx, bx), M::sub(cy, by)), M::sub(cz, bz));                       // :244
+    t_min = fmaxf(t_min, 0.0f);                                                                  // :245
+    h = t_max;                                                                                   // :247
+    idx = 0;
+    px = py = pz = 1.0f;
+    scale = kMaxScale - 1;
+    scale_exp2 = 0.5f;
+    if (M::msub(1.5f, cx, bx) > t_min) { idx ^= 1u; px = 1.5f; }  // :255-257
+    if (M::msub(1.5f, cy, by) > t_min) { idx ^= 2u; py = 1.5f; }
+    if (M::msub(1.5f, cz, bz) > t_min) { idx ^= 4u; pz = 1.5f; }
+    pidx = 0;               // parent = root (:222)
+    pd = __ldg(sc.desc);
+    iter = 0;
+    stop_scale = kMaxScale - maxDepth;
+    cone_stop = coneTrace ? kMaxScale - coneDepth : stop_scale;
+    // the sticky LOD cut (:275-277) is tested at the top of every iteration upstream; t_min only changes here
+    // and in ADVANCE, so testing it at those two places is the same thing
+    if (t_min > 0.05f) stop_scale = cone_stop;
+    if (STATS) { rs->casts += 1u; rs->record_bytes += 7u; }  // extractNode(0) :222
+  }
+
+  // The body of one loop iteration (:262-369), shared by run() and step().  `EXIT(status)` leaves the loop,
+  // `NEXT` starts the next iteration.  The iteration cap (:264-266) is enforced where it is cheap -- on the
+  // ADVANCE path, plus once after the loop (cap_fixup) -- instead of on every iteration: at most 23 PUSHes can
+  // run between two ADVANCEs, and a cast that ends with iter > 1500 is exactly a cast the reference capped.
+#define SVO_TRAV_BODY(EXIT, NEXT)                                                                                    \
+  iter++;                                                                                                            \
+  if (STATS && iter <= (uint32_t)kMaxIterations) rs->iters += 1u;                                                    \
+  const float tx_corner = M::msub(px, cx, bx); /* :280-283 */                                                        \
+  const float ty_corner = M::msub(py, cy, by);                                                                       \
+  const float tz_corner = M::msub(pz, cz, bz);                                                                       \
+  const float tc_max = fminf(fminf(tx_corner, ty_corner), tz_corner);                                                \
+  const uint32_t cs = idx ^ oct; /* child_shift :286 */                                                              \
+  if (STATS && iter <= (uint32_t)kMaxIterations) { /* size of the child record fetched here (extractChild :294) */  \
+    const uint32_t code = (pd.y >> (2u * cs)) & 3u;                                                                  \
+    rs->record_bytes += code == 1u ? 3u : (code == 3u ? 1u : 7u);                                                    \
+  }                                                                                                                  \
+  const uint32_t bit16 = 0x10000u << cs;                                                                             \
+  /* child.value != 0 (:295) is bit 16+child of the parent's descriptor */                                           \
+  if ((pd.y & bit16) != 0u && t_min <= t_max) {                                                                      \
+    if (scale == stop_scale) { EXIT(TRAV_HIT); } /* MAX_SCALE - scale == maxDepth (:300-302) */                      \
+    const float tv_max = fminf(t_max, tc_max);   /* :304 */                                                          \
+    if (t_min <= tv_max) {                       /* :310 */                                                          \
+      const uint32_t bit24 = bit16 << 8;                                                                             \
+      if ((pd.y & bit24) == 0u) { EXIT(TRAV_HIT); } /* child.cp == 0 (:311-313) */                                   \
+      if (tc_max < h) { /* PUSH :316-319 */                                                                          \
+        stk_idx[scale] = pidx;                                                                                       \
+        stk_tmax[scale] = t_max;                                                                                     \
+      }                                                                                                              \
+      h = tc_max;                                                                                                    \
+      pidx = pd.x + __popc(pd.y & (bit24 - 0x01000000u)); /* descriptors of the interior siblings below */           \
+      pd = __ldg(sc.desc + pidx);                          /* parent = child (:322) */                               \
+      const float half = M::mul(scale_exp2, 0.5f);                                                                   \
+      const float tx_center = M::madd(half, cx, tx_corner); /* :306-308 */                                           \
+      const float ty_center = M::madd(half, cy, ty_corner);                                                          \
+      const float tz_center = M::madd(half, cz, tz_corner);                                                          \
+      --scale;                                                                                                       \
+      scale_exp2 = half;                                                                                             \
+      idx = 0u;                                                                                                      \
+      if (tx_center > t_min) { idx ^= 1u; px = fadd(px, scale_exp2); } /* :328-330 (exact adds) */                   \
+      if (ty_center > t_min) { idx ^= 2u; py = fadd(py, scale_exp2); }                                               \
+      if (tz_center > t_min) { idx ^= 4u; pz = fadd(pz, scale_exp2); }                                               \
+      t_max = tv_max;                                                                                                \
+      NEXT;                                                                                                          \
+    }                                                                                                                \
+  }                                                                                                                  \
+  /* ADVANCE :337-344 */                                                                                             \
+  uint32_t step_mask = 0u;                                                                                           \
+  if (tx_corner <= tc_max) { step_mask ^= 1u; px = fsub(px, scale_exp2); }                                           \
+  if (ty_corner <= tc_max) { step_mask ^= 2u; py = fsub(py, scale_exp2); }                                           \
+  if (tz_corner <= tc_max) { step_mask ^= 4u; pz = fsub(pz, scale_exp2); }                                           \
+  if (step_mask == 0u) {                                                                                             \
+    /* all three corners are NaN (NaN direction from a zero or 555 normal): nothing changes any more and the   */    \
+    /* reference spins to the cap (:264)                                                                        */    \
+    if (STATS && iter <= (uint32_t)kMaxIterations) {                                                                 \
+      const uint32_t code = (pd.y >> (2u * cs)) & 3u, left = (uint32_t)kMaxIterations - iter;                        \
+      rs->iters += left;                                                                                             \
+      rs->record_bytes += left * (code == 1u ? 3u : (code == 3u ? 1u : 7u));                                         \
+    }                                                                                                                \
+    iter = (uint32_t)kMaxIterations + 1u;                                                                            \
+    EXIT(TRAV_MISS);                                                                                                 \
+  }                                                                                                                  \
+  t_min = tc_max;                                                                                                    \
+  if (t_min > 0.05f) stop_scale = cone_stop; /* :275-277 */                                                          \
+  idx ^= step_mask;                                                                                                  \
+  if ((idx & step_mask) != 0u) { /* POP :347-368 */                                                                  \
+    uint32_t differing_bits = 0;                                                                                     \
+    if (step_mask & 1u) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));               \
+    if (step_mask & 2u) differing_bits |= __float_as_uint(py) ^ __float_as_uint(fadd(py, scale_exp2));               \
+    if (step_mask & 4u) differing_bits |= __float_as_uint(pz) ^ __float_as_uint(fadd(pz, scale_exp2));               \
+    scale = 31 - __clz(differing_bits); /* findMSB */                                                                \
+    if (scale >= kMaxScale) { EXIT(TRAV_MISS); } /* left the cube: the loop condition fails (:262) */                \
+    scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);                                         \
+    pidx = stk_idx[scale];                                                                                           \
+    t_max = stk_tmax[scale];                                                                                         \
+    pd = __ldg(sc.desc + pidx);                                                                                      \
+    const uint32_t shx = __float_as_uint(px) >> scale;                                                               \
+    const uint32_t shy = __float_as_uint(py) >> scale;                                                               \
+    const uint32_t shz = __float_as_uint(pz) >> scale;                                                               \
+    px = __uint_as_float(shx << scale);                                                                              \
+    py = __uint_as_float(shy << scale);                                                                              \
+    pz = __uint_as_float(shz << scale);                                                                              \
+    idx = (shx & 1u) | ((shy & 1u) << 1) | ((shz & 1u) << 2);                                                        \
+    h = 0.0f;                                                                                                        \
+  }                                                                                                                  \
+  if (iter >= (uint32_t)kMaxIterations) { /* the next iteration is number 1501: the cap (:264-266) */                \
+    iter = (uint32_t)kMaxIterations + 1u;                                                                            \
+    EXIT(TRAV_MISS);                                                                                                 \
+  }
+
+  // A hit found after iteration 1500 (only possible through a run of PUSHes right after the last ADVANCE
+  // check) is a cast the reference abandoned at iteration 1501 (:264-266).
+  __device__ __forceinline__ int cap_fixup(int status) {
+    if (iter > (uint32_t)kMaxIterations) {
+      iter = (uint32_t)kMaxIterations + 1u;
+      return TRAV_MISS;
+    }
+    return status;
+  }
+
+  // the whole loop (:262-369); returns TRAV_HIT or TRAV_MISS
+  __device__ __forceinline__ int run(const SceneView &sc, uint32_t *stk_idx, float *stk_tmax, RayStats *rs) {
+    int status;
+#define SVO_EXIT(s) { status = (s); break; }
+    for (;;) {
+      SVO_TRAV_BODY(SVO_EXIT, continue)
+    }
+#undef SVO_EXIT
+    return cap_fixup(status);
+  }
+
+  // one iteration; returns TRAV_CONTINUE until the cast is over
+  __device__ __forceinline__ int step(const SceneView &sc, uint32_t *stk_idx, float *stk_tmax, RayStats *rs) {
+#define SVO_EXIT(s) return cap_fixup(s)
+    SVO_TRAV_BODY(SVO_EXIT, return TRAV_CONTINUE)
+#undef SVO_EXIT
+    return TRAV_CONTINUE;
+  }
+
+  // what the code after the loop needs (:371-431), small enough to park in memory between kernels
+  __device__ __forceinline__ HitState export_hit(int status) const {
+    HitState hs;
+    hs.pidx = pidx;
+    hs.meta = (uint32_t)status | ((idx ^ oct) << 2) | (oct << 5) | ((uint32_t)scale << 8);
+    hs.ipx = __float_as_uint(px);
+    hs.ipy = __float_as_uint(py);
+    hs.ipz = __float_as_uint(pz);
+    hs.t_min = t_min;
+    hs.iter = iter;
+    return hs;
+  }
+  __device__ __forceinline__ bool finish(const SceneView &sc, int status, CastRes &res, uint32_t &loops) const {
+    return finish_hit(sc, export_hit(status), res, loops);
+  }
+};
+
+// intersectOctree run to completion.
+template <bool FAST, bool STATS = false>
+__device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
+                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr) {
+  uint32_t stk_idx[kMaxScale + 1];  // octstack (:199-202): parent index + t_max per scale
+  float stk_tmax[kMaxScale + 1];
+  Trav<FAST, STATS> T;
+  T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
+  return T.finish(sc, T.run(sc, stk_idx, stk_tmax, rs), res, loops);
+}
+
 SVO_DI void matcolor_table(uint32_t value, vec3 &mc) {  // :514-522, :578-586
   if (value == 1u) mc = mk3(0.84f, 0.86f, 0.78f);
   if (value == 2u) mc = mk3(0.57f, 0.5f, 0.31f);
   if (value == 3u) mc = mk3(0.37f, 0.43f, 0.27f);
 }
 
-struct PixelOut {
-  vec3 color;
-  float depth;
-  uint32_t hit_id, iter;
-  float primary_t;
-};
-
 SVO_DI vec3 sky(vec3 dir) {  // :449-450, :629-631
   return mk3(fsub(0.6725f, fmul(dir.y, 0.4f)), fsub(0.8784f, fmul(dir.y, 0.4f)), fsub(1.0f, fmul(dir.y, 0.25f)));
 }
 
-// trace (svotrace.comp:435-646)
-template <bool FAST, bool STATS>
-__device__ __forceinline__ void trace_pixel(const SceneView &sc, const FrameParams &f, float beamDist, vec3 origin,
-                                            vec3 dir, float seed0, float seed1, float seed2, PixelOut &out, RayStats *rs) {
-  CastRes res;
-  res.value = res.pointer = res.iter = res.depth = 0u;  // uninitialised upstream; zero by contract
-  res.t = 2.0f;                                          // :437
-  res.scale = 0.0f;
-  res.normal = mk3(0.0f, 0.0f, 0.0f);
-  res.voxelPos = mk3(0.0f, 0.0f, 0.0f);
-  res.dbg = 0.0f;
-  res.dbg_init = 0;
-  origin = mk3(fadd(origin.x, fmul(dir.x, beamDist)), fadd(origin.y, fmul(dir.y, beamDist)),
-               fadd(origin.z, fmul(dir.z, beamDist)));  // :438
+// Everything one shader invocation keeps between its intersectOctree calls
+// (main :649-729 + trace :435-646), so that it can be suspended at a cast.
+struct Pixel {
+  int x, y;
+  vec3 origin, dir;  // ray of the cast about to run / running
+  bool cone;         // its coneTrace argument
+  int cast_i;        // which cast of the pixel this is
+  vec3 acc;          // mode 0: accum_color;  mode 2: matcolor carried across the shadow cast
+  vec3 mask;         // mode 0
+  CastRes res;       // `res`, stale fields and all
+  vec3 color;        // finalcolor
+  float depth, beamDist;
+  uint32_t hit_id, iter;
+  float primary_t;
+};
+
+// main() up to the first cast.  Returns true if the pixel wants a cast (ray in P.origin/dir/cone).
+SVO_DI bool pixel_begin(const FrameParams &f, const Planes &pl, int W, int H, int x, int y, Pixel &P) {
+  P.x = x;
+  P.y = y;
+  P.beamDist = 0.0f;
+  if (f.useBeam && pl.beam) P.beamDist = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));  // :656-658
+  const float fx = fdiv(fadd((float)x, 0.5f), (float)W);  // :662
+  const float fy = fdiv(fadd((float)y, 0.5f), (float)H);
+  vec3 dir;  // :664
+  dir.x = mixf(mixf(f.l1[0], f.l2[0], fy), mixf(f.r1[0], f.r2[0], fy), fx);
+  dir.y = mixf(mixf(f.l1[1], f.l2[1], fy), mixf(f.r1[1], f.r2[1], fy), fx);
+  dir.z = mixf(mixf(f.l1[2], f.l2[2], fy), mixf(f.r1[2], f.r2[2], fy), fx);
+  dir = normalize3(dir);  // :675
+  P.dir = dir;
+  P.origin = mk3(fadd(f.camPos[0], fmul(dir.x, P.beamDist)), fadd(f.camPos[1], fmul(dir.y, P.beamDist)),
+                 fadd(f.camPos[2], fmul(dir.z, P.beamDist)));  // :438
+  P.color = mk3(0.0f, 0.0f, 0.0f);
+  P.depth = -1.0f;  // :672
+  P.hit_id = kNoHit;
+  P.iter = 0;
+  P.primary_t = 0.0f;
+  cast_res_clear(P.res);
+  P.res.t = 2.0f;  // :437
+  P.acc = mk3(0.0f, 0.0f, 0.0f);
+  P.mask = mk3(1.0f, 1.0f, 1.0f);
+  P.cone = false;
+  P.cast_i = 0;
   const int mode = f.renderMode;
-  uint32_t loops = 0;
+  if (mode == 0) return f.casts > 0;         // :443-444
+  if (mode >= 1 && mode <= 3) return true;   // :562, :573, :634
+  P.color = P.res.voxelPos;                  // mode 4 (:643-645): uninitialised upstream, zero here
+  return false;
+}
 
-  if (mode == 0) {  // :443-560
-    vec3 accum = mk3(0.0f, 0.0f, 0.0f), mask = mk3(1.0f, 1.0f, 1.0f);
-    const float is3 = fdiv(1.0f, fsqrt(3.0f));
-    const vec3 sun_dir = mk3(is3, is3, is3);  // :546
-    for (int i = 0; i < f.casts; i++) {
-      const bool intersect = cast_ray<FAST, STATS>(sc, origin, dir, f.maxDepth, i != 0, f.coneDepth, res, loops, rs);
-      if (i == 0) {
-        out.iter = loops;
-        out.hit_id = intersect ? res.pointer : kNoHit;
-        out.primary_t = intersect ? res.t : 0.0f;
-      }
-      if (!intersect && i == 0) {  // :448-452
-        const vec3 s = sky(dir);
-        accum = mk3(fadd(accum.x, s.x), fadd(accum.y, s.y), fadd(accum.z, s.z));
-        break;
-      }
-      const vec3 normal = res.normal;      // :476 (stale on a bounce miss, as upstream)
-      const vec3 hitpoint = res.voxelPos;  // :481
-      const float ra = det_rand(seed0, fmul(seed2, 0.1f));  // :486
-      const float rb = det_rand(seed1, fmul(seed2, 0.02f));
-      const float rnd = det_rand(fadd(seed0, ra), fadd(seed1, rb));
-      const float rand1 = fmul(fmul(2.0f, 3.14159265359f), rnd);  // :487
-      const vec3 w = normal;                                        // :494-497
-      const vec3 axis = fabsf(w.x) > 0.1f ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, 0.0f, 0.0f);
-      const vec3 u = normalize3(cross3(axis, w));
-      const vec3 v = cross3(w, u);
-      vec3 newdir;
-      if (f.mirrorValue != 0 && res.value == (uint32_t)f.mirrorValue) {  // :500-504 (commented out upstream)
-        const float dn = fmul(2.0f, dot3(dir, normal));
-        newdir = mk3(fsub(dir.x, fmul(dn, normal.x)), fsub(dir.y, fmul(dn, normal.y)), fsub(dir.z, fmul(dn, normal.z)));
-      } else {  // :506
-        const float c = det_cos(rand1), s = det_sin(rand1);
-        const float omr = fsub(1.0f, rnd);
-        newdir = normalize3(mk3(fadd(fadd(fmul(u.x, c), fmul(v.x, s)), fmul(w.x, omr)),
-                                fadd(fadd(fmul(u.y, c), fmul(v.y, s)), fmul(w.y, omr)),
-                                fadd(fadd(fmul(u.z, c), fmul(v.z, s)), fmul(w.z, omr))));
-      }
-      origin = hitpoint;  // :508-509
-      dir = newdir;
-      vec3 matcolor = mk3(fsub(hitpoint.x, 1.0f), fsub(hitpoint.y, 1.0f), fsub(hitpoint.z, 1.0f));  // :511
-      matcolor_table(res.value, matcolor);
-      if (intersect) {  // :531-535
-        out.depth = res.t;
-        const float dnn = dot3(newdir, normal);
-        accum = mk3(fadd(accum.x, fmul(mask.x, 0.0f)), fadd(accum.y, fmul(mask.y, 0.0f)), fadd(accum.z, fmul(mask.z, 0.0f)));
-        mask = mk3(fmul(fmul(mask.x, matcolor.x), dnn), fmul(fmul(mask.y, matcolor.y), dnn), fmul(fmul(mask.z, matcolor.z), dnn));
-      } else {  // :536-557
-        const float diff = det_acos(dot3(dir, sun_dir));
-        if (diff < 0.4f)
-          accum = mk3(fadd(accum.x, fmul(mask.x, 7.0f)), fadd(accum.y, fmul(mask.y, 7.0f)), fadd(accum.z, fmul(mask.z, 7.0f)));
-        accum = mk3(fadd(accum.x, fmul(mask.x, 1.0f)), fadd(accum.y, fmul(mask.y, 1.0f)), fadd(accum.z, fmul(mask.z, 1.0f)));
-        out.depth = 0.0f;
-        break;
-      }
-    }
-    out.color = accum;
-    return;
+// The code of trace() that follows cast number P.cast_i.  Returns true if another cast is wanted.
+SVO_DI bool pixel_after_cast(const FrameParams &f, Pixel &P, bool intersect, uint32_t loops) {
+  CastRes &res = P.res;
+  const int mode = f.renderMode;
+  if (P.cast_i == 0) {
+    P.iter = loops;
+    P.hit_id = intersect ? res.pointer : kNoHit;
+    P.primary_t = intersect ? res.t : 0.0f;
   }
-
-  if (mode == 1 || mode == 2 || mode == 3) {
-    const bool hit = cast_ray<FAST, STATS>(sc, origin, dir, f.maxDepth, false, f.coneDepth, res, loops, rs);
-    out.iter = loops;
-    out.hit_id = hit ? res.pointer : kNoHit;
-    out.primary_t = hit ? res.t : 0.0f;
-    if (mode == 1) {  // :561-571
-      out.depth = hit ? res.t : 0.0f;
-      out.color = res.dbg_init ? mk3(0.3f, 0.3f, 0.6f) : mk3(res.dbg, res.dbg, res.dbg);
-      return;
+  if (mode == 0) {  // loop body :445-558
+    const int i = P.cast_i;
+    if (!intersect && i == 0) {  // :448-452
+      const vec3 s = sky(P.dir);
+      P.color = mk3(fadd(P.acc.x, s.x), fadd(P.acc.y, s.y), fadd(P.acc.z, s.z));
+      return false;
     }
-    if (mode == 3) {  // :633-642
-      out.depth = hit ? res.t : 0.0f;
-      out.color = hit ? mk3(fadd(fmul(res.normal.x, 0.5f), 0.5f), fadd(fmul(res.normal.y, 0.5f), 0.5f),
-                            fadd(fmul(res.normal.z, 0.5f), 0.5f))
-                      : mk3(0.0f, 0.0f, 0.0f);
-      return;
+    const vec3 normal = res.normal;      // :476 (stale on a bounce miss, as upstream)
+    const vec3 hitpoint = res.voxelPos;  // :481
+    const float seed0 = (float)P.x, seed1 = (float)P.y, seed2 = (float)f.frameNumber;  // :677-681
+    const float ra = det_rand(seed0, fmul(seed2, 0.1f));  // :486
+    const float rb = det_rand(seed1, fmul(seed2, 0.02f));
+    const float rnd = det_rand(fadd(seed0, ra), fadd(seed1, rb));
+    const float rand1 = fmul(fmul(2.0f, 3.14159265359f), rnd);  // :487
+    const vec3 w = normal;                                        // :494-497
+    const vec3 axis = fabsf(w.x) > 0.1f ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, 0.0f, 0.0f);
+    const vec3 u = normalize3(cross3(axis, w));
+    const vec3 v = cross3(w, u);
+    vec3 newdir;
+    if (f.mirrorValue != 0 && res.value == (uint32_t)f.mirrorValue) {  // :500-504 (commented out upstream)
+      const float dn = fmul(2.0f, dot3(P.dir, normal));
+      newdir = mk3(fsub(P.dir.x, fmul(dn, normal.x)), fsub(P.dir.y, fmul(dn, normal.y)), fsub(P.dir.z, fmul(dn, normal.z)));
+    } else {  // :506
+      const float c = det_cos(rand1), s = det_sin(rand1);
+      const float omr = fsub(1.0f, rnd);
+      newdir = normalize3(mk3(fadd(fadd(fmul(u.x, c), fmul(v.x, s)), fmul(w.x, omr)),
+                              fadd(fadd(fmul(u.y, c), fmul(v.y, s)), fmul(w.y, omr)),
+                              fadd(fadd(fmul(u.z, c), fmul(v.z, s)), fmul(w.z, omr))));
     }
-    if (!hit) {  // :626-632
-      out.depth = 0.0f;
-      out.color = sky(dir);
-      return;
+    P.origin = hitpoint;  // :508-509
+    P.dir = newdir;
+    vec3 matcolor = mk3(fsub(hitpoint.x, 1.0f), fsub(hitpoint.y, 1.0f), fsub(hitpoint.z, 1.0f));  // :511
+    matcolor_table(res.value, matcolor);
+    if (intersect) {  // :531-535
+      P.depth = res.t;
+      const float dnn = dot3(newdir, normal);
+      P.acc = mk3(fadd(P.acc.x, fmul(P.mask.x, 0.0f)), fadd(P.acc.y, fmul(P.mask.y, 0.0f)), fadd(P.acc.z, fmul(P.mask.z, 0.0f)));
+      P.mask = mk3(fmul(fmul(P.mask.x, matcolor.x), dnn), fmul(fmul(P.mask.y, matcolor.y), dnn), fmul(fmul(P.mask.z, matcolor.z), dnn));
+    } else {  // :536-557
+      const float is3 = fdiv(1.0f, fsqrt(3.0f));
+      const float diff = det_acos(dot3(P.dir, mk3(is3, is3, is3)));  // :546-547
+      if (diff < 0.4f)
+        P.acc = mk3(fadd(P.acc.x, fmul(P.mask.x, 7.0f)), fadd(P.acc.y, fmul(P.mask.y, 7.0f)), fadd(P.acc.z, fmul(P.mask.z, 7.0f)));
+      P.acc = mk3(fadd(P.acc.x, fmul(P.mask.x, 1.0f)), fadd(P.acc.y, fmul(P.mask.y, 1.0f)), fadd(P.acc.z, fmul(P.mask.z, 1.0f)));
+      P.depth = 0.0f;
+      P.color = P.acc;
+      return false;
     }
-    out.depth = res.t;  // :573-625
+    P.color = P.acc;
+    P.cast_i = i + 1;
+    P.cone = true;  // :445-446
+    return P.cast_i < f.casts;
+  }
+  if (mode == 1) {  // :561-571
+    P.depth = intersect ? res.t : 0.0f;
+    P.color = res.dbg_init ? mk3(0.3f, 0.3f, 0.6f) : mk3(res.dbg, res.dbg, res.dbg);
+    return false;
+  }
+  if (mode == 3) {  // :633-642
+    P.depth = intersect ? res.t : 0.0f;
+    P.color = intersect ? mk3(fadd(fmul(res.normal.x, 0.5f), 0.5f), fadd(fmul(res.normal.y, 0.5f), 0.5f),
+                              fadd(fmul(res.normal.z, 0.5f), 0.5f))
+                        : mk3(0.0f, 0.0f, 0.0f);
+    return false;
+  }
+  // mode 2 :572-632
+  const float sd = fdiv(0.5f, fsqrt(0.75f));  // normalize(vec3(0.5)) :587
+  if (P.cast_i == 0) {
+    if (!intersect) {  // :626-632
+      P.depth = 0.0f;
+      P.color = sky(P.dir);
+      return false;
+    }
+    P.depth = res.t;  // :573-604
     vec3 matcolor = mk3(0.0f, 0.0f, 0.0f);
     matcolor_table(res.value, matcolor);
-    const float sd = fdiv(0.5f, fsqrt(0.75f));  // normalize(vec3(0.5)) :587
     const vec3 sun2 = mk3(sd, sd, sd);
     float ph;
     if (res.depth >= 10u) ph = fmul(dot3(res.normal, sun2), 0.1f);  // :588-593
     else ph = fmul(dot3(mk3(0.0f, 1.0f, 0.0f), sun2), 0.1f);
     matcolor = mk3(fadd(matcolor.x, ph), fadd(matcolor.y, ph), fadd(matcolor.z, ph));
-    const float base = fmul(-0.5f, fadd(res.t, beamDist));  // :595-598
+    const float base = fmul(-0.5f, fadd(res.t, P.beamDist));  // :595-598
     const float lambdag = det_exp(fmul(base, 2.0f));
     const float lambdab = det_exp(fmul(base, 4.0f));
     const float lambdar = det_exp(fmul(base, 1.0f));
     matcolor.x = fadd(fmul(lambdar, matcolor.x), fmul(fsub(1.0f, lambdar), 1.0f));  // :602-604
     matcolor.y = fadd(fmul(lambdag, matcolor.y), fmul(fsub(1.0f, lambdag), 1.0f));
     matcolor.z = fadd(fmul(lambdab, matcolor.z), fmul(fsub(1.0f, lambdab), 1.0f));
-    const vec3 so = res.voxelPos;
-    const bool shit = cast_ray<FAST, STATS>(sc, so, sun2, f.maxDepth, false, f.coneDepth, res, loops, rs);  // :607
-    if (shit && res.t > fmul(res.scale, 1.73205080757f)) {
-      matcolor = mk3(fsub(matcolor.x, 0.2f), fsub(matcolor.y, 0.2f), fsub(matcolor.z, 0.2f));
-    } else if (res.iter > 260u) {  // :616-619
-      const float pen = fdiv(fmul(0.05f, (float)res.iter), 100.0f);
-      matcolor = mk3(fsub(matcolor.x, pen), fsub(matcolor.y, pen), fsub(matcolor.z, pen));
-    }
-    out.color = matcolor;
-    return;
+    P.acc = matcolor;
+    P.origin = res.voxelPos;  // shadow ray :607
+    P.dir = sun2;
+    P.cone = false;
+    P.cast_i = 1;
+    return true;
   }
-  out.color = res.voxelPos;  // mode 4 (:643-645): uninitialised upstream, zero here
+  vec3 matcolor = P.acc;
+  if (intersect && res.t > fmul(res.scale, 1.73205080757f)) {  // :607-615
+    matcolor = mk3(fsub(matcolor.x, 0.2f), fsub(matcolor.y, 0.2f), fsub(matcolor.z, 0.2f));
+  } else if (res.iter > 260u) {  // :616-619
+    const float pen = fdiv(fmul(0.05f, (float)res.iter), 100.0f);
+    matcolor = mk3(fsub(matcolor.x, pen), fsub(matcolor.y, pen), fsub(matcolor.z, pen));
+  }
+  P.color = matcolor;
+  return false;
 }
 
 SVO_DI unsigned char quant8(float c) {  // imageStore to rgba8 (:726), DESIGN.md U5
@@ -410,38 +545,36 @@ SVO_DI unsigned char quant8(float c) {  // imageStore to rgba8 (:726), DESIGN.md
   return (unsigned char)floorf(fadd(fmul(c, 255.0f), 0.5f));
 }
 
-// main (svotrace.comp:649-729) for pixel (x, y)
+// the end of main() (:696-727)
+template <bool AUX>
+SVO_DI void pixel_store(const SceneView &sc, const Planes &pl, int W, Pixel &P) {
+  if (P.x < 10 && P.y < 10)  // :696-700
+    P.color = sc.first_word_zero ? mk3(1.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
+  const size_t p = (size_t)P.y * (size_t)W + (size_t)P.x;
+  pl.rgba8[p] = make_uchar4(quant8(P.color.x), quant8(P.color.y), quant8(P.color.z), 255);  // :726
+  pl.depth[p] = P.depth;                                                                       // :727
+  if (AUX) {
+    pl.hit_id[p] = P.hit_id;
+    pl.iter[p] = P.iter;
+    pl.primary_t[p] = P.primary_t;
+    pl.radiance[p] = make_float4(P.color.x, P.color.y, P.color.z, 1.0f);
+  }
+}
+
+// main (svotrace.comp:649-729) for pixel (x, y), run to completion
 template <bool FAST, bool AUX, bool STATS = false>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                                             int x, int y, RayStats *rs = nullptr) {
-  float beamDist = 0.0f;
-  if (f.useBeam && pl.beam) beamDist = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));  // :656-658
-  const float fx = fdiv(fadd((float)x, 0.5f), (float)W);  // :662
-  const float fy = fdiv(fadd((float)y, 0.5f), (float)H);
-  vec3 dir;  // :664
-  dir.x = mixf(mixf(f.l1[0], f.l2[0], fy), mixf(f.r1[0], f.r2[0], fy), fx);
-  dir.y = mixf(mixf(f.l1[1], f.l2[1], fy), mixf(f.r1[1], f.r2[1], fy), fx);
-  dir.z = mixf(mixf(f.l1[2], f.l2[2], fy), mixf(f.r1[2], f.r2[2], fy), fx);
-  dir = normalize3(dir);  // :675
-  PixelOut o;
-  o.color = mk3(0.0f, 0.0f, 0.0f);
-  o.depth = -1.0f;  // :672
-  o.hit_id = kNoHit;
-  o.iter = 0;
-  o.primary_t = 0.0f;
-  trace_pixel<FAST, STATS>(sc, f, beamDist, mk3(f.camPos[0], f.camPos[1], f.camPos[2]), dir, (float)x, (float)y,
-                           (float)f.frameNumber, o, rs);
-  if (x < 10 && y < 10)  // :696-700
-    o.color = sc.first_word_zero ? mk3(1.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
-  const size_t p = (size_t)y * (size_t)W + (size_t)x;
-  pl.rgba8[p] = make_uchar4(quant8(o.color.x), quant8(o.color.y), quant8(o.color.z), 255);  // :726
-  pl.depth[p] = o.depth;                                                                       // :727
-  if (AUX) {
-    pl.hit_id[p] = o.hit_id;
-    pl.iter[p] = o.iter;
-    pl.primary_t[p] = o.primary_t;
-    pl.radiance[p] = make_float4(o.color.x, o.color.y, o.color.z, 1.0f);
+  Pixel P;
+  if (pixel_begin(f, pl, W, H, x, y, P)) {
+    bool more;
+    do {
+      uint32_t loops = 0;
+      const bool hit = cast_ray<FAST, STATS>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs);
+      more = pixel_after_cast(f, P, hit, loops);
+    } while (more);
   }
+  pixel_store<AUX>(sc, pl, W, P);
 }
 
 }  // namespace svo

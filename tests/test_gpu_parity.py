@@ -27,10 +27,14 @@ def _assert_planes_equal(got, want, what):
         assert bad == 0, "%s: plane %s differs in %d of %d elements" % (what, k, bad, same.size)
 
 
-@pytest.fixture(scope="module")
-def ctx512(svo, terrain512):
+KERNELS = [0, 1, 2]  # SVO_OPT_KERNEL: 0 tile kernel, 1 persistent megakernel with lane refill, 2 wavefront
+
+
+@pytest.fixture(scope="module", params=KERNELS, ids=["tile", "persistent", "wavefront"])
+def ctx512(request, svo, terrain512):
     c = svo.SvoContext(640, 360)
     c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+    c.set_option(svo._lib.OPT_KERNEL, request.param)
     c.upload(terrain512)
     yield c
     c.close()
@@ -95,11 +99,13 @@ def test_ray_stream_bit_exact(svo, oracle, terrain512, ctx512):
         assert st.stale_pops == 0
 
 
-def test_multichunk_tree_and_rows(svo, oracle, terrain128):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_multichunk_tree_and_rows(svo, oracle, terrain128, kernel):
     """Fill levels + chunk splices (128^3 world of 64^3 chunks) and the row-band partition."""
     W, H = 200, 120  # not a multiple of the 16x8 CTA tile
     with svo.SvoContext(W, H) as c:
         c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
         c.upload(terrain128)
         for cam in ("A", "B", "C"):
             pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
@@ -112,3 +118,34 @@ def test_multichunk_tree_and_rows(svo, oracle, terrain128):
             got = {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(),
                    "hit_id": c.read_hit_id(), "iter": c.read_iter(), "primary_t": c.read_primary_t()}
             _assert_planes_equal(got, want, "terrain128 cam " + cam)
+
+
+def test_render_stats_match_oracle(svo, oracle, terrain512):
+    """The instrumented kernel's counters (casts, iterations, reference-layout record bytes: the algorithmic
+    bytes bench.py reports) equal the oracle's."""
+    with svo.SvoContext(640, 360) as c:
+        c.upload(terrain512)
+        for cam, mode in (("A", 0), ("B", 2), ("C", 0)):
+            pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+            _, st = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=mode),
+                                  640, 360, nthreads=8, planes=("depth",))
+            got = c.render_stats(svo.camera_frame(cam, frame_number=2, render_mode=mode))
+            assert got == {"casts": st.casts, "iters": st.iters, "record_bytes": st.record_bytes}, (cam, mode, got, st.as_dict())
+
+
+def test_fast_math_is_close(svo, oracle, terrain512):
+    """SVO_OPT_FAST_MATH lets the t arithmetic contract into FFMA: not bit-exact by design; hit ids may flip on
+    a handful of silhouette pixels and t moves by a few ulp (north_star tolerance: relative t error <= 1e-5)."""
+    with svo.SvoContext(640, 360) as c:
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.set_option(svo._lib.OPT_FAST_MATH, 1)
+        c.upload(terrain512)
+        pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+        want, _ = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=3), 640, 360, nthreads=8)
+        c.render(svo.camera_frame("B", frame_number=1, render_mode=3))
+        ids, t = c.read_hit_id(), c.read_primary_t()
+        same = ids == want["hit_id"]
+        assert same.mean() > 0.999
+        both = same & (ids != svo.NO_HIT)
+        rel = np.abs(t[both] - want["primary_t"][both]) / np.maximum(want["primary_t"][both], 1e-6)
+        assert np.quantile(rel, 0.999) <= 1e-5 and rel.max() <= 1e-3
