@@ -239,7 +239,7 @@ def main():
     color_h = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     depth_h = torch.empty((H, W), dtype=torch.float32).pin_memory()
     def e2e_step(s):
-        ctx.render(frames[s])  # the 96-byte svo_frame is read from host memory by the call
+        ctx.render(frames[s])  # the 92-byte svo_frame is read from host memory by the call
         ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
         ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
     for s in range(a.warmup):
@@ -300,7 +300,7 @@ def main():
                    "world_build_s": round(build_s, 2), "upload_transcode_s": round(upload_s, 2),
                    "units": "rank r renders progressive sample s*N+r of each view; no data-path collective"},
         "clocks": clk, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96, "d2h_bytes_per_step": W * H * 8,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
                 "ms_per_step": e2e_s / a.steps * 1e3},
         "roofline": roofline,
     }

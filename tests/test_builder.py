@@ -1,0 +1,96 @@
+"""World-generation tests (CPU only): the oracle's brute-force restatement of Octree.java's builder, and the
+product's heightmap-driven builder (svo_build_terrain), which must emit the same bytes."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import svo_stream as S
+
+
+def test_oracle_builder_round_trips_dense_voxels(oracle):
+    rng = np.random.default_rng(5)
+    for n in (4, 8, 16):
+        vox = (rng.random((n, n, n)) < 0.3).astype(np.uint8) * rng.integers(1, 4, (n, n, n)).astype(np.uint8)
+        nodes, counts = oracle.build_dense(vox)
+        assert np.array_equal(S.decode_voxels(nodes, n), vox)
+        assert nodes[0] == 1  # dummy head (OctreeThread.java:21)
+
+
+def test_oracle_builder_record_types_and_normals(oracle):
+    """Flat floor, 8^3: voxels y <= 3 solid.  Top layer = surface leaves with normal +y; below = non-surface leaves
+    or subdividable blocks; above = empty subdividable leaves."""
+    n = 8
+    vox = np.zeros((n, n, n), np.uint8)
+    vox[:, :4, :] = 2  # [z, y, x]
+    nodes, counts = oracle.build_dense(vox)
+    surface, nonsurf, subdiv, interior_ = counts
+    # y=3 layer is exposed: 64 surface leaves.  The y<=3 half of the cube is 4 homogeneous 4^3 blocks; their probe
+    # points {c-1, c+s, c+s+1} (Octree.java:651-670) reach y=4,5 (empty) -> exposed -> subdivided.
+    assert surface == 64
+    b = nodes.tobytes()
+    # find one surface leaf and check its packed normal: empties are the 9 voxels above (dy=+1) -> (0, 9/2, 0) + 5 -> x=5,y=9,z=5
+    # interior voxels away from the chunk border see all 9 upper neighbours: 5 + 9*10 + 5*100 = 595
+    import struct
+    normals = set()
+    def walk(off, size):
+        rel = struct.unpack(">i", b[off + 1:off + 5])[0]
+        mask = struct.unpack(">H", b[off + 5:off + 7])[0]
+        p = off + rel
+        for i in range(8):
+            code = (mask >> (2 * i)) & 3
+            if code == 0 and struct.unpack(">i", b[p + 1:p + 5])[0] != 0:
+                walk(p, size // 2)
+            if code == 1:
+                normals.add(struct.unpack("<H", b[p + 1:p + 3])[0])
+            p += S.SIZES[code]
+    walk(0, n)
+    assert 595 in normals
+    # every normal points up (y digit > 5); x/z digits deviate from 5 only at the chunk border (fewer neighbours)
+    assert all((v // 10) % 10 > 5 for v in normals)
+
+
+@pytest.mark.parametrize("n,chunk", [(32, 32), (64, 16), (128, 32), (256, 256), (256, 64)])
+def test_fast_builder_equals_reference_builder(svo, oracle, n, chunk):
+    """svo_build_terrain (mip-pyramid builder, parallel sub-octrees) == brute-force Octree.java restatement, byte for byte,
+    including fill levels (n > chunk), the 8-way chunk splice and its 7-byte gaps (Octree.java:336)."""
+    for seed in (1, 7):
+        hm, mm = svo.terrain_inputs(n, seed=seed)
+        want, counts = oracle.build_terrain(hm, mm, n, chunk)
+        for threads in (1, 4):
+            got = svo.build_terrain(hm, mm, n, chunk, nthreads=threads)
+            assert got.size == want.size and np.array_equal(got, want), (n, chunk, seed, threads)
+
+
+def test_fast_builder_material_bands_and_extremes(svo, oracle):
+    """Adversarial heightmaps: flat, spikes, full-height walls, every material; checks the O(1) homogeneity shortcuts."""
+    n, chunk = 64, 32
+    rng = np.random.default_rng(11)
+    cases = []
+    cases.append((np.full((n, n), 30000, np.uint16), np.full((n, n), 1, np.uint8)))
+    cases.append((np.full((n, n), 30000, np.uint16), np.full((n, n), 3, np.uint8)))
+    cases.append((np.zeros((n, n), np.uint16), np.full((n, n), 2, np.uint8)))
+    cases.append((np.full((n, n), 65535, np.uint16), rng.integers(1, 4, (n, n)).astype(np.uint8)))
+    spikes = np.full((n, n), 8000, np.uint16)
+    spikes[::7, ::5] = 60000
+    cases.append((spikes, rng.integers(1, 4, (n, n)).astype(np.uint8)))
+    cases.append((rng.integers(0, 65536, (n, n)).astype(np.uint16), rng.integers(1, 4, (n, n)).astype(np.uint8)))
+    steps = (np.arange(n)[None, :] // 8 * 9000).astype(np.uint16) + np.zeros((n, 1), np.uint16)
+    cases.append((steps, np.where(np.arange(n)[:, None] % 2 == 0, 1, 2).astype(np.uint8) + np.zeros((1, n), np.uint8)))
+    for hm, mm in cases:
+        want, _ = oracle.build_terrain(hm, mm, n, chunk)
+        got = svo.build_terrain(hm, mm, n, chunk, nthreads=2)
+        assert np.array_equal(got, want)
+
+
+def test_terrain_generator_is_deterministic(svo):
+    hm1, mm1 = svo.terrain_inputs(256, seed=1, nthreads=1)
+    hm2, mm2 = svo.terrain_inputs(256, seed=1, nthreads=5)
+    assert np.array_equal(hm1, hm2) and np.array_equal(mm1, mm2)
+    assert hm1.min() == 1957 and hm1.max() == 58795  # span of assets/heightmaps/nz.png
+    assert set(np.unique(mm1)) <= {1, 2, 3}
+    hm3, _ = svo.terrain_inputs(256, seed=2)
+    assert not np.array_equal(hm1, hm3)
+    # pinned digest: the synthetic inputs of the benchmark never drift silently
+    assert hashlib.sha256(hm1.tobytes() + mm1.tobytes()).hexdigest() == open(
+        __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "terrain256_seed1.sha256")).read().strip()
