@@ -149,3 +149,80 @@ def test_fast_math_is_close(svo, oracle, terrain512):
         both = same & (ids != svo.NO_HIT)
         rel = np.abs(t[both] - want["primary_t"][both]) / np.maximum(want["primary_t"][both], 1e-6)
         assert np.quantile(rel, 0.999) <= 1e-5 and rel.max() <= 1e-3
+
+
+def test_renderer_mirror_reads_like_the_engine(svo, oracle, terrain128):
+    """The Renderer.java mirror, driven the way Main.preRun / Main.updateEarly drive the GL renderer
+    (Main.java:102-122, :267-285, :132-146), including the partial-upload path (Main.java:349-350)."""
+    svo.Renderer.resetInstance()
+    W, H = 160, 90
+    r = svo.Renderer.getInstance(W, H)
+    trace = r.addShader("svotrace", "src/shaders/svotrace.comp")
+    beam = r.addShader("beamShader", "src/shaders/svobeam.comp")
+    assert r.getShaderByName("svotrace") is trace
+    buf = np.zeros(terrain128.size + 4096, np.uint8)  # Octree's big ByteBuffer; memOffset bytes are valid
+    buf[:terrain128.size] = terrain128
+    r.addSSBO(7, buf, terrain128.size)
+    pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+    r.useProgram(trace)
+    r.glUniform3fv(8, pos)
+    for loc, v in zip((1, 2, 3, 4), (l1, l2, r1, r2)):
+        r.glUniform3fv(loc, v)
+    r.glUniform1i(5, 1)
+    r.glUniform1i(6, 2)
+    r.glUniform1i(9, terrain128.size)
+    r.glUniform1i(11, 0)
+    r._frame.maxDepth = 7
+    r.dispatchCompute(trace, (W + 7) // 8, (H + 7) // 8, 1)
+    assert r.printGLErrors() == 0
+    want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, max_depth=7), W, H, nthreads=4)
+    assert np.array_equal(r.getFramebufferImage(), want["rgba8"])
+    depth = r.getDepthImage()
+    assert np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32))
+    assert r.ctx.read_depth_at(W // 2, H // 2) == depth[H // 2, W // 2]  # the crosshair pick
+
+    # an "SDF edit": change a leaf value in place and append nothing -> updateSSBO(7, buf, start, end)
+    edited = terrain128.copy()
+    solid = np.nonzero(want["hit_id"] != svo.NO_HIT)
+    ptr = int(want["hit_id"][solid[0][0], solid[1][0]])
+    edited[ptr] = 3 if edited[ptr] != 3 else 2
+    buf[:edited.size] = edited
+    r.updateSSBO(7, buf, ptr, ptr + 1)
+    r.updateSSBO(7, buf, 5, 5)  # Renderer.java:137-140: prints "Update SSBO error: Invalid parameters." and returns
+    r.dispatchCompute(trace, (W + 7) // 8, (H + 7) // 8, 1)
+    want2, _ = oracle.render(edited, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, max_depth=7), W, H, nthreads=4)
+    assert np.array_equal(r.getFramebufferImage(), want2["rgba8"])
+    assert not np.array_equal(want2["rgba8"], want["rgba8"])
+
+    # beam pre-pass (Main.java:257-266) then a trace that consumes it (uniform 11)
+    r.useProgram(beam)
+    r.dispatchCompute(beam, 1, 1, 1)
+    got_beam = r.ctx.read_plane(svo._lib.PLANE_BEAM)
+    f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, max_depth=7)
+    want_beam = oracle.beam(edited, f, W, H)
+    assert np.array_equal(got_beam.view(np.uint32), want_beam.view(np.uint32))
+    r.glUniform1i(11, 1)
+    r.dispatchCompute(trace, 1, 1, 1)
+    f.useBeam = 1
+    want3, _ = oracle.render(edited, f, W, H, beam=want_beam, nthreads=4)
+    assert np.array_equal(r.getFramebufferImage(), want3["rgba8"])
+    assert r.printGLErrors() == 0
+    svo.Renderer.resetInstance()
+
+
+def test_errors_are_codes_not_crashes(svo, terrain128):
+    with svo.SvoContext(64, 64) as c:
+        with pytest.raises(svo.SvoError) as e:
+            c.render(svo.camera_frame("A"))
+        assert e.value.code == svo._lib.ERR_NO_SCENE
+        c.upload(terrain128)
+        bad = svo.camera_frame("A", max_depth=40)
+        with pytest.raises(svo.SvoError) as e:
+            c.render(bad)
+        assert e.value.code == svo._lib.ERR_INVALID
+        with pytest.raises(svo.SvoError):
+            c.render(svo.camera_frame("A"), 10, 200)
+        c.upload(np.zeros(0, np.uint8))  # an empty stream is legal: everything misses
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.render(svo.camera_frame("A", render_mode=3))
+        assert (c.read_hit_id() == svo.NO_HIT).all()
