@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+LIB_PATH = os.environ.get("SVO_B200_LIB") or os.path.join(_HERE, "libsvo_b200.so")  # override: A/B builds in development
 
 NO_HIT = 0xFFFFFFFF
 

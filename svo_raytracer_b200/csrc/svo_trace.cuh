@@ -97,6 +97,12 @@ SVO_DI uint32_t child_offset(uint32_t codes, uint32_t c) {
   return 7u * n7 + 3u * n1 + n3;
 }
 
+SVO_DI uint32_t find_msb(uint32_t x) {  // GLSL findMSB for x != 0
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
 SVO_DI float sign_glsl(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
 struct RayStats {  // per-thread counters of the instrumented build (svo_render_stats)
@@ -220,8 +226,8 @@ struct Trav {
 
   // The body of one loop iteration (:262-369), shared by run() and step().  `EXIT(status)` leaves the loop,
   // `NEXT` starts the next iteration.  The iteration cap (:264-266) is enforced where it is cheap -- on the
-  // ADVANCE path, plus once after the loop (cap_fixup) -- instead of on every iteration: at most 23 PUSHes can
-  // run between two ADVANCEs, and a cast that ends with iter > 1500 is exactly a cast the reference capped.
+  // POP path, plus once after the loop (cap_fixup) -- instead of on every iteration: a cast that ends with
+  // iter > 1500 is exactly a cast the reference capped, and a cast cannot run long without a POP.
 #define SVO_TRAV_BODY(EXIT, NEXT)                                                                                    \
   iter++;                                                                                                            \
   if (STATS && iter <= (uint32_t)kMaxIterations) rs->iters += 1u;                                                    \
@@ -243,8 +249,7 @@ struct Trav {
       const uint32_t bit24 = bit16 << 8;                                                                             \
       if ((pd.y & bit24) == 0u) { EXIT(TRAV_HIT); } /* child.cp == 0 (:311-313) */                                   \
       if (tc_max < h) { /* PUSH :316-319 */                                                                          \
-        stk_idx[scale] = pidx;                                                                                       \
-        stk_tmax[scale] = t_max;                                                                                     \
+        stk[scale] = make_uint2(pidx, __float_as_uint(t_max));                                                       \
       }                                                                                                              \
       h = tc_max;                                                                                                    \
       pidx = pd.x + __popc(pd.y & (bit24 - 0x01000000u)); /* descriptors of the interior siblings below */           \
@@ -255,20 +260,18 @@ struct Trav {
       const float tz_center = M::madd(half, cz, tz_corner);                                                          \
       --scale;                                                                                                       \
       scale_exp2 = half;                                                                                             \
-      idx = 0u;                                                                                                      \
-      if (tx_center > t_min) { idx ^= 1u; px = fadd(px, scale_exp2); } /* :328-330 (exact adds) */                   \
-      if (ty_center > t_min) { idx ^= 2u; py = fadd(py, scale_exp2); }                                               \
-      if (tz_center > t_min) { idx ^= 4u; pz = fadd(pz, scale_exp2); }                                               \
+      const bool gx = tx_center > t_min, gy = ty_center > t_min, gz = tz_center > t_min; /* :328-330 */              \
+      px = gx ? fadd(px, scale_exp2) : px; /* exact adds */                                                          \
+      py = gy ? fadd(py, scale_exp2) : py;                                                                           \
+      pz = gz ? fadd(pz, scale_exp2) : pz;                                                                           \
+      idx = (gx ? 1u : 0u) | (gy ? 2u : 0u) | (gz ? 4u : 0u);                                                        \
       t_max = tv_max;                                                                                                \
       NEXT;                                                                                                          \
     }                                                                                                                \
   }                                                                                                                  \
   /* ADVANCE :337-344 */                                                                                             \
-  uint32_t step_mask = 0u;                                                                                           \
-  if (tx_corner <= tc_max) { step_mask ^= 1u; px = fsub(px, scale_exp2); }                                           \
-  if (ty_corner <= tc_max) { step_mask ^= 2u; py = fsub(py, scale_exp2); }                                           \
-  if (tz_corner <= tc_max) { step_mask ^= 4u; pz = fsub(pz, scale_exp2); }                                           \
-  if (step_mask == 0u) {                                                                                             \
+  const bool sx = tx_corner <= tc_max, sy = ty_corner <= tc_max, sz = tz_corner <= tc_max;                           \
+  if (!(sx || sy || sz)) {                                                                                           \
     /* all three corners are NaN (NaN direction from a zero or 555 normal): nothing changes any more and the   */    \
     /* reference spins to the cap (:264)                                                                        */    \
     if (STATS && iter <= (uint32_t)kMaxIterations) {                                                                 \
@@ -279,19 +282,31 @@ struct Trav {
     iter = (uint32_t)kMaxIterations + 1u;                                                                            \
     EXIT(TRAV_MISS);                                                                                                 \
   }                                                                                                                  \
+  px = sx ? fsub(px, scale_exp2) : px;                                                                               \
+  py = sy ? fsub(py, scale_exp2) : py;                                                                               \
+  pz = sz ? fsub(pz, scale_exp2) : pz;                                                                               \
+  const uint32_t step_mask = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);                                       \
   t_min = tc_max;                                                                                                    \
   if (t_min > 0.05f) stop_scale = cone_stop; /* :275-277 */                                                          \
   idx ^= step_mask;                                                                                                  \
   if ((idx & step_mask) != 0u) { /* POP :347-368 */                                                                  \
+    /* The iteration cap (:264-266) is tested here only: every run of ADVANCEs ends in a POP after at most 3   */    \
+    /* steps, so the test is at most ~26 iterations late, and cap_fixup() turns any cast that ends with        */    \
+    /* iter > 1500 into exactly what the reference returns at iteration 1501.                                   */    \
+    if (iter >= (uint32_t)kMaxIterations) {                                                                          \
+      iter = (uint32_t)kMaxIterations + 1u;                                                                          \
+      EXIT(TRAV_MISS);                                                                                               \
+    }                                                                                                                \
     uint32_t differing_bits = 0;                                                                                     \
-    if (step_mask & 1u) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));               \
-    if (step_mask & 2u) differing_bits |= __float_as_uint(py) ^ __float_as_uint(fadd(py, scale_exp2));               \
-    if (step_mask & 4u) differing_bits |= __float_as_uint(pz) ^ __float_as_uint(fadd(pz, scale_exp2));               \
-    scale = 31 - __clz(differing_bits); /* findMSB */                                                                \
+    if (sx) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));                           \
+    if (sy) differing_bits |= __float_as_uint(py) ^ __float_as_uint(fadd(py, scale_exp2));                           \
+    if (sz) differing_bits |= __float_as_uint(pz) ^ __float_as_uint(fadd(pz, scale_exp2));                           \
+    scale = (int)find_msb(differing_bits); /* findMSB */                                                             \
     if (scale >= kMaxScale) { EXIT(TRAV_MISS); } /* left the cube: the loop condition fails (:262) */                \
     scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);                                         \
-    pidx = stk_idx[scale];                                                                                           \
-    t_max = stk_tmax[scale];                                                                                         \
+    const uint2 se = stk[scale];                                                                                     \
+    pidx = se.x;                                                                                                     \
+    t_max = __uint_as_float(se.y);                                                                                   \
     pd = __ldg(sc.desc + pidx);                                                                                      \
     const uint32_t shx = __float_as_uint(px) >> scale;                                                               \
     const uint32_t shy = __float_as_uint(py) >> scale;                                                               \
@@ -301,10 +316,6 @@ struct Trav {
     pz = __uint_as_float(shz << scale);                                                                              \
     idx = (shx & 1u) | ((shy & 1u) << 1) | ((shz & 1u) << 2);                                                        \
     h = 0.0f;                                                                                                        \
-  }                                                                                                                  \
-  if (iter >= (uint32_t)kMaxIterations) { /* the next iteration is number 1501: the cap (:264-266) */                \
-    iter = (uint32_t)kMaxIterations + 1u;                                                                            \
-    EXIT(TRAV_MISS);                                                                                                 \
   }
 
   // A hit found after iteration 1500 (only possible through a run of PUSHes right after the last ADVANCE
@@ -318,18 +329,20 @@ struct Trav {
   }
 
   // the whole loop (:262-369); returns TRAV_HIT or TRAV_MISS
-  __device__ __forceinline__ int run(const SceneView &sc, uint32_t *stk_idx, float *stk_tmax, RayStats *rs) {
-    int status;
-#define SVO_EXIT(s) { status = (s); break; }
+  __device__ __forceinline__ int run(const SceneView &sc, uint2 *stk, RayStats *rs) {
+#define SVO_EXIT(s) { if ((s) == TRAV_HIT) goto hit; else goto miss; }
     for (;;) {
       SVO_TRAV_BODY(SVO_EXIT, continue)
     }
 #undef SVO_EXIT
-    return cap_fixup(status);
+  hit:
+    return cap_fixup(TRAV_HIT);
+  miss:
+    return cap_fixup(TRAV_MISS);
   }
 
   // one iteration; returns TRAV_CONTINUE until the cast is over
-  __device__ __forceinline__ int step(const SceneView &sc, uint32_t *stk_idx, float *stk_tmax, RayStats *rs) {
+  __device__ __forceinline__ int step(const SceneView &sc, uint2 *stk, RayStats *rs) {
 #define SVO_EXIT(s) return cap_fixup(s)
     SVO_TRAV_BODY(SVO_EXIT, return TRAV_CONTINUE)
 #undef SVO_EXIT
@@ -357,11 +370,10 @@ struct Trav {
 template <bool FAST, bool STATS = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
                                          int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr) {
-  uint32_t stk_idx[kMaxScale + 1];  // octstack (:199-202): parent index + t_max per scale
-  float stk_tmax[kMaxScale + 1];
+  uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
   Trav<FAST, STATS> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
-  return T.finish(sc, T.run(sc, stk_idx, stk_tmax, rs), res, loops);
+  return T.finish(sc, T.run(sc, stk, rs), res, loops);
 }
 
 SVO_DI void matcolor_table(uint32_t value, vec3 &mc) {  // :514-522, :578-586

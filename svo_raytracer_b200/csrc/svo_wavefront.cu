@@ -43,8 +43,7 @@ __global__ void __launch_bounds__(128) k_wf_trav(SceneView sc, FrameParams f, Pl
   const int tiles_x = (W + 7) >> 3;
   const unsigned n = PRIMARY ? (unsigned)tiles_x * (unsigned)((y1 - y0 + 3) >> 2) * 32u : __ldg(n_rays);
 
-  uint32_t stk_idx[kMaxScale + 1];
-  float stk_tmax[kMaxScale + 1];
+  uint2 stk[kMaxScale + 1];
   Trav<FAST> T;
   bool busy = false;
   unsigned slot = 0;
@@ -96,7 +95,7 @@ __global__ void __launch_bounds__(128) k_wf_trav(SceneView sc, FrameParams f, Pl
     // ---- traverse until kRefill lanes are done (or, with the queue empty, all are) ----
     for (;;) {
       if (busy) {
-        const int status = T.step(sc, stk_idx, stk_tmax, nullptr);
+        const int status = T.step(sc, stk, nullptr);
         if (status != TRAV_CONTINUE) {
           const HitState hs = T.export_hit(status);
           hitA[slot] = make_uint4(hs.pidx, hs.meta, hs.ipx, hs.ipy);
