@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
+                    help="N>1: frames = rank r renders progressive sample s*N+r of each view (weak scaling, no collective); "
+                         "tiles = ONE frame per step split in interleaved 8-row bands, peers store straight into rank 0's "
+                         "planes over NVLink (CUDA IPC) + one NCCL fence per frame (strong scaling)")
     return ap.parse_args()
 
 
@@ -186,22 +190,41 @@ def main():
     upload_s = time.time() - t0
     info = ctx.scene_info()
 
-    # Units: with N ranks every rank renders its own progressive sample (frameNumber) of the same views --
-    # independent units, no data-path collective (weak scaling); step s on rank r is sample s*N + r.
-    def my_frame(s):
-        f = frame_for(s, a.size)
-        f.frameNumber = s * world_size + rank + 1
-        return f
-
+    tiles = world_size > 1 and a.partition == "tiles"
     total = a.warmup + a.steps
-    frames = [my_frame(s) for s in range(total)]
+    if tiles:
+        # ONE frame per step, image bands interleaved over the ranks, replicated octree.  Rank 0 owns the frame
+        # buffer; every peer maps it (CUDA IPC over NVLink) and its kernel stores its bands straight into it.
+        frames = [frame_for(s, a.size) for s in range(total)]
+        handles = [ctx.ipc_export(L.PLANE_COLOR_RGBA8), ctx.ipc_export(L.PLANE_DEPTH)] if rank == 0 else [None, None]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            for plane, h in zip((L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH), handles):
+                ctx.bind_plane(plane, ctx.ipc_import(h))
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        fence = torch.zeros(1, device="cuda")
 
-    # rays per frame and algorithmic bytes (instrumented kernel, outside the timed region)
+        def render_step(s):
+            ctx.render_interleaved(frames[s], rank, world_size)
+            dist.all_reduce(fence)  # stream-ordered frame-complete fence: after it rank 0's planes hold the whole frame
+    else:
+        # Units: rank r renders its own progressive sample (frameNumber) of the same views -- independent units, no
+        # data-path collective (weak scaling); step s on rank r is sample s*N + r.
+        def my_frame(s):
+            f = frame_for(s, a.size)
+            f.frameNumber = s * world_size + rank + 1
+            return f
+        frames = [my_frame(s) for s in range(total)]
+
+        def render_step(s):
+            ctx.render(frames[s])
+
+    # rays per frame and algorithmic bytes (instrumented kernel, outside the timed region; casts do not depend on the
+    # RNG sample: a bounce is cast iff the primary ray hit)
     per_cam = {}
     for ci, cam in enumerate(CAM_CYCLE):
         per_cam[cam] = ctx.render_stats(frames[ci])
     rays_per_step = [per_cam[CAM_CYCLE[s % 3]]["casts"] for s in range(total)]
-    # bounce rays depend on the RNG sample only through hit/miss of the PRIMARY cast: casts are identical per camera
     alg_bytes_per_step = [per_cam[CAM_CYCLE[s % 3]]["record_bytes"] + 8 * W * H for s in range(total)]
     iters_per_step = [per_cam[CAM_CYCLE[s % 3]]["iters"] for s in range(total)]
 
@@ -210,38 +233,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident timing ------------------------------------------------
     for s in range(a.warmup):
-        ctx.render(frames[s])
+        render_step(s)
     ctx.sync()
     barrier()
     clocks = ClockSampler(dev)
     launches0 = ctx.launch_count()
     ctx.timer_begin()
     for s in range(a.warmup, total):
-        ctx.render(frames[s])
+        render_step(s)
     dev_ms = ctx.timer_end()
     launches = ctx.launch_count() - launches0
     barrier()
     clk = clocks.stop()
-    if dist is not None:
-        t = torch.tensor([dev_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        max_ms = float(t.item())
-        r = torch.tensor([float(sum(rays_per_step[a.warmup:]))], device="cuda", dtype=torch.float64)
-        dist.all_reduce(r)
-        all_rays = float(r.item())
-    else:
-        max_ms, all_rays = dev_ms, float(sum(rays_per_step[a.warmup:]))
+    max_ms = reduce_max(dev_ms)
+    step_rays = float(sum(rays_per_step[a.warmup:]))
+    all_rays = step_rays if tiles else step_rays * world_size  # frames mode: every rank casts a full frame per step
     value = all_rays / (max_ms * 1e-3) / 1e6
 
     # ---- end to end through the C ABI with host buffers -------------------------
     color_h = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     depth_h = torch.empty((H, W), dtype=torch.float32).pin_memory()
+    reads = rank == 0 or not tiles  # tiles: only rank 0 holds the frame
+
     def e2e_step(s):
-        ctx.render(frames[s])  # the 92-byte svo_frame is read from host memory by the call
-        ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
-        ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
+        render_step(s)  # the 92-byte svo_frame is read from host memory by the call
+        if reads:
+            ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
+            ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
     for s in range(a.warmup):
         e2e_step(s)
     barrier()
@@ -249,11 +276,7 @@ def main():
     for s in range(a.warmup, total):
         e2e_step(s)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_value = all_rays / e2e_s / 1e6
 
     if rank != 0:
@@ -291,14 +314,16 @@ def main():
 
     out = {
         "metric": "Mrays/s (primary + diffuse bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "tree_bytes": int(nodes.size), "descriptors": info["descriptors"], "levels": info["levels"],
+        "config": {"workload": workload, "partition": a.partition if world_size > 1 else "single GPU", "tree_bytes": int(nodes.size), "descriptors": info["descriptors"], "levels": info["levels"],
                    "l2_policy": "inputs larger than L2 (octree %.2f GB, 3 camera poses cycled); no flush between steps" % (nodes.size / 1e9)
                    if nodes.size > 126e6 else "octree fits L2; camera poses cycled; no flush",
                    "fast_math": a.fast_math, "kernel": a.kernel, "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
                    "world_build_s": round(build_s, 2), "upload_transcode_s": round(upload_s, 2),
-                   "units": "rank r renders progressive sample s*N+r of each view; no data-path collective"},
+                   "units": ("one frame per step, interleaved 8-row bands per rank, peers store into rank 0's planes over NVLink, "
+                             "one NCCL all-reduce fence per frame") if tiles else
+                            "rank r renders progressive sample s*N+r of each view; no data-path collective"},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
                 "ms_per_step": e2e_s / a.steps * 1e3},

@@ -112,6 +112,9 @@ int svo_scene_info(const svo_ctx *ctx, uint64_t info[4]);
 int svo_render(svo_ctx *ctx, const svo_frame *frame);
 /* rows [y0,y1) only: the image-tile partition for multi-GPU */
 int svo_render_rows(svo_ctx *ctx, const svo_frame *frame, int y0, int y1);
+/* 8-row bands part, part+parts, part+2*parts, ... of the frame in ONE launch: the interleaved
+ * image partition of the multi-GPU mode (rank = part, world size = parts). */
+int svo_render_interleaved(svo_ctx *ctx, const svo_frame *frame, int part, int parts);
 /* replaces dispatchCompute(beamShader, W/8/4, H/8/4, 1) (Main.java:257-266) */
 int svo_beam(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
@@ -132,6 +135,15 @@ void *svo_device_ptr(svo_ctx *ctx, int plane);
 /* redirect a plane to caller-owned device memory (e.g. a peer GPU's frame
  * buffer mapped over NVLink); NULL restores the context's own allocation */
 int svo_bind_plane(svo_ctx *ctx, int plane, void *device_ptr);
+
+/* Multi-GPU frame buffers over NVLink (one process per GPU).  svo_ipc_export fills a 64-byte
+ * handle (cudaIpcMemHandle_t) for one of this context's own planes; the owning process sends it
+ * to its peers by any means; svo_ipc_import maps it in the peer process and returns a device
+ * pointer that svo_bind_plane accepts, so a peer's kernel stores its image tiles straight into
+ * the owner's plane (no gather step).  svo_ipc_close unmaps. */
+int svo_ipc_export(svo_ctx *ctx, int plane, uint8_t handle[64]);
+int svo_ipc_import(svo_ctx *ctx, const uint8_t handle[64], void **device_ptr);
+int svo_ipc_close(svo_ctx *ctx, void *device_ptr);
 
 /* -- ray streams (new): n independent intersectOctree calls.
  *    svo_cast: host buffers in/out.  svo_cast_device: device buffers. */

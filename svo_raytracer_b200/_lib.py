@@ -53,6 +53,7 @@ SYMBOLS = {
     "svo_scene_info": (_i, [_vp, C.POINTER(_u64 * 4)]),
     "svo_render": (_i, [_vp, C.POINTER(Frame)]),
     "svo_render_rows": (_i, [_vp, C.POINTER(Frame), _i, _i]),
+    "svo_render_interleaved": (_i, [_vp, C.POINTER(Frame), _i, _i]),
     "svo_beam": (_i, [_vp, C.POINTER(Frame)]),
     "svo_sync": (_i, [_vp]),
     "svo_read_plane": (_i, [_vp, _i, _vp, _u64]),
@@ -66,6 +67,9 @@ SYMBOLS = {
     "svo_read_radiance_f32": (_i, [_vp, _vp]),
     "svo_device_ptr": (_vp, [_vp, _i]),
     "svo_bind_plane": (_i, [_vp, _i, _vp]),
+    "svo_ipc_export": (_i, [_vp, _i, _vp]),
+    "svo_ipc_import": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "svo_ipc_close": (_i, [_vp, _vp]),
     "svo_cast": (_i, [_vp, _vp, _u64, _vp, _i]),
     "svo_cast_device": (_i, [_vp, _vp, _u64, _vp, _i]),
     "svo_timer_begin": (_i, [_vp]),

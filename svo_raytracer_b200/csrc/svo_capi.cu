@@ -135,6 +135,8 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.aux = c->opt_aux != 0;
   l.kernel = c->opt_kernel;
   l.sm_count = c->sm_count;
+  l.band_stride = 0;
+  l.band_offset = 0;
   l.ctas_per_sm = c->ctas_per_sm;
   l.tile_counter = c->d_tile_counter;
   return l;
@@ -403,6 +405,25 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
 }
 int svo_render(svo_ctx *c, const svo_frame *frame) { return svo_render_rows(c, frame, 0, c ? c->H : 0); }
 
+int svo_render_interleaved(svo_ctx *c, const svo_frame *frame, int part, int parts) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_render before svo_upload");
+  int rc = check_frame(c, frame);
+  if (rc) return rc;
+  if (parts < 1 || part < 0 || part >= parts) return fail(c, SVO_ERR_INVALID, "part must be in [0, parts)");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (c->opt_aux && (rc = ensure_aux(c)) != SVO_OK) return rc;
+  FrameParams fp;
+  memcpy(&fp, frame, sizeof fp);
+  LaunchCfg cfg = launch_cfg(c);
+  cfg.kernel = 0;  // the band-interleaved partition is a feature of the tile kernel
+  cfg.band_stride = parts;
+  cfg.band_offset = part;
+  SVO_CUDA(c, launch_render(cfg, scene_view(c), fp, planes_of(c), c->W, c->H, 0, c->H, c->stream));
+  c->launches++;
+  return SVO_OK;
+}
+
 int svo_beam(svo_ctx *c, const svo_frame *frame) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_beam before svo_upload");
@@ -472,6 +493,37 @@ int svo_bind_plane(svo_ctx *c, int plane, void *device_ptr) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (plane < 0 || plane > SVO_PLANE_RADIANCE) return fail(c, SVO_ERR_INVALID, "bad plane");
   c->bound[plane] = device_ptr;
+  return SVO_OK;
+}
+
+int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[64]) {
+  if (!c || !handle) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (plane < 0 || plane > SVO_PLANE_RADIANCE) return fail(c, SVO_ERR_INVALID, "bad plane");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (plane >= SVO_PLANE_HIT_ID) {
+    int rc = ensure_aux(c);
+    if (rc) return rc;
+  }
+  if (!c->own[plane]) return fail(c, SVO_ERR_INVALID, "plane not allocated");
+  cudaIpcMemHandle_t hnd;
+  SVO_CUDA(c, cudaIpcGetMemHandle(&hnd, c->own[plane]));
+  memcpy(handle, &hnd, 64);
+  return SVO_OK;
+}
+int svo_ipc_import(svo_ctx *c, const uint8_t handle[64], void **device_ptr) {
+  if (!c || !handle || !device_ptr) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, handle, 64);
+  SVO_CUDA(c, cudaIpcOpenMemHandle(device_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+  return SVO_OK;
+}
+int svo_ipc_close(svo_ctx *c, void *device_ptr) {
+  if (!c || !device_ptr) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  SVO_CUDA(c, cudaIpcCloseMemHandle(device_ptr));
   return SVO_OK;
 }
 

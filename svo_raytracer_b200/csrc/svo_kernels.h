@@ -35,6 +35,7 @@ struct LaunchCfg {
   bool aux;      // also write hit_id / iter / primary_t / radiance
   int kernel;    // variant selector (SVO_OPT_KERNEL)
   int sm_count;
+  int band_stride, band_offset;  // tile kernel: interleaved 8-row bands (0 = all bands)
   int ctas_per_sm;             // persistent grid = sm_count * ctas_per_sm
   unsigned int *tile_counter;  // device word: the persistent kernel's tile queue head
 };

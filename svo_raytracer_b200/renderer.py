@@ -124,6 +124,10 @@ class SvoContext:
         else:
             self._check(self._lib.svo_render_rows(self._h, C.byref(frame), int(y0 or 0), int(self.height if y1 is None else y1)))
 
+    def render_interleaved(self, frame: Frame, part: int, parts: int):
+        """Render 8-row bands part, part+parts, ... in one launch (multi-GPU image partition)."""
+        self._check(self._lib.svo_render_interleaved(self._h, C.byref(frame), int(part), int(parts)))
+
     def beam(self, frame: Frame):
         self._check(self._lib.svo_beam(self._h, C.byref(frame)))
 
@@ -176,6 +180,22 @@ class SvoContext:
 
     def bind_plane(self, plane: int, device_ptr: Optional[int]):
         self._check(self._lib.svo_bind_plane(self._h, plane, C.c_void_p(device_ptr or 0)))
+
+    def ipc_export(self, plane: int) -> bytes:
+        """64-byte CUDA IPC handle of one of this context's own planes (send it to the peer processes)."""
+        buf = (C.c_uint8 * 64)()
+        self._check(self._lib.svo_ipc_export(self._h, plane, buf))
+        return bytes(buf)
+
+    def ipc_import(self, handle: bytes) -> int:
+        """Map a peer's plane; the returned device pointer can be given to bind_plane."""
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self._lib.svo_ipc_import(self._h, buf, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, device_ptr: int):
+        self._check(self._lib.svo_ipc_close(self._h, C.c_void_p(device_ptr)))
 
     # -- ray streams ----------------------------------------------------------
     def cast(self, rays: np.ndarray, max_depth: int = 13) -> np.ndarray:

@@ -183,8 +183,9 @@ def test_renderer_mirror_reads_like_the_engine(svo, oracle, terrain128):
 
     # an "SDF edit": change a leaf value in place and append nothing -> updateSSBO(7, buf, start, end)
     edited = terrain128.copy()
-    solid = np.nonzero(want["hit_id"] != svo.NO_HIT)
-    ptr = int(want["hit_id"][solid[0][0], solid[1][0]])
+    hits = want["hit_id"][:, 20:]  # outside the 10x10 debug overlay (svotrace.comp:700)
+    solid = np.nonzero(hits != svo.NO_HIT)
+    ptr = int(hits[solid[0][len(solid[0]) // 2], solid[1][len(solid[0]) // 2]])
     edited[ptr] = 3 if edited[ptr] != 3 else 2
     buf[:edited.size] = edited
     r.updateSSBO(7, buf, ptr, ptr + 1)
@@ -226,3 +227,81 @@ def test_errors_are_codes_not_crashes(svo, terrain128):
         c.set_option(svo._lib.OPT_AUX_PLANES, 1)
         c.render(svo.camera_frame("A", render_mode=3))
         assert (c.read_hit_id() == svo.NO_HIT).all()
+
+
+def test_interleaved_band_partition_single_gpu(svo, oracle, terrain128):
+    """svo_render_interleaved: parts 0..2 of 3 rendered one after the other fill the same frame the oracle renders."""
+    W, H = 200, 117
+    with svo.SvoContext(W, H) as c:
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.upload(terrain128)
+        pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+        want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=7), W, H, nthreads=4)
+        f = svo.camera_frame("B", frame_number=2, render_mode=0, max_depth=7)
+        for part in (2, 0, 1):
+            c.render_interleaved(f, part, 3)
+        got = {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(),
+               "hit_id": c.read_hit_id(), "iter": c.read_iter(), "primary_t": c.read_primary_t()}
+        _assert_planes_equal(got, want, "interleaved")
+
+
+def _ipc_worker(rank, world, port, q):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import svo_raytracer_b200 as svo
+        from svo_raytracer_b200 import _lib as L
+        W, H, n = 320, 200, 128
+        hm, mm = svo.terrain_inputs(n)
+        nodes = svo.build_terrain(hm, mm, n, 64)  # replicated octree
+        ctx = svo.SvoContext(W, H, device=rank)
+        ctx.upload(nodes)
+        planes = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
+        handles = [ctx.ipc_export(p) for p in planes] if rank == 0 else [None, None]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            for p, h in zip(planes, handles):
+                ctx.bind_plane(p, ctx.ipc_import(h))
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        fence = torch.zeros(1, device="cuda")
+        f = svo.camera_frame("B", frame_number=1, render_mode=2, max_depth=7)
+        ctx.render_interleaved(f, rank, world)
+        dist.all_reduce(fence)
+        torch.cuda.synchronize()
+        if rank == 0:
+            q.put((ctx.read_color_rgba8(), ctx.read_depth()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_tiles_over_nvlink(svo, oracle):
+    """Two processes, two GPUs: each renders its interleaved bands; rank 1 stores straight into rank 0's planes through a
+    CUDA-IPC mapping (NVLink), one NCCL fence; rank 0's frame equals the oracle's."""
+    import ctypes as C
+    import socket
+    import torch.multiprocessing as mp
+    n = C.c_int()
+    svo._lib.lib().svo_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rgba, depth = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    hm, mm = svo.terrain_inputs(128)
+    nodes = svo.build_terrain(hm, mm, 128, 64)
+    pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+    want, _ = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, max_depth=7), 320, 200, nthreads=4)
+    assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32))
