@@ -78,7 +78,11 @@ enum svo_option {
   SVO_OPT_FAST_MATH = 2,   /* 0: --fmad=false validation kernels (default, bit-exact contract); 1: fma-contracted build */
   SVO_OPT_KERNEL = 3,      /* traversal kernel variant; default 0 = best measured */
   SVO_OPT_L2_PERSIST = 4,  /* 0/1: pin the upper octree levels with an L2 access-policy window; default 1 */
-  SVO_OPT_RAY_SORT = 5     /* 0/1: bin ray streams by octant/direction before tracing; default 1 */
+  SVO_OPT_RAY_SORT = 5,    /* 0/1: bin ray streams by octant/direction before tracing; default 1 */
+  SVO_OPT_CONTENT_BOUNDS = 6 /* 0/1: end casts that cannot hit anything once they are outside the bounding box of the
+                              * octree's non-empty leaves (computed at upload).  Outputs are unchanged; only the
+                              * iteration count of MISSING casts differs, so it is ignored in render mode 1 and with
+                              * SVO_OPT_AUX_PLANES.  default 1 */
 };
 
 /* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and

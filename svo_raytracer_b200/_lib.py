@@ -19,7 +19,7 @@ OK, ERR_INVALID, ERR_OOM, ERR_NO_DEVICE, ERR_CUDA, ERR_FORMAT, ERR_NO_SCENE = 0,
 # enum svo_plane
 PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIMARY_T, PLANE_RADIANCE = range(7)
 # enum svo_option
-OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT = 1, 2, 3, 4, 5
+OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS = 1, 2, 3, 4, 5, 6
 
 
 class SvoError(RuntimeError):

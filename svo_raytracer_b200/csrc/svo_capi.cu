@@ -47,7 +47,8 @@ struct svo_ctx {
   void *d_rays = nullptr, *d_hits = nullptr;
   uint64_t cast_cap = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 0;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 0, opt_bounds = 1;
+  CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   WaveWorkspace ws{};  // wavefront variant, allocated on first use
   void *ws_block = nullptr;
@@ -119,8 +120,22 @@ int ensure_wavefront(svo_ctx *c) {
   return SVO_OK;
 }
 
-SceneView scene_view(const svo_ctx *c) {
+SceneView scene_view(const svo_ctx *c, const svo_frame *frame = nullptr) {
   SceneView v;
+  // content box of the frame: leaves at any depth, plus every non-empty record at the depths where this frame's
+  // casts stop (maxDepth, and coneDepth for the cone-traced bounces), padded by 2^-9 (see Trav::setup)
+  CellBox b = c->leaf_box;
+  if (frame) {
+    b.add(c->depth_box[frame->maxDepth]);
+    b.add(c->depth_box[frame->coneDepth]);
+  } else {
+    for (const CellBox &d : c->depth_box) b.add(d);
+  }
+  for (int a = 0; a < 3; a++) {
+    if (b.empty()) { v.box_lo[a] = 4.0f; v.box_hi[a] = -4.0f; continue; }
+    v.box_lo[a] = 1.0f + (float)b.lo[a] * (1.0f / 16777216.0f) - 0.001953125f;
+    v.box_hi[a] = 1.0f + (float)b.hi[a] * (1.0f / 16777216.0f) + 0.001953125f;
+  }
   v.desc = c->d_desc;
   v.refbase = c->d_refbase;
   v.raw = c->d_raw;
@@ -133,6 +148,7 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   LaunchCfg l;
   l.fast = c->opt_fast != 0;
   l.aux = c->opt_aux != 0;
+  l.box = false;
   l.kernel = c->opt_kernel;
   l.sm_count = c->sm_count;
   l.band_stride = 0;
@@ -162,6 +178,10 @@ int check_frame(svo_ctx *c, const svo_frame *f) {
   return SVO_OK;
 }
 
+// The content-box shortcut changes only the iteration count of casts that miss; it is used where nothing shows
+// that count: not in render mode 1 (iteration heat map, svotrace.comp:561-571) and not with the validation planes.
+bool box_allowed(const svo_ctx *c, const svo_frame *f) { return c->opt_bounds && !c->opt_aux && f->renderMode != 1; }
+
 // (re)build the device descriptor arrays from the host shadow of the stream
 int retranscode(svo_ctx *c) {
   Transcoded t;
@@ -189,6 +209,8 @@ int retranscode(svo_ctx *c) {
   uint32_t w0 = 0;
   for (uint64_t i = 0; i < 4 && i < c->nbytes; i++) w0 |= c->h_raw[i];
   c->first_word_zero = (w0 == 0);
+  c->leaf_box = t.leaf_box;
+  for (int d = 0; d < 24; d++) c->depth_box[d] = t.depth_box[d];
   c->have_scene = true;
 
   // L2 access-policy window over the hot upper levels (a prefix of the BFS array)
@@ -302,6 +324,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_KERNEL: c->opt_kernel = (int)value; return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
     case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
+    case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
     default: return fail(c, SVO_ERR_INVALID, "unknown option");
   }
 }
@@ -313,6 +336,7 @@ int svo_get_option(const svo_ctx *c, int option, int64_t *value) {
     case SVO_OPT_KERNEL: *value = c->opt_kernel; return SVO_OK;
     case SVO_OPT_L2_PERSIST: *value = c->opt_l2; return SVO_OK;
     case SVO_OPT_RAY_SORT: *value = c->opt_sort; return SVO_OK;
+    case SVO_OPT_CONTENT_BOUNDS: *value = c->opt_bounds; return SVO_OK;
     default: return fail(const_cast<svo_ctx *>(c), SVO_ERR_INVALID, "unknown option");
   }
 }
@@ -399,7 +423,9 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
     c->launches += (uint64_t)wavefront_launches(fp);
     return SVO_OK;
   }
-  SVO_CUDA(c, launch_render(launch_cfg(c), scene_view(c), fp, planes_of(c), c->W, c->H, y0, y1, c->stream));
+  LaunchCfg cfg = launch_cfg(c);
+  cfg.box = box_allowed(c, frame);
+  SVO_CUDA(c, launch_render(cfg, scene_view(c, frame), fp, planes_of(c), c->W, c->H, y0, y1, c->stream));
   c->launches++;
   return SVO_OK;
 }
@@ -419,7 +445,8 @@ int svo_render_interleaved(svo_ctx *c, const svo_frame *frame, int part, int par
   cfg.kernel = 0;  // the band-interleaved partition is a feature of the tile kernel
   cfg.band_stride = parts;
   cfg.band_offset = part;
-  SVO_CUDA(c, launch_render(cfg, scene_view(c), fp, planes_of(c), c->W, c->H, 0, c->H, c->stream));
+  cfg.box = box_allowed(c, frame);
+  SVO_CUDA(c, launch_render(cfg, scene_view(c, frame), fp, planes_of(c), c->W, c->H, 0, c->H, c->stream));
   c->launches++;
   return SVO_OK;
 }

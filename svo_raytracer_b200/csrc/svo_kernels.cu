@@ -14,8 +14,8 @@ namespace svo {
 // ---------------------------------------------------------------------------
 // (CTAs are launched top to bottom: a scrambled row order was measured 5-15 % slower -- CTAs of neighbouring rows
 // running together share their octree working set in L1/L2, which outweighs the better tail balance.)
-template <bool FAST, bool AUX>
-__global__ void __launch_bounds__(128) k_render_tile(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
+template <bool FAST, bool AUX, bool BOX>
+__global__ void __launch_bounds__(128, 8) k_render_tile(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
                                                      int band_stride, int band_offset) {
   // CTA row blockIdx.y renders 8-row band number blockIdx.y * band_stride + band_offset (counted from y0): with
   // stride = number of GPUs and offset = rank this is the interleaved image partition of the multi-GPU mode.
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k_render_tile(SceneView sc, FrameParams f
   const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
   const int y = y0 + ((int)blockIdx.y * band_stride + band_offset) * 8 + (warp >> 1) * 4 + (lane >> 3);
   if (x >= W || y >= y1) return;
-  shade_pixel<FAST, AUX>(sc, f, pl, W, H, x, y);
+  shade_pixel<FAST, AUX, false, BOX>(sc, f, pl, W, H, x, y);
 }
 
 // ---------------------------------------------------------------------------
@@ -251,13 +251,17 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
   const int stride = cfg.band_stride > 0 ? cfg.band_stride : 1, offset = cfg.band_stride > 0 ? cfg.band_offset : 0;
   const dim3 grid((W + 15) / 16, bands > offset ? (bands - offset + stride - 1) / stride : 0);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+#define SVO_LAUNCH_TILE(F, A, B) k_render_tile<F, A, B><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset)
   if (cfg.fast) {
-    if (cfg.aux) k_render_tile<true, true><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset);
-    else k_render_tile<true, false><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset);
+    if (cfg.aux) SVO_LAUNCH_TILE(true, true, false);
+    else if (cfg.box) SVO_LAUNCH_TILE(true, false, true);
+    else SVO_LAUNCH_TILE(true, false, false);
   } else {
-    if (cfg.aux) k_render_tile<false, true><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset);
-    else k_render_tile<false, false><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset);
+    if (cfg.aux) SVO_LAUNCH_TILE(false, true, false);
+    else if (cfg.box) SVO_LAUNCH_TILE(false, false, true);
+    else SVO_LAUNCH_TILE(false, false, false);
   }
+#undef SVO_LAUNCH_TILE
   return cudaGetLastError();
 }
 

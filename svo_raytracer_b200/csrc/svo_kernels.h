@@ -12,6 +12,7 @@ struct SceneView {
   uint64_t nbytes;
   uint32_t ndesc;
   uint32_t first_word_zero;  // octreeBuffer[0] == 0 (svotrace.comp:696)
+  float box_lo[3], box_hi[3];  // padded bounds of everything a cast of this frame can hit (cube coordinates [1,2])
 };
 
 struct FrameParams {  // == svo_frame (include/svo_b200.h)
@@ -33,6 +34,7 @@ struct Planes {
 struct LaunchCfg {
   bool fast;     // Ops<true>: fma-contracted t arithmetic
   bool aux;      // also write hit_id / iter / primary_t / radiance
+  bool box;      // end casts that are outside the content box (SceneView::box_*)
   int kernel;    // variant selector (SVO_OPT_KERNEL)
   int sm_count;
   int band_stride, band_offset;  // tile kernel: interleaved 8-row bands (0 = all bands)

@@ -172,9 +172,14 @@ SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uin
 }
 
 // One intersectOctree call (svotrace.comp:211-432) as a resumable state machine.
-template <bool FAST, bool STATS = false>
+// BOX: also use the frame's content box (SceneView::box_*): a cast whose ray never enters the box, or has left
+// it, cannot hit anything and is ended as a miss at once.  Only the iteration count of a MISSING cast differs
+// from the reference, so callers enable it only where that count is unobservable (not render mode 1, no
+// validation planes, no ray-stream API).
+template <bool FAST, bool STATS = false, bool BOX = false>
 struct Trav {
   typedef Ops<FAST> M;
+  float tb_out;             // BOX: ray parameter at which the ray leaves the content box
   float cx, cy, cz;         // t*_coef
   float bx, by, bz;         // t*_bias
   float t_min, t_max, h;
@@ -222,7 +227,23 @@ struct Trav {
     // and in ADVANCE, so testing it at those two places is the same thing
     if (t_min > 0.05f) stop_scale = cone_stop;
     if (STATS) { rs->casts += 1u; rs->record_bytes += 7u; }  // extractNode(0) :222
+    if (BOX) {
+      // slab test in the mirrored coordinates of the traversal (the ray moves towards smaller coordinates on every
+      // axis): it enters the box through the high faces and leaves through the low ones.  The box is padded by
+      // 2^-9 and rays with a direction component below 2^-8 are exempt (their t arithmetic is too ill-conditioned
+      // to bound how far the reference's cell walk strays from the true ray), see DESIGN.md.
+      const float hx = (oct & 1u) ? 3.0f - sc.box_lo[0] : sc.box_hi[0], lx = (oct & 1u) ? 3.0f - sc.box_hi[0] : sc.box_lo[0];
+      const float hy = (oct & 2u) ? 3.0f - sc.box_lo[1] : sc.box_hi[1], ly = (oct & 2u) ? 3.0f - sc.box_hi[1] : sc.box_lo[1];
+      const float hz = (oct & 4u) ? 3.0f - sc.box_lo[2] : sc.box_hi[2], lz = (oct & 4u) ? 3.0f - sc.box_hi[2] : sc.box_lo[2];
+      const float tb_in = fmaxf(fmaxf(hx * cx - bx, hy * cy - by), fmaxf(hz * cz - bz, 0.0f));
+      tb_out = fminf(fminf(lx * cx - bx, ly * cy - by), lz * cz - bz);
+      const float dmin = fminf(fminf(fabsf(d.x), fabsf(d.y)), fabsf(d.z));
+      if (!(dmin >= 0.00390625f)) tb_out = __uint_as_float(0x7f800000u);  // exempt (also NaN directions)
+      else if (!(tb_in <= tb_out)) tb_out = -1.0f;                         // never inside the box: ends at the first POP/ADVANCE test
+    }
   }
+  // true if the cast can end now: nothing can be hit any more
+  __device__ __forceinline__ bool outside_box() const { return BOX && t_min > tb_out; }
 
   // The body of one loop iteration (:262-369), shared by run() and step().  `EXIT(status)` leaves the loop,
   // `NEXT` starts the next iteration.  The iteration cap (:264-266) is enforced where it is cheap -- on the
@@ -297,6 +318,7 @@ struct Trav {
       iter = (uint32_t)kMaxIterations + 1u;                                                                          \
       EXIT(TRAV_MISS);                                                                                               \
     }                                                                                                                \
+    if (BOX && t_min > tb_out) { EXIT(TRAV_MISS); } /* the ray has left the content box for good */                  \
     uint32_t differing_bits = 0;                                                                                     \
     if (sx) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));                           \
     if (sy) differing_bits |= __float_as_uint(py) ^ __float_as_uint(fadd(py, scale_exp2));                           \
@@ -367,12 +389,13 @@ struct Trav {
 };
 
 // intersectOctree run to completion.
-template <bool FAST, bool STATS = false>
+template <bool FAST, bool STATS = false, bool BOX = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
                                          int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr) {
   uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
-  Trav<FAST, STATS> T;
+  Trav<FAST, STATS, BOX> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
+  if (T.outside_box()) return T.finish(sc, TRAV_MISS, res, loops);  // the ray never reaches the content box
   return T.finish(sc, T.run(sc, stk, rs), res, loops);
 }
 
@@ -574,7 +597,7 @@ SVO_DI void pixel_store(const SceneView &sc, const Planes &pl, int W, Pixel &P) 
 }
 
 // main (svotrace.comp:649-729) for pixel (x, y), run to completion
-template <bool FAST, bool AUX, bool STATS = false>
+template <bool FAST, bool AUX, bool STATS = false, bool BOX = false>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                                             int x, int y, RayStats *rs = nullptr) {
   Pixel P;
@@ -582,7 +605,7 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
     bool more;
     do {
       uint32_t loops = 0;
-      const bool hit = cast_ray<FAST, STATS>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs);
+      const bool hit = cast_ray<FAST, STATS, BOX>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs);
       more = pixel_after_cast(f, P, hit, loops);
     } while (more);
   }

@@ -8,6 +8,7 @@ struct Pending {
   uint32_t off;    // byte offset of the node record (Node.descriptor, svotrace.comp:85)
   uint32_t cp;     // its childPtr (relative)
   uint32_t codes;  // its leafMask
+  uint32_t x, y, z;  // cell coordinates at the node's own depth
 };
 
 inline uint32_t rd(const uint8_t *raw, uint64_t n, uint32_t p) { return ((uint64_t)p < n) ? raw[p] : 0u; }  // getByte, out of range = 0
@@ -22,13 +23,15 @@ bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std:
   out.desc.clear();
   out.refbase.clear();
   out.level_start.clear();
+  out.leaf_box = CellBox();
+  for (CellBox &b : out.depth_box) b = CellBox();
   if (nbytes >= (1ull << 32)) {
     err = "node stream must be < 4 GiB (the engine addresses it with int32 byte offsets)";
     return false;
   }
   const uint64_t limit = (nbytes > 4096 ? nbytes : 4096);
   std::vector<Pending> cur, next;
-  cur.push_back({0u, rd_be32(raw, nbytes, 1u), rd_be16(raw, nbytes, 5u)});  // extractNode(0), svotrace.comp:222
+  cur.push_back({0u, rd_be32(raw, nbytes, 1u), rd_be16(raw, nbytes, 5u), 0u, 0u, 0u});  // extractNode(0), svotrace.comp:222
   // Tree depth D nodes have children at scale 22-D; scale 0 children (D = 22)
   // can only be hit, never entered (maxDepth <= 23), so 23 levels suffice.
   for (int depth = 0; depth <= 22 && !cur.empty(); depth++) {
@@ -45,12 +48,17 @@ bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std:
         const uint32_t value = rd(raw, nbytes, p);
         if (value != 0u) {
           nonzero |= 1u << c;
-          if (code == 0u && depth < 22) {
-            const uint32_t ccp = rd_be32(raw, nbytes, p + 1u);
-            if (ccp != 0u) {  // child.cp != 0: the traversal may PUSH into it (:311)
-              has_desc |= 1u << c;
-              next.push_back({p, ccp, rd_be16(raw, nbytes, p + 5u)});
-            }
+          const uint32_t cx = 2u * nd.x + (c & 1u), cy = 2u * nd.y + ((c >> 1) & 1u), cz = 2u * nd.z + ((c >> 2) & 1u);
+          const int cdepth = depth + 1, sh = 24 - cdepth;  // child cells are at tree depth depth+1 <= 23
+          CellBox cell;
+          cell.lo[0] = cx << sh; cell.lo[1] = cy << sh; cell.lo[2] = cz << sh;
+          cell.hi[0] = (cx + 1u) << sh; cell.hi[1] = (cy + 1u) << sh; cell.hi[2] = (cz + 1u) << sh;
+          out.depth_box[cdepth].add(cell);
+          const uint32_t ccp = code == 0u ? rd_be32(raw, nbytes, p + 1u) : 0u;
+          if (ccp == 0u) out.leaf_box.add(cell);  // child.cp == 0: a hit wherever the traversal meets it (:311)
+          else if (depth < 22) {                  // child.cp != 0: the traversal may PUSH into it
+            has_desc |= 1u << c;
+            next.push_back({p, ccp, rd_be16(raw, nbytes, p + 5u), cx, cy, cz});
           }
         }
         p += size;

@@ -18,10 +18,29 @@
 
 namespace svo {
 
+// Axis-aligned box of octree cells in integer cell units of depth 24 (cube edge = 2^24), empty if lo > hi.
+struct CellBox {
+  uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  uint32_t hi[3] = {0u, 0u, 0u};
+  bool empty() const { return lo[0] > hi[0]; }
+  void add(const CellBox &o) {
+    for (int a = 0; a < 3; a++) {
+      if (o.lo[a] < lo[a]) lo[a] = o.lo[a];
+      if (o.hi[a] > hi[a]) hi[a] = o.hi[a];
+    }
+  }
+};
+
 struct Transcoded {
   std::vector<uint2> desc;
   std::vector<uint32_t> refbase;
   std::vector<uint32_t> level_start;  // desc index where each BFS level begins
+  // Where a cast can end in a hit: `leaf_box` bounds every record with value != 0 that the traversal treats
+  // as a leaf (child.cp == 0, svotrace.comp:311), `depth_box[d]` bounds every record with value != 0 at tree
+  // depth d (a cast stops there when d == maxDepth, svotrace.comp:300).  Rays outside the union of the boxes
+  // that apply to a frame cannot hit anything.
+  CellBox leaf_box;
+  CellBox depth_box[24];
 };
 
 // Returns false (with `err` set) if the stream cannot be a tree (more

@@ -305,3 +305,41 @@ def test_two_gpu_tiles_over_nvlink(svo, oracle):
     pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
     want, _ = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, max_depth=7), 320, 200, nthreads=4)
     assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32))
+
+
+@pytest.mark.parametrize("cam", ["A", "B", "C"])
+@pytest.mark.parametrize("mode", [0, 2, 3, 4])
+def test_content_bounds_fast_path_keeps_outputs(svo, oracle, terrain512, cam, mode):
+    """Production configuration (no validation planes): casts that are outside the bounding box of the octree's
+    non-empty leaves are ended early (SVO_OPT_CONTENT_BOUNDS).  The reference's outputs -- colour and depth -- must
+    not change by a bit; with the option off they must not either."""
+    pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+    want, _ = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=4, render_mode=mode), 640, 360,
+                            nthreads=8, planes=("rgba8", "depth"))
+    with svo.SvoContext(640, 360) as c:
+        c.upload(terrain512)
+        for bounds in (1, 0):
+            c.set_option(svo._lib.OPT_CONTENT_BOUNDS, bounds)
+            assert c.get_option(svo._lib.OPT_CONTENT_BOUNDS) == bounds
+            c.render(svo.camera_frame(cam, frame_number=4, render_mode=mode))
+            assert np.array_equal(c.read_color_rgba8(), want["rgba8"]), (cam, mode, bounds)
+            d = c.read_depth()
+            assert np.array_equal(d.view(np.uint32), want["depth"].view(np.uint32)), (cam, mode, bounds)
+
+
+def test_content_bounds_inside_camera_and_shallow_depths(svo, oracle, terrain128):
+    """Cameras inside the terrain's bounding box, looking up and sideways, and maxDepth values at which interior
+    (fill-level) nodes become hits: the box must follow the frame's maxDepth / coneDepth."""
+    W, H = 160, 96
+    cams = [((1.5, 1.05, 1.5), (-1, 0.2, -1), (-1, 1.5, -1), (1, 0.2, -1), (1, 1.5, -1)),
+            ((1.2, 1.12, 1.8), (-1.6, -0.9, -1), (-1.6, 0.9, -1), (1.6, -0.9, -1), (1.6, 0.9, -1)),
+            ((1.5, 1.5, 2.0), (-1.6, -0.9, -1), (-1.6, 0.9, -1), (1.6, -0.9, -1), (1.6, 0.9, -1))]
+    with svo.SvoContext(W, H) as c:
+        c.upload(terrain128)
+        for cam in cams:
+            for max_depth, cone_depth, mode in ((7, 11, 0), (7, 5, 0), (1, 11, 2), (3, 2, 0), (5, 11, 3)):
+                want, _ = oracle.render(terrain128, oracle.make_frame(*cam, frame_number=1, render_mode=mode, max_depth=max_depth,
+                                                                      cone_depth=cone_depth), W, H, nthreads=4, planes=("rgba8", "depth"))
+                c.render(svo.make_frame(*cam, frame_number=1, render_mode=mode, max_depth=max_depth, cone_depth=cone_depth))
+                assert np.array_equal(c.read_color_rgba8(), want["rgba8"]), (cam[0], max_depth, cone_depth, mode)
+                assert np.array_equal(c.read_depth().view(np.uint32), want["depth"].view(np.uint32))

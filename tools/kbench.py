@@ -20,10 +20,11 @@ ctx = svo.SvoContext(W, H)
 ctx.upload(nodes)
 stats = {c: ctx.render_stats(svo.camera_frame(c, frame_number=1, render_mode=mode, max_depth=depth)) for c in "ABC"}
 for v in variants:
-    fast = v.endswith("f")
-    k = int(v.rstrip("f"))
+    fast = "f" in v
+    k = int(v.rstrip("fn"))
     ctx.set_option(L.OPT_KERNEL, k)
     ctx.set_option(L.OPT_FAST_MATH, int(fast))
+    ctx.set_option(L.OPT_CONTENT_BOUNDS, 0 if "n" in v else 1)
     line = []
     tot_ms, tot_rays = 0.0, 0
     for cam in "ABC":
