@@ -142,6 +142,8 @@ SceneView scene_view(const svo_ctx *c, const svo_frame *frame = nullptr) {
   v.nbytes = c->nbytes;
   v.ndesc = c->ndesc;
   v.first_word_zero = c->first_word_zero;
+  v.top = nullptr;
+  v.ntop = 0;
   return v;
 }
 LaunchCfg launch_cfg(const svo_ctx *c) {

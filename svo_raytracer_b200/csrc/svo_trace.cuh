@@ -176,9 +176,15 @@ SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uin
 // it, cannot hit anything and is ended as a miss at once.  Only the iteration count of a MISSING cast differs
 // from the reference, so callers enable it only where that count is unobservable (not render mode 1, no
 // validation planes, no ray-stream API).
-template <bool FAST, bool STATS = false, bool BOX = false>
+// TOP: the first sc.ntop descriptors (the upper octree levels: the array is breadth-first) are read from a
+// shared-memory copy (sc.top) instead of global memory.
+template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
 struct Trav {
   typedef Ops<FAST> M;
+  static __device__ __forceinline__ uint2 fetch(const SceneView &sc, uint32_t i) {
+    if (TOP && i < sc.ntop) return sc.top[i];
+    return __ldg(sc.desc + i);
+  }
   float tb_out;             // BOX: ray parameter at which the ray leaves the content box
   float cx, cy, cz;         // t*_coef
   float bx, by, bz;         // t*_bias
@@ -219,7 +225,7 @@ struct Trav {
     if (M::msub(1.5f, cy, by) > t_min) { idx ^= 2u; py = 1.5f; }
     if (M::msub(1.5f, cz, bz) > t_min) { idx ^= 4u; pz = 1.5f; }
     pidx = 0;               // parent = root (:222)
-    pd = __ldg(sc.desc);
+    pd = fetch(sc, 0u);
     iter = 0;
     stop_scale = kMaxScale - maxDepth;
     cone_stop = coneTrace ? kMaxScale - coneDepth : stop_scale;
@@ -274,7 +280,7 @@ struct Trav {
       }                                                                                                              \
       h = tc_max;                                                                                                    \
       pidx = pd.x + __popc(pd.y & (bit24 - 0x01000000u)); /* descriptors of the interior siblings below */           \
-      pd = __ldg(sc.desc + pidx);                          /* parent = child (:322) */                               \
+      pd = fetch(sc, pidx);                                /* parent = child (:322) */                               \
       const float half = M::mul(scale_exp2, 0.5f);                                                                   \
       const float tx_center = M::madd(half, cx, tx_corner); /* :306-308 */                                           \
       const float ty_center = M::madd(half, cy, ty_corner);                                                          \
@@ -329,7 +335,7 @@ struct Trav {
     const uint2 se = stk[scale];                                                                                     \
     pidx = se.x;                                                                                                     \
     t_max = __uint_as_float(se.y);                                                                                   \
-    pd = __ldg(sc.desc + pidx);                                                                                      \
+    pd = fetch(sc, pidx);                                                                                            \
     const uint32_t shx = __float_as_uint(px) >> scale;                                                               \
     const uint32_t shy = __float_as_uint(py) >> scale;                                                               \
     const uint32_t shz = __float_as_uint(pz) >> scale;                                                               \
@@ -389,11 +395,11 @@ struct Trav {
 };
 
 // intersectOctree run to completion.
-template <bool FAST, bool STATS = false, bool BOX = false>
+template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
                                          int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr) {
   uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
-  Trav<FAST, STATS, BOX> T;
+  Trav<FAST, STATS, BOX, TOP> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
   if (T.outside_box()) return T.finish(sc, TRAV_MISS, res, loops);  // the ray never reaches the content box
   return T.finish(sc, T.run(sc, stk, rs), res, loops);
@@ -597,7 +603,7 @@ SVO_DI void pixel_store(const SceneView &sc, const Planes &pl, int W, Pixel &P) 
 }
 
 // main (svotrace.comp:649-729) for pixel (x, y), run to completion
-template <bool FAST, bool AUX, bool STATS = false, bool BOX = false>
+template <bool FAST, bool AUX, bool STATS = false, bool BOX = false, bool TOP = false>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                                             int x, int y, RayStats *rs = nullptr) {
   Pixel P;
@@ -605,7 +611,7 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
     bool more;
     do {
       uint32_t loops = 0;
-      const bool hit = cast_ray<FAST, STATS, BOX>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs);
+      const bool hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs);
       more = pixel_after_cast(f, P, hit, loops);
     } while (more);
   }

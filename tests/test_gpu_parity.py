@@ -307,9 +307,10 @@ def test_two_gpu_tiles_over_nvlink(svo, oracle):
     assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32))
 
 
+@pytest.mark.parametrize("kernel", [0, 4])
 @pytest.mark.parametrize("cam", ["A", "B", "C"])
 @pytest.mark.parametrize("mode", [0, 2, 3, 4])
-def test_content_bounds_fast_path_keeps_outputs(svo, oracle, terrain512, cam, mode):
+def test_content_bounds_fast_path_keeps_outputs(svo, oracle, terrain512, cam, mode, kernel):
     """Production configuration (no validation planes): casts that are outside the bounding box of the octree's
     non-empty leaves are ended early (SVO_OPT_CONTENT_BOUNDS).  The reference's outputs -- colour and depth -- must
     not change by a bit; with the option off they must not either."""
@@ -317,6 +318,7 @@ def test_content_bounds_fast_path_keeps_outputs(svo, oracle, terrain512, cam, mo
     want, _ = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=4, render_mode=mode), 640, 360,
                             nthreads=8, planes=("rgba8", "depth"))
     with svo.SvoContext(640, 360) as c:
+        c.set_option(svo._lib.OPT_KERNEL, kernel)  # 4 = upper levels staged in shared memory
         c.upload(terrain512)
         for bounds in (1, 0):
             c.set_option(svo._lib.OPT_CONTENT_BOUNDS, bounds)

@@ -21,7 +21,10 @@ ctx.upload(nodes)
 stats = {c: ctx.render_stats(svo.camera_frame(c, frame_number=1, render_mode=mode, max_depth=depth)) for c in "ABC"}
 for v in variants:
     fast = "f" in v
-    k = int(v.rstrip("fn"))
+    k = int(v.rstrip("fnp"))
+    if "p" in v:  # L2 access-policy window over the descriptor prefix (takes effect at upload)
+        ctx.set_option(L.OPT_L2_PERSIST, 1)
+        ctx.upload(nodes)
     ctx.set_option(L.OPT_KERNEL, k)
     ctx.set_option(L.OPT_FAST_MATH, int(fast))
     ctx.set_option(L.OPT_CONTENT_BOUNDS, 0 if "n" in v else 1)
