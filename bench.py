@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
                     help="N>1: frames = rank r renders progressive sample s*N+r of each view (weak scaling, no collective); "
                          "tiles = ONE frame per step split in interleaved 8-row bands, peers store straight into rank 0's "
@@ -76,16 +77,23 @@ def frame_for(step: int, size: int):
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        self.t0 = self.t1 = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.p is None:
@@ -98,19 +106,27 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, all_sm = [], [], set(), []
         for line in self.f:
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(c[2]), float(c[3])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+            all_sm.append(clk)
+            mx.append(cmax)
+            if self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                continue  # only samples taken DURING the timed region
+            sm.append(clk)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        if not sm:  # region shorter than the sampling period: fall back to the samples around it
+            sm = all_sm[-3:]
         self.f.close()
         os.unlink(self.f.name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -202,11 +218,40 @@ def main():
             for plane, h in zip((L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH), handles):
                 ctx.bind_plane(plane, ctx.ipc_import(h))
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        fence = torch.zeros(1, device="cuda")
+        if a.fence == "nccl":
+            fence = torch.zeros(1, device="cuda")
 
-        def render_step(s):
-            ctx.render_interleaved(frames[s], rank, world_size)
-            dist.all_reduce(fence)  # stream-ordered frame-complete fence: after it rank 0's planes hold the whole frame
+            def render_step(s, consume=None, release=False):
+                ctx.render_interleaved(frames[s], rank, world_size)
+                dist.all_reduce(fence)  # stream-ordered frame-complete fence: after it rank 0's planes hold the whole frame
+                if consume is not None:
+                    consume()
+                if release:
+                    dist.all_reduce(fence)  # the frame has been consumed: peers may overwrite the planes
+        else:
+            # fences are counters in GPU memory bumped by remote atomics over NVLink (svo_fence_*): no collective
+            fh = [None] * world_size
+            dist.all_gather_object(fh, ctx.fence_export())
+            if rank == 0:
+                peer_fences = [ctx.ipc_import(fh[r]) for r in range(1, world_size)]
+            else:
+                owner_fence = [ctx.ipc_import(fh[0])]
+            done = [0]
+
+            def render_step(s, consume=None, release=False):
+                k = done[0]
+                done[0] += 1
+                if rank == 0:
+                    ctx.render_interleaved(frames[s], 0, world_size)
+                    ctx.fence_signal()
+                    ctx.fence_wait((k + 1) * world_size)  # every GPU has stored its bands of frame k
+                    if consume is not None:
+                        consume()
+                    ctx.fence_signal(peer_fences)        # frame k consumed: the peers may overwrite the planes
+                else:
+                    ctx.fence_wait(k)                     # the owner has consumed frames 0..k-1
+                    ctx.render_interleaved(frames[s], rank, world_size)
+                    ctx.fence_signal(owner_fence)
     else:
         # Units: rank r renders its own progressive sample (frameNumber) of the same views -- independent units, no
         # data-path collective (weak scaling); step s on rank r is sample s*N + r.
@@ -216,8 +261,10 @@ def main():
             return f
         frames = [my_frame(s) for s in range(total)]
 
-        def render_step(s):
+        def render_step(s, consume=None, release=False):
             ctx.render(frames[s])
+            if consume is not None:
+                consume()
 
     # rays per frame and algorithmic bytes (instrumented kernel, outside the timed region; casts do not depend on the
     # RNG sample: a bounce is cast iff the primary ray hit)
@@ -241,16 +288,18 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------
+    clocks = ClockSampler(dev)  # started early: nvidia-smi needs ~100 ms before its first sample
     for s in range(a.warmup):
         render_step(s)
     ctx.sync()
     barrier()
-    clocks = ClockSampler(dev)
     launches0 = ctx.launch_count()
+    clocks.begin()
     ctx.timer_begin()
     for s in range(a.warmup, total):
         render_step(s)
     dev_ms = ctx.timer_end()
+    clocks.end()
     launches = ctx.launch_count() - launches0
     barrier()
     clk = clocks.stop()
@@ -264,11 +313,12 @@ def main():
     depth_h = torch.empty((H, W), dtype=torch.float32).pin_memory()
     reads = rank == 0 or not tiles  # tiles: only rank 0 holds the frame
 
+    def readback():
+        ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
+        ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
+
     def e2e_step(s):
-        render_step(s)  # the 92-byte svo_frame is read from host memory by the call
-        if reads:
-            ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
-            ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
+        render_step(s, readback if reads else None, True)  # the 92-byte svo_frame is read from host memory by the call
     for s in range(a.warmup):
         e2e_step(s)
     barrier()
@@ -331,7 +381,7 @@ def main():
                    "fast_math": a.fast_math, "kernel": a.kernel, "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
                    "world_build_s": round(build_s, 2), "upload_transcode_s": round(upload_s, 2),
                    "units": ("one frame per step, interleaved 8-row bands per rank, peers store into rank 0's planes over NVLink, "
-                             "one NCCL all-reduce fence per frame") if tiles else
+                             "frame-complete fence = " + ("remote atomics over NVLink" if a.fence == "p2p" else "NCCL all-reduce")) if tiles else
                             "rank r renders progressive sample s*N+r of each view; no data-path collective"},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,

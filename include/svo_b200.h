@@ -140,14 +140,27 @@ void *svo_device_ptr(svo_ctx *ctx, int plane);
  * buffer mapped over NVLink); NULL restores the context's own allocation */
 int svo_bind_plane(svo_ctx *ctx, int plane, void *device_ptr);
 
-/* Multi-GPU frame buffers over NVLink (one process per GPU).  svo_ipc_export fills a 64-byte
- * handle (cudaIpcMemHandle_t) for one of this context's own planes; the owning process sends it
- * to its peers by any means; svo_ipc_import maps it in the peer process and returns a device
- * pointer that svo_bind_plane accepts, so a peer's kernel stores its image tiles straight into
- * the owner's plane (no gather step).  svo_ipc_close unmaps. */
-int svo_ipc_export(svo_ctx *ctx, int plane, uint8_t handle[64]);
-int svo_ipc_import(svo_ctx *ctx, const uint8_t handle[64], void **device_ptr);
+/* Multi-GPU frame buffers over NVLink (one process per GPU).  svo_ipc_export fills a 72-byte
+ * handle (cudaIpcMemHandle_t of the memory block + the plane's offset inside it) for one of this
+ * context's own planes; the owning process sends it to its peers by any means; svo_ipc_import maps
+ * it in the peer process and returns a device pointer that svo_bind_plane accepts, so a peer's
+ * kernel stores its image tiles straight into the owner's plane (no gather step).  svo_ipc_close
+ * unmaps everything the context imported. */
+#define SVO_IPC_HANDLE_BYTES 72
+int svo_ipc_export(svo_ctx *ctx, int plane, uint8_t handle[SVO_IPC_HANDLE_BYTES]);
+int svo_ipc_import(svo_ctx *ctx, const uint8_t handle[SVO_IPC_HANDLE_BYTES], void **device_ptr);
 int svo_ipc_close(svo_ctx *ctx, void *device_ptr);
+/* Stream-ordered fences between the GPUs of the tile partition, without a collective.  Every context owns a
+ * counter; svo_fence_export gives its IPC handle (-> svo_ipc_import in the other processes).
+ * svo_fence_signal(ctx, ptrs, n) enqueues one kernel that, after everything already in the stream, adds 1 to each
+ * of the n counters (n = 0: the context's own counter); svo_fence_wait(ctx, target) enqueues a kernel that waits
+ * until the context's own counter has reached `target` (modulo 2^32; gives up after ~2 s so that a dead peer
+ * cannot hang the GPU).  Protocol of bench.py --partition tiles: peers signal the frame owner when their bands
+ * are stored ("frame complete" = frames * n_gpus), the owner signals the peers when it has consumed the frame. */
+int svo_fence_export(svo_ctx *ctx, uint8_t handle[SVO_IPC_HANDLE_BYTES]);
+int svo_fence_signal(svo_ctx *ctx, void *const *fence_ptrs, int n);
+int svo_fence_wait(svo_ctx *ctx, uint32_t target);
+int svo_fence_reset(svo_ctx *ctx);
 
 /* -- ray streams (new): n independent intersectOctree calls.
  *    svo_cast: host buffers in/out.  svo_cast_device: device buffers. */

@@ -70,6 +70,10 @@ SYMBOLS = {
     "svo_ipc_export": (_i, [_vp, _i, _vp]),
     "svo_ipc_import": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "svo_ipc_close": (_i, [_vp, _vp]),
+    "svo_fence_export": (_i, [_vp, _vp]),
+    "svo_fence_signal": (_i, [_vp, C.POINTER(_vp), _i]),
+    "svo_fence_wait": (_i, [_vp, C.c_uint32]),
+    "svo_fence_reset": (_i, [_vp]),
     "svo_cast": (_i, [_vp, _vp, _u64, _vp, _i]),
     "svo_cast_device": (_i, [_vp, _vp, _u64, _vp, _i]),
     "svo_timer_begin": (_i, [_vp]),

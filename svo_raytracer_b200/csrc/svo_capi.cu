@@ -50,6 +50,9 @@ struct svo_ctx {
   int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 0, opt_bounds = 1;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
+  unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
+  struct IpcMap { cudaIpcMemHandle_t handle; void *base; };
+  std::vector<IpcMap> ipc_maps;  // peer blocks opened by svo_ipc_import
   WaveWorkspace ws{};  // wavefront variant, allocated on first use
   void *ws_block = nullptr;
   int ctas_per_sm = 8;
@@ -180,6 +183,30 @@ int check_frame(svo_ctx *c, const svo_frame *f) {
   return SVO_OK;
 }
 
+// cudaIpcGetMemHandle names the whole cudaMalloc block that contains a pointer and cudaIpcOpenMemHandle returns
+// that block's base (small allocations share a block), so the handle blob carries the offset as well:
+// bytes [0,64) cudaIpcMemHandle_t, bytes [64,72) offset of the exported pointer inside its block.
+int export_handle(svo_ctx *c, void *ptr, uint8_t handle[72]) {
+  typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+  static GetRange get_range = nullptr;
+  if (!get_range) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+      return fail(c, SVO_ERR_CUDA, "cuMemGetAddressRange is not available");
+    get_range = (GetRange)fn;
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0) return fail(c, SVO_ERR_CUDA, "cuMemGetAddressRange failed");
+  cudaIpcMemHandle_t hnd;
+  SVO_CUDA(c, cudaIpcGetMemHandle(&hnd, (void *)(uintptr_t)base));
+  memcpy(handle, &hnd, 64);
+  const uint64_t off = (uint64_t)(uintptr_t)ptr - base;
+  memcpy(handle + 64, &off, 8);
+  return SVO_OK;
+}
+
 // The content-box shortcut changes only the iteration count of casts that miss; it is used where nothing shows
 // that count: not in render mode 1 (iteration heat map, svotrace.comp:561-571) and not with the validation planes.
 bool box_allowed(const svo_ctx *c, const svo_frame *f) { return c->opt_bounds && !c->opt_aux && f->renderMode != 1; }
@@ -282,6 +309,8 @@ int svo_create(svo_ctx **out, int device, int width, int height) {
     c->stream = c->own_stream;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
     if ((e = cudaMalloc((void **)&c->d_tile_counter, 64)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(counter)"); break; }
+    if ((e = cudaMalloc((void **)&c->d_fence, 256)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(fence)"); break; }
+    cudaMemsetAsync(c->d_fence, 0, 256, c->stream);
     for (int p = SVO_PLANE_COLOR_RGBA8; p <= SVO_PLANE_BEAM; p++) {
       size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
       if ((e = cudaMalloc(&c->own[p], bytes ? bytes : 16)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(plane)"); break; }
@@ -300,6 +329,7 @@ void svo_destroy(svo_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  for (auto &m : c->ipc_maps) cudaIpcCloseMemHandle(m.base);
   for (int p = 0; p < 7; p++)
     if (c->own[p]) cudaFree(c->own[p]);
   if (c->d_raw) cudaFree(c->d_raw);
@@ -308,6 +338,7 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_rays) cudaFree(c->d_rays);
   if (c->d_hits) cudaFree(c->d_hits);
   if (c->d_tile_counter) cudaFree(c->d_tile_counter);
+  if (c->d_fence) cudaFree(c->d_fence);
   if (c->ws_block) cudaFree(c->ws_block);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -525,7 +556,7 @@ int svo_bind_plane(svo_ctx *c, int plane, void *device_ptr) {
   return SVO_OK;
 }
 
-int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[64]) {
+int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[72]) {
   if (!c || !handle) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
   if (plane < 0 || plane > SVO_PLANE_RADIANCE) return fail(c, SVO_ERR_INVALID, "bad plane");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
@@ -535,24 +566,72 @@ int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[64]) {
     if (rc) return rc;
   }
   if (!c->own[plane]) return fail(c, SVO_ERR_INVALID, "plane not allocated");
-  cudaIpcMemHandle_t hnd;
-  SVO_CUDA(c, cudaIpcGetMemHandle(&hnd, c->own[plane]));
-  memcpy(handle, &hnd, 64);
+  return export_handle(c, c->own[plane], handle);
+}
+int svo_fence_export(svo_ctx *c, uint8_t handle[72]) {
+  if (!c || !handle) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  return export_handle(c, c->d_fence, handle);
+}
+int svo_fence_signal(svo_ctx *c, void *const *fence_ptrs, int n) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (n < 0 || n > 16 || (n > 0 && !fence_ptrs)) return fail(c, SVO_ERR_INVALID, "bad fence list (at most 16)");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  FenceList fl;
+  fl.n = n > 0 ? n : 1;
+  for (int i = 0; i < 16; i++) fl.p[i] = nullptr;
+  if (n == 0) fl.p[0] = c->d_fence;
+  for (int i = 0; i < n; i++) fl.p[i] = (unsigned int *)fence_ptrs[i];
+  SVO_CUDA(c, launch_fence_signal(fl, c->stream));
+  c->launches++;
   return SVO_OK;
 }
-int svo_ipc_import(svo_ctx *c, const uint8_t handle[64], void **device_ptr) {
+int svo_fence_wait(svo_ctx *c, uint32_t target) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, launch_fence_wait(c->d_fence, target, c->stream));
+  c->launches++;
+  return SVO_OK;
+}
+int svo_fence_reset(svo_ctx *c) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaMemsetAsync(c->d_fence, 0, 256, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SVO_OK;
+}
+
+int svo_ipc_import(svo_ctx *c, const uint8_t handle[72], void **device_ptr) {
   if (!c || !handle || !device_ptr) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
   SVO_CUDA(c, cudaSetDevice(c->device));
   cudaIpcMemHandle_t hnd;
   memcpy(&hnd, handle, 64);
-  SVO_CUDA(c, cudaIpcOpenMemHandle(device_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+  uint64_t off = 0;
+  memcpy(&off, handle + 64, 8);
+  // one block may be imported several times (planes and fences can share it): open it once per process
+  for (auto &m : c->ipc_maps)
+    if (memcmp(&m.handle, &hnd, 64) == 0) {
+      *device_ptr = (char *)m.base + off;
+      return SVO_OK;
+    }
+  void *base = nullptr;
+  SVO_CUDA(c, cudaIpcOpenMemHandle(&base, hnd, cudaIpcMemLazyEnablePeerAccess));
+  svo_ctx::IpcMap m;
+  m.handle = hnd;
+  m.base = base;
+  c->ipc_maps.push_back(m);
+  *device_ptr = (char *)base + off;
   return SVO_OK;
 }
 int svo_ipc_close(svo_ctx *c, void *device_ptr) {
-  if (!c || !device_ptr) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  // unmaps every block this context imported (device_ptr is accepted for symmetry with svo_ipc_import)
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  (void)device_ptr;
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
-  SVO_CUDA(c, cudaIpcCloseMemHandle(device_ptr));
+  for (auto &m : c->ipc_maps) cudaIpcCloseMemHandle(m.base);
+  c->ipc_maps.clear();
+  cudaGetLastError();
   return SVO_OK;
 }
 

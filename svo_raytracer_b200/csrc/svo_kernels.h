@@ -63,6 +63,9 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
                           int y0, int y1, cudaStream_t stream);
 cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1,
                                 unsigned long long *d_counters, cudaStream_t stream);
+struct FenceList { unsigned int *p[16]; int n; };
+cudaError_t launch_fence_signal(const FenceList &fl, cudaStream_t stream);
+cudaError_t launch_fence_wait(unsigned int *fence, unsigned int target, cudaStream_t stream);
 cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int blocks, uint32_t *sink, cudaStream_t stream);
 cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d_rays, const uint32_t *d_order, uint64_t n,
                         void *d_out, int maxDepth, cudaStream_t stream);

@@ -182,17 +182,35 @@ class SvoContext:
         self._check(self._lib.svo_bind_plane(self._h, plane, C.c_void_p(device_ptr or 0)))
 
     def ipc_export(self, plane: int) -> bytes:
-        """64-byte CUDA IPC handle of one of this context's own planes (send it to the peer processes)."""
-        buf = (C.c_uint8 * 64)()
+        """72-byte IPC handle of one of this context's own planes (send it to the peer processes)."""
+        buf = (C.c_uint8 * 72)()
         self._check(self._lib.svo_ipc_export(self._h, plane, buf))
         return bytes(buf)
 
     def ipc_import(self, handle: bytes) -> int:
         """Map a peer's plane; the returned device pointer can be given to bind_plane."""
-        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        buf = (C.c_uint8 * 72).from_buffer_copy(handle)
         p = C.c_void_p()
         self._check(self._lib.svo_ipc_import(self._h, buf, C.byref(p)))
         return int(p.value)
+
+    def fence_export(self) -> bytes:
+        buf = (C.c_uint8 * 72)()
+        self._check(self._lib.svo_fence_export(self._h, buf))
+        return bytes(buf)
+
+    def fence_signal(self, fence_ptrs: Sequence[int] = ()):
+        """Enqueue: add 1 to each of the given (imported) fence counters; none given = this context's own."""
+        n = len(fence_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(p) for p in fence_ptrs])
+        self._check(self._lib.svo_fence_signal(self._h, arr, n))
+
+    def fence_wait(self, target: int):
+        """Enqueue on the owner: wait until the counter reaches `target` (modulo 2^32)."""
+        self._check(self._lib.svo_fence_wait(self._h, target & 0xFFFFFFFF))
+
+    def fence_reset(self):
+        self._check(self._lib.svo_fence_reset(self._h))
 
     def ipc_close(self, device_ptr: int):
         self._check(self._lib.svo_ipc_close(self._h, C.c_void_p(device_ptr)))

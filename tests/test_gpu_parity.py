@@ -267,14 +267,26 @@ def _ipc_worker(rank, world, port, q):
         if rank != 0:
             for p, h in zip(planes, handles):
                 ctx.bind_plane(p, ctx.ipc_import(h))
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        fence = torch.zeros(1, device="cuda")
+        # frame-complete fence without a collective: counters bumped by remote atomics over NVLink
+        fh = [None] * world
+        dist.all_gather_object(fh, ctx.fence_export())
         f = svo.camera_frame("B", frame_number=1, render_mode=2, max_depth=7)
-        ctx.render_interleaved(f, rank, world)
-        dist.all_reduce(fence)
-        torch.cuda.synchronize()
+        for k in range(3):  # three frames: the peer may not overwrite a frame the owner has not consumed
+            if rank == 0:
+                peers = [ctx.ipc_import(fh[r]) for r in range(1, world)] if k == 0 else peers
+                ctx.render_interleaved(f, 0, world)
+                ctx.fence_signal()
+                ctx.fence_wait((k + 1) * world)
+                rgba, depth = ctx.read_color_rgba8(), ctx.read_depth()  # consume (stream-ordered after the wait)
+                ctx.fence_signal(peers)
+            else:
+                owner = [ctx.ipc_import(fh[0])] if k == 0 else owner
+                ctx.fence_wait(k)
+                ctx.render_interleaved(f, rank, world)
+                ctx.fence_signal(owner)
+        ctx.sync()
         if rank == 0:
-            q.put((ctx.read_color_rgba8(), ctx.read_depth()))
+            q.put((rgba, depth))
         dist.barrier()
     finally:
         dist.destroy_process_group()
