@@ -195,6 +195,12 @@ int svo_math_probe(svo_ctx *ctx, int fn, const float *x, const float *y, float *
 int svo_build_terrain(const uint16_t *height, const uint8_t *mat, int n, int chunk, uint8_t *out,
                       uint64_t cap, uint64_t *out_bytes, int nthreads);
 
+/* Host-only view of the upload-time transcode (tests; no device needed): out[0] descriptors, [1] levels,
+ * [2] FNV-1a hash of (descriptor.x, descriptor.y, reference child-block offset) over all descriptors, [3] 1 if
+ * nothing in the tree can be hit, [4..6] x/y/z bounds of the non-empty leaves as (lo << 32 | hi) in units of
+ * 2^-24 of the cube edge, [7] hash of the per-depth bounds.  desc_out (optional) receives the triples. */
+int svo_transcode_probe(const uint8_t *nodes, uint64_t nbytes, int nthreads, uint64_t out[8], uint32_t *desc_out, uint64_t desc_cap);
+
 /* Deterministic synthetic inputs for benchmarks and tests (the reference's
  * 8192^2 heightmap / material PNGs are absent upstream): n*n u16 heights with
  * the value span of assets/heightmaps/nz.png and n*n u8 materials in {1,2,3}.

@@ -83,6 +83,7 @@ SYMBOLS = {
     "svo_gather_probe": (_i, [_vp, _u64, _i, C.POINTER(C.c_double)]),
     "svo_math_probe": (_i, [_vp, _i, _vp, _vp, _vp, _u64]),
     "svo_terrain_generate": (_i, [_i, _i, _vp, _vp, _i]),
+    "svo_transcode_probe": (_i, [_vp, _u64, _i, C.POINTER(_u64 * 8), _vp, _u64]),
     "svo_build_terrain": (_i, [_vp, _vp, _i, _i, _vp, _u64, C.POINTER(_u64), _i]),
 }
 

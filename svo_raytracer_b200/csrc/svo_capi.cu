@@ -690,6 +690,32 @@ int svo_launch_count(const svo_ctx *c, uint64_t *count) {
   return SVO_OK;
 }
 
+int svo_transcode_probe(const uint8_t *nodes, uint64_t nbytes, int nthreads, uint64_t out[8], uint32_t *desc_out, uint64_t desc_cap) {
+  if ((!nodes && nbytes) || !out) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  Transcoded t;
+  std::string err;
+  if (!transcode_stream(nodes, nbytes, t, err, nthreads)) return fail(nullptr, SVO_ERR_FORMAT, err);
+  uint64_t h = 1469598103934665603ull;  // FNV-1a over descriptors and reference offsets
+  auto mix = [&](uint32_t v) { for (int i = 0; i < 4; i++) { h ^= (v >> (8 * i)) & 0xFFu; h *= 1099511628211ull; } };
+  for (size_t i = 0; i < t.desc.size(); i++) { mix(t.desc[i].x); mix(t.desc[i].y); mix(t.refbase[i]); }
+  out[0] = t.desc.size();
+  out[1] = t.level_start.size();
+  out[2] = h;
+  CellBox b = t.leaf_box;
+  for (const CellBox &d : t.depth_box) b.add(d);
+  out[3] = b.empty();
+  out[4] = ((uint64_t)t.leaf_box.lo[0] << 32) | t.leaf_box.hi[0];
+  out[5] = ((uint64_t)t.leaf_box.lo[1] << 32) | t.leaf_box.hi[1];
+  out[6] = ((uint64_t)t.leaf_box.lo[2] << 32) | t.leaf_box.hi[2];
+  out[7] = 0;
+  for (const CellBox &d : t.depth_box) out[7] = out[7] * 31 + d.lo[1] + 7 * d.hi[1];
+  if (desc_out)
+    for (size_t i = 0; i < t.desc.size() && 3 * i + 2 < desc_cap; i++) {
+      desc_out[3 * i] = t.desc[i].x; desc_out[3 * i + 1] = t.desc[i].y; desc_out[3 * i + 2] = t.refbase[i];
+    }
+  return SVO_OK;
+}
+
 int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
   if (!c || !counters) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
   if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_render_stats before svo_upload");

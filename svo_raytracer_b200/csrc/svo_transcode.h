@@ -45,6 +45,6 @@ struct Transcoded {
 
 // Returns false (with `err` set) if the stream cannot be a tree (more
 // descriptors than bytes: cyclic or heavily aliased child pointers).
-bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std::string &err);
+bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std::string &err, int nthreads = 0);
 
 }  // namespace svo
