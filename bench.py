@@ -317,16 +317,38 @@ def main():
         ctx.read_plane_into(L.PLANE_COLOR_RGBA8, color_h.data_ptr(), color_h.numel())
         ctx.read_plane_into(L.PLANE_DEPTH, depth_h.data_ptr(), depth_h.numel() * 4)
 
-    def e2e_step(s):
+    def e2e_step_sync(s):
         render_step(s, readback if reads else None, True)  # the 92-byte svo_frame is read from host memory by the call
-    for s in range(a.warmup):
-        e2e_step(s)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(a.warmup, total):
-        e2e_step(s)
-    barrier()
-    e2e_s = reduce_max(time.perf_counter() - t0)
+
+    def timed(step_fn, finish=None):
+        for s in range(a.warmup):
+            step_fn(s)
+        if finish:
+            finish()
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(a.warmup, total):
+            step_fn(s)
+        if finish:
+            finish()
+        barrier()
+        return reduce_max(time.perf_counter() - t0)
+
+    e2e_sync_s = timed(e2e_step_sync)
+    e2e_s = e2e_sync_s
+    if not tiles:
+        # the public pipelined path: two colour/depth sets on the device and two pinned sets on the host, frame s+1
+        # renders while frame s crosses PCIe (svo_read_planes_async / svo_swap_buffers); every frame still lands in
+        # host memory inside the timed region (svo_read_wait before the clock stops)
+        color_h2, depth_h2 = torch.empty_like(color_h).pin_memory(), torch.empty_like(depth_h).pin_memory()
+        host_sets = ((color_h, depth_h), (color_h2, depth_h2))
+
+        def e2e_step_pipelined(s):
+            ctx.render(frames[s])
+            ch, dh = host_sets[s & 1]
+            ctx.read_planes_async(ch.data_ptr(), dh.data_ptr())
+            ctx.swap_buffers()
+        e2e_s = timed(e2e_step_pipelined, ctx.read_wait)
     e2e_value = all_rays / e2e_s / 1e6
 
     if rank != 0:
@@ -385,7 +407,10 @@ def main():
                             "rank r renders progressive sample s*N+r of each view; no data-path collective"},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
-                "ms_per_step": e2e_s / a.steps * 1e3},
+                "ms_per_step": e2e_s / a.steps * 1e3,
+                "how": "svo_render + svo_read_planes_async + svo_swap_buffers per frame (read-back of frame s overlaps the render of "
+                       "frame s+1), svo_read_wait inside the timed region" if not tiles else "rank 0 reads the assembled frame back after every frame-complete fence",
+                "blocking_value": all_rays / e2e_sync_s / 1e6},
         "roofline": roofline,
     }
     if cpu is not None:

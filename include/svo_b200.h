@@ -25,6 +25,7 @@ extern "C" {
 
 #define SVO_ABI_VERSION 1
 #define SVO_NO_HIT 0xFFFFFFFFu
+#define SVO_FRAME_ACCUMULATE 1
 
 enum svo_status {
   SVO_OK = 0,
@@ -55,7 +56,8 @@ typedef struct svo_frame {
   int32_t casts;
   int32_t coneDepth;
   int32_t mirrorValue;
-  int32_t flags; /* reserved, must be 0 */
+  int32_t flags; /* bit 0 (SVO_FRAME_ACCUMULATE): progressive running mean over frameNumber, the block the shader
+                  * has commented out at svotrace.comp:712-719; other bits must be 0 */
 } svo_frame;
 
 /* ray-stream records (new capability, BASELINE.json configs[3]) */
@@ -78,7 +80,7 @@ enum svo_option {
   SVO_OPT_FAST_MATH = 2,   /* 0: --fmad=false validation kernels (default, bit-exact contract); 1: fma-contracted build */
   SVO_OPT_KERNEL = 3,      /* traversal kernel variant; default 0 = best measured */
   SVO_OPT_L2_PERSIST = 4,  /* 0/1: pin the upper octree levels with an L2 access-policy window; default 1 */
-  SVO_OPT_RAY_SORT = 5,    /* 0/1: bin ray streams by octant/direction before tracing; default 1 */
+  SVO_OPT_RAY_SORT = 5,    /* 0/1: bin ray streams (>= 65536 rays) by direction octant + origin Morton code before tracing; default 1 */
   SVO_OPT_CONTENT_BOUNDS = 6 /* 0/1: end casts that cannot hit anything once they are outside the bounding box of the
                               * octree's non-empty leaves (computed at upload).  Outputs are unchanged; only the
                               * iteration count of MISSING casts differs, so it is ignored in render mode 1 and with
@@ -134,6 +136,15 @@ int svo_read_hit_id(svo_ctx *ctx, uint32_t *dst);
 int svo_read_iter(svo_ctx *ctx, uint32_t *dst);
 int svo_read_primary_t(svo_ctx *ctx, float *dst);
 int svo_read_radiance_f32(svo_ctx *ctx, float *dst);
+/* Pipelined read-back (the engine's glGetTexImage every frame, Main.java:132-146, without stalling the GPU):
+ * the context keeps two colour/depth sets.  svo_read_planes_async enqueues, on a copy stream and after everything
+ * rendered so far, the device->host copies of the CURRENT set into (pinned) host memory; svo_swap_buffers makes the
+ * other set the render target (the next render waits, on the device, for that set's last copy); svo_read_wait
+ * blocks the host until all enqueued copies have landed.  Per frame: svo_render; svo_read_planes_async;
+ * svo_swap_buffers -- frame s+1 renders while frame s crosses PCIe. */
+int svo_read_planes_async(svo_ctx *ctx, uint8_t *rgba8_dst, float *depth_dst);
+int svo_swap_buffers(svo_ctx *ctx);
+int svo_read_wait(svo_ctx *ctx);
 /* device address of a plane (for CUDA/NCCL/peer interop); NULL if absent */
 void *svo_device_ptr(svo_ctx *ctx, int plane);
 /* redirect a plane to caller-owned device memory (e.g. a peer GPU's frame

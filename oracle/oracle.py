@@ -90,7 +90,7 @@ def _ptr(a):
 
 
 def make_frame(cam_pos, l1, l2, r1, r2, frame_number=1, render_mode=0, use_beam=0, max_depth=13, casts=2,
-               cone_depth=11, mirror_value=0) -> Frame:
+               cone_depth=11, mirror_value=0, flags=0) -> Frame:
     f = Frame()
     f.camPos[:] = [float(v) for v in cam_pos]
     f.l1[:] = [float(v) for v in l1]
@@ -98,7 +98,7 @@ def make_frame(cam_pos, l1, l2, r1, r2, frame_number=1, render_mode=0, use_beam=
     f.r1[:] = [float(v) for v in r1]
     f.r2[:] = [float(v) for v in r2]
     f.frameNumber, f.renderMode, f.useBeam = int(frame_number), int(render_mode), int(use_beam)
-    f.maxDepth, f.casts, f.coneDepth, f.mirrorValue, f.flags = int(max_depth), int(casts), int(cone_depth), int(mirror_value), 0
+    f.maxDepth, f.casts, f.coneDepth, f.mirrorValue, f.flags = int(max_depth), int(casts), int(cone_depth), int(mirror_value), int(flags)
     return f
 
 
@@ -125,13 +125,14 @@ def cast_rays(nodes: np.ndarray, rays: np.ndarray, max_depth=13, nthreads=1):
 
 
 def render(nodes: np.ndarray, frame: Frame, width: int, height: int, y0=0, y1=None, beam=None, nthreads=1,
-           planes=("rgba8", "depth", "radiance", "hit_id", "iter", "primary_t")):
-    """svotrace.comp main() over rows [y0, y1).  Returns (dict of planes, Stats)."""
+           planes=("rgba8", "depth", "radiance", "hit_id", "iter", "primary_t"), prev_rgba8=None):
+    """svotrace.comp main() over rows [y0, y1).  Returns (dict of planes, Stats).  prev_rgba8: the framebuffer
+    content before the frame (only read when frame.flags bit 0 -- progressive accumulation -- is set)."""
     nodes = np.ascontiguousarray(nodes, dtype=np.uint8)
     y1 = height if y1 is None else y1
     out = {}
     if "rgba8" in planes:
-        out["rgba8"] = np.zeros((height, width, 4), np.uint8)
+        out["rgba8"] = np.zeros((height, width, 4), np.uint8) if prev_rgba8 is None else np.ascontiguousarray(prev_rgba8, np.uint8).copy()
     if "depth" in planes:
         out["depth"] = np.zeros((height, width), np.float32)
     if "radiance" in planes:

@@ -15,6 +15,8 @@
  *   U4  `out` struct parameters keep the caller's stale fields;
  *   U5  imageStore to rgba8: NaN -> 0, clamp to [0,1], floor(c*255+0.5);
  *   U6  findMSB(0) = -1 cannot occur (differing_bits != 0 whenever POP runs);
+ *   U8  frame.flags bit 0 enables the progressive running mean the shader has commented out (:712-719);
+ *       the rgba8 plane is then read before it is written (unorm8 -> float = c / 255).
  *   U7  hit_id / iter / primary_t planes are new outputs (the shader's
  *       pointer store is commented out, svotrace.comp:728): hit_id is
  *       res.pointer of the PRIMARY cast on hit, NO_HIT on miss; iter is the
@@ -540,6 +542,18 @@ static void shade_pixel(render_job_t *j, int x, int y) {
     o.color[2] = first_zero ? 0.0f : 1.0f;
   }
   size_t p = (size_t)y * (size_t)j->width + (size_t)x;
+  if ((f->flags & 1) && j->rgba8 && f->frameNumber > 1) {                           /* :712-719 (commented out upstream) */
+    for (int a = 0; a < 3; a++) {
+      float last = (float)j->rgba8[4 * p + a] / 255.0f;                             /* imageLoad of the rgba8 image */
+      if (f->frameNumber < 100) {                                                   /* MAX_FRAME_ITER :43 */
+        float s = (float)f->frameNumber * last;
+        s = s + o.color[a];
+        o.color[a] = s / (float)(f->frameNumber + 1);
+      } else {
+        o.color[a] = last;
+      }
+    }
+  }
   if (j->rgba8) {                                                                   /* :726 */
     j->rgba8[4 * p + 0] = quant8(o.color[0]);
     j->rgba8[4 * p + 1] = quant8(o.color[1]);

@@ -52,7 +52,7 @@ typedef struct svo_o_frame {
   int32_t casts;       /* mode-0 loop count, reference 2 (svotrace.comp:444) */
   int32_t coneDepth;   /* sticky LOD cut, reference 11 (svotrace.comp:275-277) */
   int32_t mirrorValue; /* 0 = as shipped; else voxel value that reflects (svotrace.comp:500-504, commented out upstream) */
-  int32_t flags;       /* reserved, 0 */
+  int32_t flags;       /* bit 0: progressive running mean (svotrace.comp:712-719, commented out upstream) */
 } svo_o_frame;
 
 typedef struct svo_o_stats {

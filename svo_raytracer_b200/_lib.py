@@ -65,6 +65,9 @@ SYMBOLS = {
     "svo_read_iter": (_i, [_vp, _vp]),
     "svo_read_primary_t": (_i, [_vp, _vp]),
     "svo_read_radiance_f32": (_i, [_vp, _vp]),
+    "svo_read_planes_async": (_i, [_vp, _vp, _vp]),
+    "svo_swap_buffers": (_i, [_vp]),
+    "svo_read_wait": (_i, [_vp]),
     "svo_device_ptr": (_vp, [_vp, _i]),
     "svo_bind_plane": (_i, [_vp, _i, _vp]),
     "svo_ipc_export": (_i, [_vp, _i, _vp]),

@@ -43,11 +43,20 @@ struct svo_ctx {
   // planes
   void *own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *bound[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // second colour/depth set for pipelined read-back (svo_swap_buffers / svo_read_planes_async)
+  void *back[2] = {nullptr, nullptr};
+  int render_set = 0;  // 0: own[], 1: back[]
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_rendered = nullptr, ev_copied[2] = {nullptr, nullptr};
   // ray-stream scratch
   void *d_rays = nullptr, *d_hits = nullptr;
   uint64_t cast_cap = 0;
+  uint32_t *d_sort = nullptr;  // 4 * sort_cap words (keys, keys_alt, idx, order) + CUB temp
+  void *d_sort_temp = nullptr;
+  uint64_t sort_cap = 0;
+  size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 0, opt_bounds = 1;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 1, opt_bounds = 1;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
@@ -91,7 +100,11 @@ size_t plane_elems(const svo_ctx *c, int plane) {
   if (plane == SVO_PLANE_BEAM) return (size_t)(c->W / 4) * (size_t)(c->H / 4);
   return (size_t)c->W * (size_t)c->H;
 }
-void *plane_ptr(const svo_ctx *c, int plane) { return c->bound[plane] ? c->bound[plane] : c->own[plane]; }
+void *plane_ptr(const svo_ctx *c, int plane) {
+  if (c->bound[plane]) return c->bound[plane];
+  if (plane <= SVO_PLANE_DEPTH && c->render_set == 1 && c->back[plane]) return c->back[plane];
+  return c->own[plane];
+}
 
 int ensure_aux(svo_ctx *c) {
   for (int p = SVO_PLANE_HIT_ID; p <= SVO_PLANE_RADIANCE; p++) {
@@ -179,7 +192,7 @@ int check_frame(svo_ctx *c, const svo_frame *f) {
   if (f->maxDepth < 1 || f->maxDepth > 23) return fail(c, SVO_ERR_INVALID, "maxDepth must be in [1,23]");
   if (f->coneDepth < 1 || f->coneDepth > 23) return fail(c, SVO_ERR_INVALID, "coneDepth must be in [1,23]");
   if (f->casts < 0 || f->casts > 64) return fail(c, SVO_ERR_INVALID, "casts must be in [0,64]");
-  if (f->flags != 0) return fail(c, SVO_ERR_INVALID, "flags must be 0");
+  if ((f->flags & ~SVO_FRAME_ACCUMULATE) != 0) return fail(c, SVO_ERR_INVALID, "unknown bits in flags");
   return SVO_OK;
 }
 
@@ -337,6 +350,14 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_refbase) cudaFree(c->d_refbase);
   if (c->d_rays) cudaFree(c->d_rays);
   if (c->d_hits) cudaFree(c->d_hits);
+  for (int p = 0; p < 2; p++)
+    if (c->back[p]) cudaFree(c->back[p]);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
+  for (int p = 0; p < 2; p++)
+    if (c->ev_copied[p]) cudaEventDestroy(c->ev_copied[p]);
+  if (c->d_sort) cudaFree(c->d_sort);
+  if (c->d_sort_temp) cudaFree(c->d_sort_temp);
   if (c->d_tile_counter) cudaFree(c->d_tile_counter);
   if (c->d_fence) cudaFree(c->d_fence);
   if (c->ws_block) cudaFree(c->ws_block);
@@ -540,6 +561,52 @@ int svo_read_depth_at(svo_ctx *c, int x, int y, float *dst) {
   return SVO_OK;
 }
 
+// ---- pipelined read-back: render frame s+1 while frame s travels to the host -----------------------------------
+static int ensure_pipeline(svo_ctx *c) {
+  if (c->copy_stream) return SVO_OK;
+  SVO_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
+  for (int p = 0; p < 2; p++) SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[p], cudaEventDisableTiming));
+  for (int p = 0; p < 2; p++) {
+    const size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
+    SVO_CUDA(c, cudaMalloc(&c->back[p], bytes));
+    SVO_CUDA(c, cudaMemsetAsync(c->back[p], 0, bytes, c->stream));
+  }
+  return SVO_OK;
+}
+
+int svo_read_planes_async(svo_ctx *c, uint8_t *rgba8_dst, float *depth_dst) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_pipeline(c);
+  if (rc) return rc;
+  SVO_CUDA(c, cudaEventRecord(c->ev_rendered, c->stream));        // everything rendered so far
+  SVO_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered, 0));
+  const size_t n = (size_t)c->W * (size_t)c->H;
+  if (rgba8_dst) SVO_CUDA(c, cudaMemcpyAsync(rgba8_dst, plane_ptr(c, SVO_PLANE_COLOR_RGBA8), n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (depth_dst) SVO_CUDA(c, cudaMemcpyAsync(depth_dst, plane_ptr(c, SVO_PLANE_DEPTH), n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+  SVO_CUDA(c, cudaEventRecord(c->ev_copied[c->render_set], c->copy_stream));
+  return SVO_OK;
+}
+
+int svo_swap_buffers(svo_ctx *c) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_pipeline(c);
+  if (rc) return rc;
+  c->render_set ^= 1;
+  // the next render overwrites this set: wait (on the device) until its last read-back has left it
+  SVO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[c->render_set], 0));
+  return SVO_OK;
+}
+
+int svo_read_wait(svo_ctx *c) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (c->copy_stream) SVO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  return SVO_OK;
+}
+
 void *svo_device_ptr(svo_ctx *c, int plane) {
   if (!c || plane < 0 || plane > SVO_PLANE_RADIANCE) return nullptr;
   if (plane >= SVO_PLANE_HIT_ID && !c->own[plane] && !c->bound[plane]) {
@@ -641,7 +708,32 @@ int svo_cast_device(svo_ctx *c, const void *d_rays, uint64_t n, void *d_out, int
   if (maxDepth < 1 || maxDepth > 23) return fail(c, SVO_ERR_INVALID, "maxDepth must be in [1,23]");
   if (n && (!d_rays || !d_out)) return fail(c, SVO_ERR_INVALID, "NULL ray or hit buffer");
   SVO_CUDA(c, cudaSetDevice(c->device));
-  SVO_CUDA(c, launch_cast(launch_cfg(c), scene_view(c), d_rays, nullptr, n, d_out, maxDepth, c->stream));
+  const uint32_t *order = nullptr;
+  if (c->opt_sort && n >= 65536 && n < (1ull << 31)) {  // bin by octant + origin Morton code; results go back to the caller's order
+    if (n > c->sort_cap) {
+      SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+      for (int p = 0; p < 2; p++)
+    if (c->back[p]) cudaFree(c->back[p]);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
+  for (int p = 0; p < 2; p++)
+    if (c->ev_copied[p]) cudaEventDestroy(c->ev_copied[p]);
+  if (c->d_sort) cudaFree(c->d_sort);
+      if (c->d_sort_temp) cudaFree(c->d_sort_temp);
+      c->d_sort = nullptr;
+      c->d_sort_temp = nullptr;
+      c->sort_cap = 0;
+      c->sort_temp_bytes = ray_sort_temp_bytes(n);
+      SVO_CUDA(c, cudaMalloc((void **)&c->d_sort, 4 * n * sizeof(uint32_t)));
+      SVO_CUDA(c, cudaMalloc(&c->d_sort_temp, c->sort_temp_bytes ? c->sort_temp_bytes : 16));
+      c->sort_cap = n;
+    }
+    uint32_t *keys = c->d_sort, *keys_alt = keys + c->sort_cap, *idx = keys_alt + c->sort_cap, *ord = idx + c->sort_cap;
+    SVO_CUDA(c, launch_ray_sort(d_rays, n, keys, keys_alt, idx, ord, c->d_sort_temp, c->sort_temp_bytes, c->stream));
+    c->launches += 2;
+    order = ord;
+  }
+  SVO_CUDA(c, launch_cast(launch_cfg(c), scene_view(c), d_rays, order, n, d_out, maxDepth, c->stream));
   if (n) c->launches++;
   return SVO_OK;
 }

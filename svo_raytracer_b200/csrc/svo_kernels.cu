@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) k_render_persistent(SceneView sc, FramePa
         const int y = y0 + (int)(tile / (unsigned)tiles_x) * 4 + (int)(k >> 3);
         if (x < W && y < y1) {
           if (pixel_begin(f, pl, W, H, x, y, P)) state = NEED_SETUP;
-          else pixel_store<AUX>(sc, pl, W, P);  // no cast wanted (mode 4): done, lane stays idle
+          else pixel_store<AUX>(sc, f, pl, W, P);  // no cast wanted (mode 4): done, lane stays idle
         }
       }
       pool_next += min(avail, (unsigned)__popc(want));
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_render_persistent(SceneView sc, FramePa
       const bool hit = T.finish(sc, status, P.res, loops);
       if (pixel_after_cast(f, P, hit, loops)) state = NEED_SETUP;
       else {
-        pixel_store<AUX>(sc, pl, W, P);
+        pixel_store<AUX>(sc, f, pl, W, P);
         state = NEED_PIXEL;
       }
     }

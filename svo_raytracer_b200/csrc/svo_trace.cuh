@@ -586,12 +586,27 @@ SVO_DI unsigned char quant8(float c) {  // imageStore to rgba8 (:726), DESIGN.md
   return (unsigned char)floorf(fadd(fmul(c, 255.0f), 0.5f));
 }
 
-// the end of main() (:696-727)
-template <bool AUX>
-SVO_DI void pixel_store(const SceneView &sc, const Planes &pl, int W, Pixel &P) {
+// progressive running mean (:712-719, commented out upstream; svo_frame.flags bit 0)
+SVO_DI float accumulate1(int frameNumber, unsigned char last8, float c) {
+  const float last = fdiv((float)last8, 255.0f);  // imageLoad of the rgba8 image
+  if (frameNumber < 100) return fdiv(fadd(fmul((float)frameNumber, last), c), (float)(frameNumber + 1));  // MAX_FRAME_ITER :43
+  return last;
+}
+SVO_DI void pixel_finish(const SceneView &sc, const FrameParams &f, const Planes &pl, size_t p, Pixel &P) {
   if (P.x < 10 && P.y < 10)  // :696-700
     P.color = sc.first_word_zero ? mk3(1.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
+  if ((f.flags & 1) && f.frameNumber > 1) {
+    const uchar4 last = pl.rgba8[p];
+    P.color = mk3(accumulate1(f.frameNumber, last.x, P.color.x), accumulate1(f.frameNumber, last.y, P.color.y),
+                  accumulate1(f.frameNumber, last.z, P.color.z));
+  }
+}
+
+// the end of main() (:696-727)
+template <bool AUX>
+SVO_DI void pixel_store(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, Pixel &P) {
   const size_t p = (size_t)P.y * (size_t)W + (size_t)P.x;
+  pixel_finish(sc, f, pl, p, P);
   pl.rgba8[p] = make_uchar4(quant8(P.color.x), quant8(P.color.y), quant8(P.color.z), 255);  // :726
   pl.depth[p] = P.depth;                                                                       // :727
   if (AUX) {
@@ -615,7 +630,7 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
       more = pixel_after_cast(f, P, hit, loops);
     } while (more);
   }
-  pixel_store<AUX>(sc, pl, W, P);
+  pixel_store<AUX>(sc, f, pl, W, P);
 }
 
 }  // namespace svo

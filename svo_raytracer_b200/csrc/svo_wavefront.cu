@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(SceneView sc, FrameParams f, P
       valid = x < W && y < y1;
       if (valid) {
         if (!pixel_begin(f, pl, W, H, x, y, P)) {  // no cast at all (mode 4)
-          pixel_store<AUX>(sc, pl, W, P);
+          pixel_store<AUX>(sc, f, pl, W, P);
           valid = false;
         }
       }
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(128) k_wf_shade(SceneView sc, FrameParams f, P
         pl.primary_t[p] = P.primary_t;
       }
       if (!more) {  // the end of main() (:696-727)
-        if (P.x < 10 && P.y < 10) P.color = sc.first_word_zero ? mk3(1.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
         const size_t p = (size_t)P.y * (size_t)W + (size_t)P.x;
+        pixel_finish(sc, f, pl, p, P);
         pl.rgba8[p] = make_uchar4(quant8(P.color.x), quant8(P.color.y), quant8(P.color.z), 255);
         pl.depth[p] = P.depth;
         if (AUX) pl.radiance[p] = make_float4(P.color.x, P.color.y, P.color.z, 1.0f);

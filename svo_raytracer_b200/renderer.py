@@ -37,7 +37,7 @@ _PLANE_DTYPE = {
 
 
 def make_frame(cam_pos, l1, l2, r1, r2, frame_number=1, render_mode=2, use_beam=0, max_depth=13, casts=2,
-               cone_depth=11, mirror_value=0) -> Frame:
+               cone_depth=11, mirror_value=0, flags=0) -> Frame:
     """The uniforms of Main.java:269-283 as one struct (defaults = the shader's #defines)."""
     f = Frame()
     f.camPos[:] = [float(v) for v in cam_pos]
@@ -46,7 +46,7 @@ def make_frame(cam_pos, l1, l2, r1, r2, frame_number=1, render_mode=2, use_beam=
     f.r1[:] = [float(v) for v in r1]
     f.r2[:] = [float(v) for v in r2]
     f.frameNumber, f.renderMode, f.useBeam = int(frame_number), int(render_mode), int(use_beam)
-    f.maxDepth, f.casts, f.coneDepth, f.mirrorValue, f.flags = int(max_depth), int(casts), int(cone_depth), int(mirror_value), 0
+    f.maxDepth, f.casts, f.coneDepth, f.mirrorValue, f.flags = int(max_depth), int(casts), int(cone_depth), int(mirror_value), int(flags)
     return f
 
 
@@ -174,6 +174,16 @@ class SvoContext:
 
     def read_radiance(self):
         return self.read_plane(L.PLANE_RADIANCE)
+
+    def read_planes_async(self, rgba8_ptr: int, depth_ptr: int):
+        """Enqueue the read-back of the current colour/depth set into (pinned) host memory; see svo_read_planes_async."""
+        self._check(self._lib.svo_read_planes_async(self._h, C.c_void_p(rgba8_ptr or 0), C.c_void_p(depth_ptr or 0)))
+
+    def swap_buffers(self):
+        self._check(self._lib.svo_swap_buffers(self._h))
+
+    def read_wait(self):
+        self._check(self._lib.svo_read_wait(self._h))
 
     def device_ptr(self, plane: int) -> int:
         return int(self._lib.svo_device_ptr(self._h, plane) or 0)

@@ -357,3 +357,109 @@ def test_content_bounds_inside_camera_and_shallow_depths(svo, oracle, terrain128
                 c.render(svo.make_frame(*cam, frame_number=1, render_mode=mode, max_depth=max_depth, cone_depth=cone_depth))
                 assert np.array_equal(c.read_color_rgba8(), want["rgba8"]), (cam[0], max_depth, cone_depth, mode)
                 assert np.array_equal(c.read_depth().view(np.uint32), want["depth"].view(np.uint32))
+
+
+def _blob_world(oracle, n=64):
+    """BASELINE configs[2] in miniature ("mirrorblobs"): terrain floor + spheres of value 4 (the mirror material)."""
+    z, y, x = np.mgrid[0:n, 0:n, 0:n]
+    vox = np.zeros((n, n, n), np.uint8)
+    h = (6 + 3 * np.sin(x / 7.0) + 2 * np.cos(z / 5.0)).astype(int)
+    vox[y <= h] = 1
+    vox[(y <= h) & (y >= h - 1)] = 3
+    rng = np.random.default_rng(1)  # sphere list from a fixed seed
+    for _ in range(6):
+        c = rng.uniform(12, n - 12, 3)
+        r = rng.uniform(4, 9)
+        vox[(x - c[0]) ** 2 + (y - max(c[1], 16)) ** 2 + (z - c[2]) ** 2 <= r * r] = 4
+    nodes, _ = oracle.build_dense(vox)
+    return nodes
+
+
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_mirror_material_and_deeper_paths(svo, oracle, kernel):
+    """svo_frame.casts = 5 (4 bounces) with the mirror rule the shader has commented out (svotrace.comp:500-504) on
+    value-4 spheres: the path-traced configuration of BASELINE configs[2], bit-exact against the oracle."""
+    nodes = _blob_world(oracle)
+    W, H = 192, 108
+    with svo.SvoContext(W, H) as c:
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
+        c.upload(nodes)
+        for cam in ("B", "C"):
+            pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+            kw = dict(frame_number=7, render_mode=0, max_depth=6, casts=5, cone_depth=5, mirror_value=4)
+            want, st = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, **kw), W, H, nthreads=8)
+            assert st.casts > 2 * W * H * 0.3  # paths really go deeper than one bounce
+            got = _render_gpu(svo, c, svo.camera_frame(cam, **kw))
+            _assert_planes_equal(got, want, "mirror cam %s" % cam)
+
+
+def test_progressive_accumulation(svo, oracle, terrain128):
+    """svo_frame.flags bit 0: the running mean over frameNumber the shader has commented out (svotrace.comp:712-719),
+    accumulated in the rgba8 framebuffer exactly as written there; frames 1..4 against the oracle."""
+    W, H = 160, 90
+    pos, l1, l2, r1, r2 = svo.CAMERAS["C"]
+    prev = None
+    with svo.SvoContext(W, H) as c:
+        c.upload(terrain128)
+        for frame in (1, 2, 3, 4):
+            kw = dict(frame_number=frame, render_mode=0, max_depth=7, flags=1)
+            want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, **kw), W, H, nthreads=4,
+                                    planes=("rgba8", "depth"), prev_rgba8=prev)
+            c.render(svo.camera_frame("C", **kw))
+            got = c.read_color_rgba8()
+            assert np.array_equal(got, want["rgba8"]), frame
+            prev = want["rgba8"]
+        first, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=4, render_mode=0, max_depth=7), W, H,
+                                 nthreads=4, planes=("rgba8",))
+        assert not np.array_equal(first["rgba8"], prev)  # the mean differs from a single sample
+
+
+def test_ray_binning_keeps_results(svo, oracle, terrain512):
+    """SVO_OPT_RAY_SORT: rays are traced in (octant, origin Morton) order; every hit record lands in the caller's
+    slot, so the output equals the unsorted run and the oracle."""
+    rng = np.random.default_rng(9)
+    n = 100003
+    rays = np.zeros(n, dtype=svo.RAY_DTYPE)
+    rays["o"] = rng.uniform(1.0, 2.0, (n, 3)).astype(np.float32)
+    rays["o"][:, 1] = rng.uniform(1.0, 1.3, n).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["d"][:7] = np.nan
+    rays["o"][7:14] = np.nan
+    want, _ = oracle.cast_rays(terrain512, rays, max_depth=9, nthreads=8)
+    with svo.SvoContext(64, 64) as c:
+        c.upload(terrain512)
+        for sort in (1, 0):
+            c.set_option(svo._lib.OPT_RAY_SORT, sort)
+            got = c.cast(rays, max_depth=9)
+            for k in ("id", "value", "iter"):
+                assert (got[k] == want[k]).all(), (sort, k)
+            assert (got["t"].view(np.uint32) == want["t"].view(np.uint32)).all()
+
+
+def test_pipelined_readback(svo, oracle, terrain128):
+    """svo_read_planes_async / svo_swap_buffers: frame s+1 renders while frame s is copied to the host; both frames
+    arrive intact."""
+    import torch
+    W, H = 160, 90
+    pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+    with svo.SvoContext(W, H) as c:
+        c.upload(terrain128)
+        sets = [(torch.empty((H, W, 4), dtype=torch.uint8).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory()) for _ in range(2)]
+        for base in (1, 3, 5):
+            for k in range(2):
+                c.render(svo.camera_frame("B", frame_number=base + k, render_mode=0, max_depth=7))
+                c.read_planes_async(sets[k][0].data_ptr(), sets[k][1].data_ptr())
+                c.swap_buffers()
+            c.read_wait()
+            for k in range(2):
+                want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=base + k, render_mode=0, max_depth=7),
+                                        W, H, nthreads=4, planes=("rgba8", "depth"))
+                assert np.array_equal(sets[k][0].numpy(), want["rgba8"]), (base, k)
+                assert np.array_equal(sets[k][1].numpy().view(np.uint32), want["depth"].view(np.uint32)), (base, k)
+        # the blocking readers follow the current set
+        c.render(svo.camera_frame("B", frame_number=9, render_mode=0, max_depth=7))
+        want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=9, render_mode=0, max_depth=7), W, H,
+                                nthreads=4, planes=("rgba8",))
+        assert np.array_equal(c.read_color_rgba8(), want["rgba8"])
