@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
                     help="N>1: frames = rank r renders progressive sample s*N+r of each view (weak scaling, no collective); "
@@ -161,11 +163,13 @@ def cpu_arm(nodes, size, steps, warmup, budget_s, cores):
         r, t = run(warmup + s, y0, y0 + rows)
         rays += r
         secs += t
-    return rays / secs / 1e6, "rows [%d,%d) of each 1920x1080 frame, %d steps, cameras A/B/C cycled" % (y0, y0 + rows, steps), secs / steps * 1e3
+    return rays / secs / 1e6, "rows [%d,%d) of each %dx%d frame, %d steps, cameras A/B/C cycled" % (y0, y0 + rows, W, H, steps), secs / steps * 1e3
 
 
 def main():
     a = parse()
+    global W, H
+    W, H = a.width, a.height
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -379,7 +383,7 @@ def main():
     # dram__bytes_write.sum, mean of the three camera frames), profiles/r01_tile_full.json
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_tile_full.json")
-    if os.path.exists(tpath) and a.size == 8192 and a.kernel == 0 and world_size == 1:
+    if os.path.exists(tpath) and a.size == 8192 and a.kernel == 0 and world_size == 1 and (W, H) == (1920, 1080):
         caps = json.load(open(tpath))
         traffic = float(np.mean([c["dram_traffic_MB"] for c in caps])) * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
