@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
                     help="N>1: frames = rank r renders progressive sample s*N+r of each view (weak scaling, no collective); "
@@ -205,6 +206,7 @@ def main():
     ctx = svo.SvoContext(W, H, device=dev)
     ctx.set_option(L.OPT_FAST_MATH, a.fast_math)
     ctx.set_option(L.OPT_KERNEL, a.kernel)
+    ctx.set_option(L.OPT_BAND_ROWS, a.band_rows)
     t0 = time.time()
     ctx.upload(nodes)
     upload_s = time.time() - t0
@@ -216,13 +218,15 @@ def main():
         # ONE frame per step, image bands interleaved over the ranks, replicated octree.  Rank 0 owns the frame
         # buffer; every peer maps it (CUDA IPC over NVLink) and its kernel stores its bands straight into it.
         frames = [frame_for(s, a.size) for s in range(total)]
-        handles = [ctx.ipc_export(L.PLANE_COLOR_RGBA8), ctx.ipc_export(L.PLANE_DEPTH)] if rank == 0 else [None, None]
-        dist.broadcast_object_list(handles, src=0)
-        if rank != 0:
-            for plane, h in zip((L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH), handles):
-                ctx.bind_plane(plane, ctx.ipc_import(h))
+        PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        drain = lambda: None
         if a.fence == "nccl":
+            handles = [ctx.ipc_export(p) for p in PL] if rank == 0 else [None, None]
+            dist.broadcast_object_list(handles, src=0)
+            if rank != 0:
+                for plane, h in zip(PL, handles):
+                    ctx.bind_plane(plane, ctx.ipc_import(h))
             fence = torch.zeros(1, device="cuda")
 
             def render_step(s, consume=None, release=False):
@@ -233,29 +237,56 @@ def main():
                 if release:
                     dist.all_reduce(fence)  # the frame has been consumed: peers may overwrite the planes
         else:
-            # fences are counters in GPU memory bumped by remote atomics over NVLink (svo_fence_*): no collective
+            # No collective in the data path.  Rank 0 owns TWO colour/depth sets; frame k goes to set k&1, so two
+            # frames are in flight.  Fences are counters in GPU memory bumped by remote atomics over NVLink
+            # (svo_fence_*): slot 2+(k&1) of rank 0's counter = "bands of frame k stored" (complete at (k//2+1)*N),
+            # slot 0 of every peer's counter = "frames consumed by rank 0".
+            handles = [ctx.ipc_export(p | s) for s in (0, L.PLANE_BACK) for p in PL] if rank == 0 else [None] * 4
+            dist.broadcast_object_list(handles, src=0)
+            if rank == 0:
+                sets = [[ctx.device_ptr(p | s) for p in PL] for s in (0, L.PLANE_BACK)]
+            else:
+                ptrs = [ctx.ipc_import(h) for h in handles]
+                sets = [ptrs[0:2], ptrs[2:4]]
             fh = [None] * world_size
             dist.all_gather_object(fh, ctx.fence_export())
             if rank == 0:
                 peer_fences = [ctx.ipc_import(fh[r]) for r in range(1, world_size)]
             else:
                 owner_fence = [ctx.ipc_import(fh[0])]
-            done = [0]
+            state = {"k": 0, "pending": None}
+
+            def bind(k):
+                for plane, ptr in zip(PL, sets[k & 1]):
+                    ctx.bind_plane(plane, ptr)
+
+            def finish(j, consume):
+                ctx.fence_wait((j // 2 + 1) * world_size, slot=2 + (j & 1))  # every GPU has stored its bands of frame j
+                if consume is not None:
+                    bind(j)
+                    consume()
+                ctx.fence_signal(peer_fences, slot=0)  # frame j consumed: its plane set may be overwritten
 
             def render_step(s, consume=None, release=False):
-                k = done[0]
-                done[0] += 1
+                k = state["k"]
+                state["k"] = k + 1
                 if rank == 0:
+                    bind(k)
                     ctx.render_interleaved(frames[s], 0, world_size)
-                    ctx.fence_signal()
-                    ctx.fence_wait((k + 1) * world_size)  # every GPU has stored its bands of frame k
-                    if consume is not None:
-                        consume()
-                    ctx.fence_signal(peer_fences)        # frame k consumed: the peers may overwrite the planes
+                    ctx.fence_signal((), slot=2 + (k & 1))
+                    if state["pending"] is not None:
+                        finish(*state["pending"])
+                    state["pending"] = (k, consume)
                 else:
-                    ctx.fence_wait(k)                     # the owner has consumed frames 0..k-1
+                    ctx.fence_wait(max(k - 1, 0), slot=0)  # rank 0 has consumed frames 0..k-2: set k&1 is free
+                    bind(k)
                     ctx.render_interleaved(frames[s], rank, world_size)
-                    ctx.fence_signal(owner_fence)
+                    ctx.fence_signal(owner_fence, slot=2 + (k & 1))
+
+            def drain():
+                if rank == 0 and state["pending"] is not None:
+                    finish(*state["pending"])
+                    state["pending"] = None
     else:
         # Units: rank r renders its own progressive sample (frameNumber) of the same views -- independent units, no
         # data-path collective (weak scaling); step s on rank r is sample s*N + r.
@@ -264,6 +295,8 @@ def main():
             f.frameNumber = s * world_size + rank + 1
             return f
         frames = [my_frame(s) for s in range(total)]
+
+        drain = lambda: None
 
         def render_step(s, consume=None, release=False):
             ctx.render(frames[s])
@@ -295,6 +328,7 @@ def main():
     clocks = ClockSampler(dev)  # started early: nvidia-smi needs ~100 ms before its first sample
     for s in range(a.warmup):
         render_step(s)
+    drain()
     ctx.sync()
     barrier()
     launches0 = ctx.launch_count()
@@ -302,6 +336,7 @@ def main():
     ctx.timer_begin()
     for s in range(a.warmup, total):
         render_step(s)
+    drain()
     dev_ms = ctx.timer_end()
     clocks.end()
     launches = ctx.launch_count() - launches0
@@ -327,12 +362,14 @@ def main():
     def timed(step_fn, finish=None):
         for s in range(a.warmup):
             step_fn(s)
+        drain()
         if finish:
             finish()
         barrier()
         t0 = time.perf_counter()
         for s in range(a.warmup, total):
             step_fn(s)
+        drain()
         if finish:
             finish()
         barrier()

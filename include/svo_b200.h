@@ -72,7 +72,9 @@ enum svo_plane {
   SVO_PLANE_HIT_ID = 3,      /* new: primary res.pointer (svotrace.comp:294,381; store commented out at :728) */
   SVO_PLANE_ITER = 4,        /* new: primary loop iterations (render mode 1 shows it as a heat map, :428) */
   SVO_PLANE_PRIMARY_T = 5,   /* new: primary res.t */
-  SVO_PLANE_RADIANCE = 6     /* new: finalcolor before the rgba8 store, float4 */
+  SVO_PLANE_RADIANCE = 6,    /* new: finalcolor before the rgba8 store, float4 */
+  SVO_PLANE_BACK = 0x100     /* OR-ed to COLOR_RGBA8 / DEPTH in svo_device_ptr and svo_ipc_export: the second set
+                              * (svo_swap_buffers); without it they name the first set */
 };
 
 enum svo_option {
@@ -85,6 +87,7 @@ enum svo_option {
                               * octree's non-empty leaves (computed at upload).  Outputs are unchanged; only the
                               * iteration count of MISSING casts differs, so it is ignored in render mode 1 and with
                               * SVO_OPT_AUX_PLANES.  default 1 */
+  ,SVO_OPT_BAND_ROWS = 7     /* image rows per band of svo_render_interleaved (multiple of 8); default 8 */
 };
 
 /* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and
@@ -118,8 +121,8 @@ int svo_scene_info(const svo_ctx *ctx, uint64_t info[4]);
 int svo_render(svo_ctx *ctx, const svo_frame *frame);
 /* rows [y0,y1) only: the image-tile partition for multi-GPU */
 int svo_render_rows(svo_ctx *ctx, const svo_frame *frame, int y0, int y1);
-/* 8-row bands part, part+parts, part+2*parts, ... of the frame in ONE launch: the interleaved
- * image partition of the multi-GPU mode (rank = part, world size = parts). */
+/* Bands part, part+parts, part+2*parts, ... of the frame (SVO_OPT_BAND_ROWS image rows each, default 8) in ONE
+ * launch: the interleaved image partition of the multi-GPU mode (rank = part, world size = parts). */
 int svo_render_interleaved(svo_ctx *ctx, const svo_frame *frame, int part, int parts);
 /* replaces dispatchCompute(beamShader, W/8/4, H/8/4, 1) (Main.java:257-266) */
 int svo_beam(svo_ctx *ctx, const svo_frame *frame);
@@ -169,8 +172,8 @@ int svo_ipc_close(svo_ctx *ctx, void *device_ptr);
  * cannot hang the GPU).  Protocol of bench.py --partition tiles: peers signal the frame owner when their bands
  * are stored ("frame complete" = frames * n_gpus), the owner signals the peers when it has consumed the frame. */
 int svo_fence_export(svo_ctx *ctx, uint8_t handle[SVO_IPC_HANDLE_BYTES]);
-int svo_fence_signal(svo_ctx *ctx, void *const *fence_ptrs, int n);
-int svo_fence_wait(svo_ctx *ctx, uint32_t target);
+int svo_fence_signal(svo_ctx *ctx, void *const *fence_ptrs, int n, int slot);
+int svo_fence_wait(svo_ctx *ctx, int slot, uint32_t target);
 int svo_fence_reset(svo_ctx *ctx);
 
 /* -- ray streams (new): n independent intersectOctree calls.

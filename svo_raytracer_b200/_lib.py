@@ -18,8 +18,9 @@ NO_HIT = 0xFFFFFFFF
 OK, ERR_INVALID, ERR_OOM, ERR_NO_DEVICE, ERR_CUDA, ERR_FORMAT, ERR_NO_SCENE = 0, 1, 2, 100, 999, 1000, 1001
 # enum svo_plane
 PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIMARY_T, PLANE_RADIANCE = range(7)
+PLANE_BACK = 0x100
 # enum svo_option
-OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS = 1, 2, 3, 4, 5, 6
+OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS, OPT_BAND_ROWS = 1, 2, 3, 4, 5, 6, 7
 
 
 class SvoError(RuntimeError):
@@ -74,8 +75,8 @@ SYMBOLS = {
     "svo_ipc_import": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "svo_ipc_close": (_i, [_vp, _vp]),
     "svo_fence_export": (_i, [_vp, _vp]),
-    "svo_fence_signal": (_i, [_vp, C.POINTER(_vp), _i]),
-    "svo_fence_wait": (_i, [_vp, C.c_uint32]),
+    "svo_fence_signal": (_i, [_vp, C.POINTER(_vp), _i, _i]),
+    "svo_fence_wait": (_i, [_vp, _i, C.c_uint32]),
     "svo_fence_reset": (_i, [_vp]),
     "svo_cast": (_i, [_vp, _vp, _u64, _vp, _i]),
     "svo_cast_device": (_i, [_vp, _vp, _u64, _vp, _i]),

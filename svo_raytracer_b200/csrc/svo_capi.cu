@@ -56,7 +56,7 @@ struct svo_ctx {
   uint64_t sort_cap = 0;
   size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 1, opt_bounds = 1;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
@@ -68,6 +68,8 @@ struct svo_ctx {
   uint64_t launches = 0;
   std::string err;
 };
+
+static int ensure_pipeline(svo_ctx *c);
 
 namespace {
 
@@ -171,6 +173,7 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.sm_count = c->sm_count;
   l.band_stride = 0;
   l.band_offset = 0;
+  l.band_ctas = c->opt_band_rows / 8;
   l.ctas_per_sm = c->ctas_per_sm;
   l.tile_counter = c->d_tile_counter;
   return l;
@@ -281,6 +284,20 @@ int retranscode(svo_ctx *c) {
 
 }  // namespace
 
+// ---- pipelined read-back: render frame s+1 while frame s travels to the host -----------------------------------
+static int ensure_pipeline(svo_ctx *c) {
+  if (c->copy_stream) return SVO_OK;
+  SVO_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
+  for (int p = 0; p < 2; p++) SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[p], cudaEventDisableTiming));
+  for (int p = 0; p < 2; p++) {
+    const size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
+    SVO_CUDA(c, cudaMalloc(&c->back[p], bytes));
+    SVO_CUDA(c, cudaMemsetAsync(c->back[p], 0, bytes, c->stream));
+  }
+  return SVO_OK;
+}
+
 extern "C" {
 
 int svo_abi_version(void) { return SVO_ABI_VERSION; }
@@ -379,6 +396,10 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
     case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
+    case SVO_OPT_BAND_ROWS:
+      if (value < 8 || value > 4096 || value % 8) return fail(c, SVO_ERR_INVALID, "band rows must be a multiple of 8");
+      c->opt_band_rows = (int)value;
+      return SVO_OK;
     default: return fail(c, SVO_ERR_INVALID, "unknown option");
   }
 }
@@ -391,6 +412,7 @@ int svo_get_option(const svo_ctx *c, int option, int64_t *value) {
     case SVO_OPT_L2_PERSIST: *value = c->opt_l2; return SVO_OK;
     case SVO_OPT_RAY_SORT: *value = c->opt_sort; return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: *value = c->opt_bounds; return SVO_OK;
+    case SVO_OPT_BAND_ROWS: *value = c->opt_band_rows; return SVO_OK;
     default: return fail(const_cast<svo_ctx *>(c), SVO_ERR_INVALID, "unknown option");
   }
 }
@@ -561,20 +583,6 @@ int svo_read_depth_at(svo_ctx *c, int x, int y, float *dst) {
   return SVO_OK;
 }
 
-// ---- pipelined read-back: render frame s+1 while frame s travels to the host -----------------------------------
-static int ensure_pipeline(svo_ctx *c) {
-  if (c->copy_stream) return SVO_OK;
-  SVO_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
-  for (int p = 0; p < 2; p++) SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[p], cudaEventDisableTiming));
-  for (int p = 0; p < 2; p++) {
-    const size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
-    SVO_CUDA(c, cudaMalloc(&c->back[p], bytes));
-    SVO_CUDA(c, cudaMemsetAsync(c->back[p], 0, bytes, c->stream));
-  }
-  return SVO_OK;
-}
-
 int svo_read_planes_async(svo_ctx *c, uint8_t *rgba8_dst, float *depth_dst) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
@@ -608,7 +616,12 @@ int svo_read_wait(svo_ctx *c) {
 }
 
 void *svo_device_ptr(svo_ctx *c, int plane) {
+  if (c && (plane == (SVO_PLANE_COLOR_RGBA8 | SVO_PLANE_BACK) || plane == (SVO_PLANE_DEPTH | SVO_PLANE_BACK))) {
+    cudaSetDevice(c->device);
+    return ensure_pipeline(c) == SVO_OK ? c->back[plane & 0xFF] : nullptr;
+  }
   if (!c || plane < 0 || plane > SVO_PLANE_RADIANCE) return nullptr;
+  if (plane <= SVO_PLANE_DEPTH) return c->own[plane];  // the front set, whatever is bound or current
   if (plane >= SVO_PLANE_HIT_ID && !c->own[plane] && !c->bound[plane]) {
     cudaSetDevice(c->device);
     if (ensure_aux(c) != SVO_OK) return nullptr;
@@ -625,6 +638,12 @@ int svo_bind_plane(svo_ctx *c, int plane, void *device_ptr) {
 
 int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[72]) {
   if (!c || !handle) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (plane == (SVO_PLANE_COLOR_RGBA8 | SVO_PLANE_BACK) || plane == (SVO_PLANE_DEPTH | SVO_PLANE_BACK)) {
+    SVO_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    return export_handle(c, c->back[plane & 0xFF], handle);
+  }
   if (plane < 0 || plane > SVO_PLANE_RADIANCE) return fail(c, SVO_ERR_INVALID, "bad plane");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
   SVO_CUDA(c, cudaSetDevice(c->device));
@@ -640,23 +659,25 @@ int svo_fence_export(svo_ctx *c, uint8_t handle[72]) {
   SVO_CUDA(c, cudaSetDevice(c->device));
   return export_handle(c, c->d_fence, handle);
 }
-int svo_fence_signal(svo_ctx *c, void *const *fence_ptrs, int n) {
+int svo_fence_signal(svo_ctx *c, void *const *fence_ptrs, int n, int slot) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (n < 0 || n > 16 || (n > 0 && !fence_ptrs)) return fail(c, SVO_ERR_INVALID, "bad fence list (at most 16)");
+  if (slot < 0 || slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   FenceList fl;
   fl.n = n > 0 ? n : 1;
   for (int i = 0; i < 16; i++) fl.p[i] = nullptr;
-  if (n == 0) fl.p[0] = c->d_fence;
-  for (int i = 0; i < n; i++) fl.p[i] = (unsigned int *)fence_ptrs[i];
+  if (n == 0) fl.p[0] = c->d_fence + 8 * slot;
+  for (int i = 0; i < n; i++) fl.p[i] = (unsigned int *)fence_ptrs[i] + 8 * slot;  // slots are 32 bytes apart
   SVO_CUDA(c, launch_fence_signal(fl, c->stream));
   c->launches++;
   return SVO_OK;
 }
-int svo_fence_wait(svo_ctx *c, uint32_t target) {
+int svo_fence_wait(svo_ctx *c, int slot, uint32_t target) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (slot < 0 || slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
   SVO_CUDA(c, cudaSetDevice(c->device));
-  SVO_CUDA(c, launch_fence_wait(c->d_fence, target, c->stream));
+  SVO_CUDA(c, launch_fence_wait(c->d_fence + 8 * slot, c->d_fence + 7, target, c->stream));
   c->launches++;
   return SVO_OK;
 }

@@ -16,12 +16,14 @@ namespace svo {
 // running together share their octree working set in L1/L2, which outweighs the better tail balance.)
 template <bool FAST, bool AUX, bool BOX>
 __global__ void __launch_bounds__(128, 8) k_render_tile(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
-                                                     int band_stride, int band_offset) {
-  // CTA row blockIdx.y renders 8-row band number blockIdx.y * band_stride + band_offset (counted from y0): with
-  // stride = number of GPUs and offset = rank this is the interleaved image partition of the multi-GPU mode.
+                                                     int band_stride, int band_offset, int band_ctas) {
+  // A band is band_ctas consecutive CTA rows (8 image rows each).  This launch renders bands number
+  // i * band_stride + band_offset (counted from y0): with stride = number of GPUs and offset = rank this is the
+  // interleaved image partition of the multi-GPU mode; stride 1 is the whole image.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-  const int y = y0 + ((int)blockIdx.y * band_stride + band_offset) * 8 + (warp >> 1) * 4 + (lane >> 3);
+  const int band = (int)blockIdx.y / band_ctas, in_band = (int)blockIdx.y % band_ctas;
+  const int y = y0 + ((band * band_stride + band_offset) * band_ctas + in_band) * 8 + (warp >> 1) * 4 + (lane >> 3);
   if (x >= W || y >= y1) return;
   shade_pixel<FAST, AUX, false, BOX>(sc, f, pl, W, H, x, y);
 }
@@ -144,14 +146,14 @@ __global__ void k_fence_signal(FenceList fl) {
   __threadfence_system();  // the stores of the preceding kernels in this stream are complete; order the bumps after them
   if ((int)threadIdx.x < fl.n) atomicAdd_system(fl.p[threadIdx.x], 1u);
 }
-__global__ void k_fence_wait(volatile unsigned int *fence, unsigned int target) {
+__global__ void k_fence_wait(volatile unsigned int *fence, volatile unsigned int *dead, unsigned int target) {
   const long long t0 = clock64();
   // modular comparison (the counter runs forever).  Give up after ~4e9 cycles (~2 s) instead of hanging the GPU,
-  // and latch the failure in word 1 so that every later wait returns at once.
+  // and latch the failure so that every later wait returns at once.
   while ((int)(*fence - target) < 0) {
-    if (fence[1] == 0xDEADu) break;
-    if (clock64() - t0 > 4000000000ll) { ((unsigned int *)fence)[1] = 0xDEADu; break; }
-    __nanosleep(200);
+    if (*dead == 0xDEADu) break;
+    if (clock64() - t0 > 4000000000ll) { *dead = 0xDEADu; break; }
+    __nanosleep(100);
   }
   __threadfence_system();
 }
@@ -293,11 +295,12 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
     return cudaGetLastError();
   }
   const dim3 block(128);
-  const int bands = (y1 - y0 + 7) / 8;
   const int stride = cfg.band_stride > 0 ? cfg.band_stride : 1, offset = cfg.band_stride > 0 ? cfg.band_offset : 0;
-  const dim3 grid((W + 15) / 16, bands > offset ? (bands - offset + stride - 1) / stride : 0);
+  const int band_ctas = cfg.band_stride > 0 && cfg.band_ctas > 0 ? cfg.band_ctas : 1;
+  const int bands = ((y1 - y0 + 7) / 8 + band_ctas - 1) / band_ctas;  // bands of band_ctas CTA rows (the last may be short)
+  const dim3 grid((W + 15) / 16, bands > offset ? ((bands - offset + stride - 1) / stride) * band_ctas : 0);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-#define SVO_LAUNCH_TILE(F, A, B) k_render_tile<F, A, B><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset)
+#define SVO_LAUNCH_TILE(F, A, B) k_render_tile<F, A, B><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas)
   if (cfg.fast) {
     if (cfg.aux) SVO_LAUNCH_TILE(true, true, false);
     else if (cfg.box) SVO_LAUNCH_TILE(true, false, true);
@@ -324,8 +327,8 @@ cudaError_t launch_fence_signal(const FenceList &fl, cudaStream_t stream) {
   k_fence_signal<<<1, 32, 0, stream>>>(fl);
   return cudaGetLastError();
 }
-cudaError_t launch_fence_wait(unsigned int *fence, unsigned int target, cudaStream_t stream) {
-  k_fence_wait<<<1, 1, 0, stream>>>(fence, target);
+cudaError_t launch_fence_wait(unsigned int *fence, unsigned int *dead, unsigned int target, cudaStream_t stream) {
+  k_fence_wait<<<1, 1, 0, stream>>>(fence, dead, target);
   return cudaGetLastError();
 }
 

@@ -39,7 +39,8 @@ struct LaunchCfg {
   bool box;      // end casts that are outside the content box (SceneView::box_*)
   int kernel;    // variant selector (SVO_OPT_KERNEL)
   int sm_count;
-  int band_stride, band_offset;  // tile kernel: interleaved 8-row bands (0 = all bands)
+  int band_stride, band_offset;  // tile kernel: interleaved bands (stride 0 = all bands)
+  int band_ctas;                 // CTA rows (8 image rows each) per band
   int ctas_per_sm;             // persistent grid = sm_count * ctas_per_sm
   unsigned int *tile_counter;  // device word: the persistent kernel's tile queue head
 };
@@ -65,7 +66,7 @@ cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const
                                 unsigned long long *d_counters, cudaStream_t stream);
 struct FenceList { unsigned int *p[16]; int n; };
 cudaError_t launch_fence_signal(const FenceList &fl, cudaStream_t stream);
-cudaError_t launch_fence_wait(unsigned int *fence, unsigned int target, cudaStream_t stream);
+cudaError_t launch_fence_wait(unsigned int *fence, unsigned int *dead, unsigned int target, cudaStream_t stream);
 cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int blocks, uint32_t *sink, cudaStream_t stream);
 cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d_rays, const uint32_t *d_order, uint64_t n,
                         void *d_out, int maxDepth, cudaStream_t stream);

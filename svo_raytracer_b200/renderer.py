@@ -209,15 +209,15 @@ class SvoContext:
         self._check(self._lib.svo_fence_export(self._h, buf))
         return bytes(buf)
 
-    def fence_signal(self, fence_ptrs: Sequence[int] = ()):
-        """Enqueue: add 1 to each of the given (imported) fence counters; none given = this context's own."""
+    def fence_signal(self, fence_ptrs: Sequence[int] = (), slot: int = 0):
+        """Enqueue: add 1 to slot `slot` of each given (imported) fence counter; none given = this context's own."""
         n = len(fence_ptrs)
         arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(p) for p in fence_ptrs])
-        self._check(self._lib.svo_fence_signal(self._h, arr, n))
+        self._check(self._lib.svo_fence_signal(self._h, arr, n, slot))
 
-    def fence_wait(self, target: int):
-        """Enqueue on the owner: wait until the counter reaches `target` (modulo 2^32)."""
-        self._check(self._lib.svo_fence_wait(self._h, target & 0xFFFFFFFF))
+    def fence_wait(self, target: int, slot: int = 0):
+        """Enqueue: wait until slot `slot` of this context's own counter reaches `target` (modulo 2^32)."""
+        self._check(self._lib.svo_fence_wait(self._h, slot, target & 0xFFFFFFFF))
 
     def fence_reset(self):
         self._check(self._lib.svo_fence_reset(self._h))

@@ -238,11 +238,14 @@ def test_interleaved_band_partition_single_gpu(svo, oracle, terrain128):
         pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
         want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=7), W, H, nthreads=4)
         f = svo.camera_frame("B", frame_number=2, render_mode=0, max_depth=7)
-        for part in (2, 0, 1):
-            c.render_interleaved(f, part, 3)
-        got = {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(),
-               "hit_id": c.read_hit_id(), "iter": c.read_iter(), "primary_t": c.read_primary_t()}
-        _assert_planes_equal(got, want, "interleaved")
+        for band_rows, parts in ((8, 3), (24, 2), (64, 3), (32, 8)):
+            c.set_option(svo._lib.OPT_BAND_ROWS, band_rows)
+            c.render(svo.camera_frame("A", frame_number=1, render_mode=3, max_depth=7))  # scribble over every plane first
+            for part in reversed(range(parts)):
+                c.render_interleaved(f, part, parts)
+            got = {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(),
+                   "hit_id": c.read_hit_id(), "iter": c.read_iter(), "primary_t": c.read_primary_t()}
+            _assert_planes_equal(got, want, "interleaved %d rows x %d parts" % (band_rows, parts))
 
 
 def _ipc_worker(rank, world, port, q):
