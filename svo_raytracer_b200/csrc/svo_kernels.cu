@@ -20,10 +20,11 @@ __global__ void __launch_bounds__(128, 8) k_render_tile(SceneView sc, FrameParam
   // A band is band_ctas consecutive CTA rows (8 image rows each).  This launch renders bands number
   // i * band_stride + band_offset (counted from y0): with stride = number of GPUs and offset = rank this is the
   // interleaved image partition of the multi-GPU mode; stride 1 is the whole image.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  // CTA = 128 threads: 16x8 pixels (2x2 warps); CTA = 64 threads: 8x8 pixels (1x2 warps)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_x = blockDim.x >> 6;
+  const int x = (blockIdx.x * warps_x + (warp % warps_x)) * 8 + (lane & 7);
   const int band = (int)blockIdx.y / band_ctas, in_band = (int)blockIdx.y % band_ctas;
-  const int y = y0 + ((band * band_stride + band_offset) * band_ctas + in_band) * 8 + (warp >> 1) * 4 + (lane >> 3);
+  const int y = y0 + ((band * band_stride + band_offset) * band_ctas + in_band) * 8 + (warp / warps_x) * 4 + (lane >> 3);
   if (x >= W || y >= y1) return;
   shade_pixel<FAST, AUX, false, BOX>(sc, f, pl, W, H, x, y);
 }
@@ -294,11 +295,12 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
     k_render_tile_smem<<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1);
     return cudaGetLastError();
   }
-  const dim3 block(128);
+  const dim3 block(cfg.kernel == 5 ? 64 : 128);
   const int stride = cfg.band_stride > 0 ? cfg.band_stride : 1, offset = cfg.band_stride > 0 ? cfg.band_offset : 0;
   const int band_ctas = cfg.band_stride > 0 && cfg.band_ctas > 0 ? cfg.band_ctas : 1;
   const int bands = ((y1 - y0 + 7) / 8 + band_ctas - 1) / band_ctas;  // bands of band_ctas CTA rows (the last may be short)
-  const dim3 grid((W + 15) / 16, bands > offset ? ((bands - offset + stride - 1) / stride) * band_ctas : 0);
+  const bool small_cta = cfg.kernel == 5;  // experiment: 64-thread CTAs (8x8 pixels)
+  const dim3 grid(small_cta ? (W + 7) / 8 : (W + 15) / 16, bands > offset ? ((bands - offset + stride - 1) / stride) * band_ctas : 0);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
 #define SVO_LAUNCH_TILE(F, A, B) k_render_tile<F, A, B><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas)
   if (cfg.fast) {
