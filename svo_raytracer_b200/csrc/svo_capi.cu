@@ -91,6 +91,14 @@ int cuda_fail(svo_ctx *c, cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail((c), e_, #call); \
   } while (0)
 
+// device scratch freed on every return path
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <class T> T *as() const { return (T *)p; }
+};
+
 size_t plane_elem_bytes(int plane) {
   switch (plane) {
     case SVO_PLANE_COLOR_RGBA8: return 4;
@@ -836,8 +844,9 @@ int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
   if (rc) return rc;
   SVO_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_aux(c)) != SVO_OK) return rc;
-  unsigned long long *d = nullptr;
-  SVO_CUDA(c, cudaMalloc((void **)&d, 3 * sizeof(unsigned long long)));
+  DevBuf dbuf;
+  SVO_CUDA(c, dbuf.alloc(3 * sizeof(unsigned long long)));
+  unsigned long long *d = dbuf.as<unsigned long long>();
   SVO_CUDA(c, cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), c->stream));
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
@@ -846,7 +855,6 @@ int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
   unsigned long long h[3];
   SVO_CUDA(c, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(d);
   for (int i = 0; i < 3; i++) counters[i] = h[i];
   return SVO_OK;
 }
@@ -856,10 +864,11 @@ int svo_gather_probe(svo_ctx *c, uint64_t working_set_bytes, int loads_per_threa
   if (working_set_bytes < 4096 || loads_per_thread < 8) return fail(c, SVO_ERR_INVALID, "working set or load count too small");
   SVO_CUDA(c, cudaSetDevice(c->device));
   const uint64_t words = working_set_bytes / 8;
-  void *buf = nullptr;
-  uint32_t *sink = nullptr;
-  SVO_CUDA(c, cudaMalloc(&buf, words * 8));
-  SVO_CUDA(c, cudaMalloc((void **)&sink, 64));
+  DevBuf b0, b1;
+  SVO_CUDA(c, b0.alloc(words * 8));
+  SVO_CUDA(c, b1.alloc(64));
+  void *buf = b0.p;
+  uint32_t *sink = b1.as<uint32_t>();
   SVO_CUDA(c, cudaMemsetAsync(buf, 1, words * 8, c->stream));
   const int loads = (loads_per_thread + 7) / 8 * 8;
   const int blocks = c->sm_count * 8;
@@ -875,8 +884,6 @@ int svo_gather_probe(svo_ctx *c, uint64_t working_set_bytes, int loads_per_threa
     if (ms < best) best = ms;
   }
   c->launches += 6;
-  cudaFree(buf);
-  cudaFree(sink);
   *sectors_per_s = (double)blocks * 256.0 * (double)loads / ((double)best * 1e-3);
   return SVO_OK;
 }
@@ -886,19 +893,17 @@ int svo_math_probe(svo_ctx *c, int fn, const float *x, const float *y, float *ou
   if (n == 0) return SVO_OK;
   if (!x || !out || (fn == 4 && !y)) return fail(c, SVO_ERR_INVALID, "NULL argument");
   SVO_CUDA(c, cudaSetDevice(c->device));
-  float *dx = nullptr, *dy = nullptr, *dout = nullptr;
-  SVO_CUDA(c, cudaMalloc((void **)&dx, n * 4));
-  SVO_CUDA(c, cudaMalloc((void **)&dy, n * 4));
-  SVO_CUDA(c, cudaMalloc((void **)&dout, n * 4));
+  DevBuf bx, by, bo;
+  SVO_CUDA(c, bx.alloc(n * 4));
+  SVO_CUDA(c, by.alloc(n * 4));
+  SVO_CUDA(c, bo.alloc(n * 4));
+  float *dx = bx.as<float>(), *dy = by.as<float>(), *dout = bo.as<float>();
   SVO_CUDA(c, cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, c->stream));
   SVO_CUDA(c, cudaMemcpyAsync(dy, y ? y : x, n * 4, cudaMemcpyHostToDevice, c->stream));
   SVO_CUDA(c, launch_math_probe(fn, dx, dy, dout, n, c->stream));
   c->launches++;
   SVO_CUDA(c, cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, c->stream));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(dx);
-  cudaFree(dy);
-  cudaFree(dout);
   return SVO_OK;
 }
 

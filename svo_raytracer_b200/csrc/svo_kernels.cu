@@ -120,6 +120,86 @@ __global__ void __launch_bounds__(128) k_render_persistent(SceneView sc, FramePa
 }
 
 // ---------------------------------------------------------------------------
+// Kernel variant 6: variant 0 made CTA-synchronous between casts, with the rays of every cast after the first
+// re-dealt inside the CTA by direction octant.  Primary rays are traced by the thread that owns the pixel (an
+// 8x4 tile per warp is already coherent).  Bounce / shadow rays of the CTA's 128 pixels are counting-sorted in
+// shared memory by octant_mask (svotrace.comp:238-241; finished pixels last), traced by whichever thread gets
+// them, and the 28-byte end state of the cast (HitState) is handed back to the owning thread, which runs the
+// code after the loop and the shading exactly as in variant 0.  Rays of one octant visit children in the same
+// order and -- starting from neighbouring pixels -- share their descent, so a warp agrees on PUSH/ADVANCE/POP far
+// more often; finished pixels collect in whole warps that retire at once.  Per-ray arithmetic is untouched.
+// ---------------------------------------------------------------------------
+template <bool FAST, bool AUX, bool BOX>
+__global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  __shared__ float s_ray[7][128];        // origin xyz, dir xyz, cone flag
+  __shared__ unsigned char s_owner[128];  // slot -> thread that owns the pixel
+  __shared__ uint32_t s_hit[7][128];      // HitState per owning thread
+  __shared__ unsigned short s_cnt[4][10]; // per warp, per key
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  const bool valid = x < W && y < y1;
+  Pixel P;
+  bool wants = valid && pixel_begin(f, pl, W, H, x, y, P);
+  uint2 stk[kMaxScale + 1];
+  for (int cast = 0; __syncthreads_or(wants); cast++) {
+    HitState hs;
+    if (cast == 0) {
+      if (wants) {
+        Trav<FAST, false, BOX> T;
+        T.setup(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, nullptr);
+        hs = T.export_hit(T.outside_box() ? TRAV_MISS : T.run(sc, stk, nullptr));
+      }
+    } else {
+      // ---- counting sort of the CTA's rays by octant (key 8 = no ray) ----
+      const unsigned key = wants ? ((P.dir.x > 0.0f ? 1u : 0u) | (P.dir.y > 0.0f ? 2u : 0u) | (P.dir.z > 0.0f ? 4u : 0u)) : 8u;
+      unsigned my_rank = 0;
+#pragma unroll
+      for (unsigned b = 0; b < 9; b++) {
+        const unsigned m = __ballot_sync(0xffffffffu, key == b);
+        if (key == b) my_rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[warp][b] = (unsigned short)__popc(m);
+      }
+      __syncthreads();
+      unsigned base = 0;
+      for (unsigned b = 0; b < 9; b++)
+        for (int w = 0; w < 4; w++)
+          if (b < key || (b == key && w < warp)) base += s_cnt[w][b];
+      const unsigned slot = base + my_rank;
+      s_owner[slot] = (unsigned char)tid;
+      s_ray[0][slot] = P.origin.x; s_ray[1][slot] = P.origin.y; s_ray[2][slot] = P.origin.z;
+      s_ray[3][slot] = P.dir.x; s_ray[4][slot] = P.dir.y; s_ray[5][slot] = P.dir.z;
+      s_ray[6][slot] = (wants && P.cone) ? 1.0f : 0.0f;
+      unsigned nrays = 0;
+      for (int w = 0; w < 4; w++)
+        for (unsigned b = 0; b < 8; b++) nrays += s_cnt[w][b];
+      __syncthreads();
+      // ---- trace the ray in slot `tid`, hand its end state to the owner ----
+      if ((unsigned)tid < nrays) {
+        Trav<FAST, false, BOX> T;
+        T.setup(sc, mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]), f.maxDepth,
+                s_ray[6][tid] != 0.0f, f.coneDepth, nullptr);
+        const HitState r = T.export_hit(T.outside_box() ? TRAV_MISS : T.run(sc, stk, nullptr));
+        const unsigned o = s_owner[tid];
+        s_hit[0][o] = r.pidx; s_hit[1][o] = r.meta; s_hit[2][o] = r.ipx; s_hit[3][o] = r.ipy; s_hit[4][o] = r.ipz;
+        s_hit[5][o] = __float_as_uint(r.t_min); s_hit[6][o] = r.iter;
+      }
+      __syncthreads();
+      if (wants) {
+        hs.pidx = s_hit[0][tid]; hs.meta = s_hit[1][tid]; hs.ipx = s_hit[2][tid]; hs.ipy = s_hit[3][tid]; hs.ipz = s_hit[4][tid];
+        hs.t_min = __uint_as_float(s_hit[5][tid]); hs.iter = s_hit[6][tid];
+      }
+    }
+    if (wants) {
+      uint32_t loops;
+      const bool hit = finish_hit(sc, hs, P.res, loops);
+      wants = pixel_after_cast(f, P, hit, loops);
+    }
+  }
+  if (valid) pixel_store<AUX>(sc, f, pl, W, P);
+}
+
+// ---------------------------------------------------------------------------
 // Kernel variant 4 (experiment): variant 0 with the upper octree levels staged in shared memory.  Every CTA
 // copies the first kTopDescs descriptors (breadth-first array: levels 0..3 and part of 4) before tracing.
 // ---------------------------------------------------------------------------
@@ -287,6 +367,22 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
       if (cfg.aux) k_render_persistent<false, true><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
       else k_render_persistent<false, false><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
     }
+    return cudaGetLastError();
+  }
+  if (cfg.kernel == 6 && cfg.band_stride == 0) {
+    const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+#define SVO_LAUNCH_BINNED(F, A, B) k_render_tile_binned<F, A, B><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1)
+    if (cfg.fast) {
+      if (cfg.aux) SVO_LAUNCH_BINNED(true, true, false);
+      else if (cfg.box) SVO_LAUNCH_BINNED(true, false, true);
+      else SVO_LAUNCH_BINNED(true, false, false);
+    } else {
+      if (cfg.aux) SVO_LAUNCH_BINNED(false, true, false);
+      else if (cfg.box) SVO_LAUNCH_BINNED(false, false, true);
+      else SVO_LAUNCH_BINNED(false, false, false);
+    }
+#undef SVO_LAUNCH_BINNED
     return cudaGetLastError();
   }
   if (cfg.kernel == 4 && !cfg.aux && !cfg.fast && cfg.box && cfg.band_stride == 0) {

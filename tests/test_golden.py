@@ -49,7 +49,7 @@ def test_oracle_reproduces_golden_ray_stream(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 6])
 def test_cuda_reproduces_golden(svo, kernel):
     with svo.SvoContext(W, H) as c:
         c.set_option(svo._lib.OPT_AUX_PLANES, 1)

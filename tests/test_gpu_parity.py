@@ -27,10 +27,10 @@ def _assert_planes_equal(got, want, what):
         assert bad == 0, "%s: plane %s differs in %d of %d elements" % (what, k, bad, same.size)
 
 
-KERNELS = [0, 1, 2]  # SVO_OPT_KERNEL: 0 tile kernel, 1 persistent megakernel with lane refill, 2 wavefront
+KERNELS = [0, 1, 2, 6]  # SVO_OPT_KERNEL: 0 tile, 1 persistent megakernel, 2 wavefront, 6 tile + per-CTA octant binning of bounce rays
 
 
-@pytest.fixture(scope="module", params=KERNELS, ids=["tile", "persistent", "wavefront"])
+@pytest.fixture(scope="module", params=KERNELS, ids=["tile", "persistent", "wavefront", "binned"])
 def ctx512(request, svo, terrain512):
     c = svo.SvoContext(640, 360)
     c.set_option(svo._lib.OPT_AUX_PLANES, 1)
@@ -322,7 +322,7 @@ def test_two_gpu_tiles_over_nvlink(svo, oracle):
     assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32))
 
 
-@pytest.mark.parametrize("kernel", [0, 4])
+@pytest.mark.parametrize("kernel", [0, 4, 6])
 @pytest.mark.parametrize("cam", ["A", "B", "C"])
 @pytest.mark.parametrize("mode", [0, 2, 3, 4])
 def test_content_bounds_fast_path_keeps_outputs(svo, oracle, terrain512, cam, mode, kernel):
@@ -378,7 +378,7 @@ def _blob_world(oracle, n=64):
     return nodes
 
 
-@pytest.mark.parametrize("kernel", [0, 2])
+@pytest.mark.parametrize("kernel", [0, 2, 6])
 def test_mirror_material_and_deeper_paths(svo, oracle, kernel):
     """svo_frame.casts = 5 (4 bounces) with the mirror rule the shader has commented out (svotrace.comp:500-504) on
     value-4 spheres: the path-traced configuration of BASELINE configs[2], bit-exact against the oracle."""
