@@ -88,6 +88,8 @@ enum svo_option {
                               * iteration count of MISSING casts differs, so it is ignored in render mode 1 and with
                               * SVO_OPT_AUX_PLANES.  default 1 */
   ,SVO_OPT_BAND_ROWS = 7     /* image rows per band of svo_render_interleaved (multiple of 8); default 8 */
+  ,SVO_OPT_GPU_TRANSCODE = 8 /* 0/1: build the traversal descriptors from the uploaded stream on the device (default 1)
+                              * or on the host; same result bit for bit */
 };
 
 /* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and
@@ -214,6 +216,9 @@ int svo_build_terrain(const uint16_t *height, const uint8_t *mat, int n, int chu
  * nothing in the tree can be hit, [4..6] x/y/z bounds of the non-empty leaves as (lo << 32 | hi) in units of
  * 2^-24 of the cube edge, [7] hash of the per-depth bounds.  desc_out (optional) receives the triples. */
 int svo_transcode_probe(const uint8_t *nodes, uint64_t nbytes, int nthreads, uint64_t out[8], uint32_t *desc_out, uint64_t desc_cap);
+
+/* The same 8 words as svo_transcode_probe, computed from what the context actually holds on the device. */
+int svo_scene_probe(svo_ctx *ctx, uint64_t out[8]);
 
 /* Deterministic synthetic inputs for benchmarks and tests (the reference's
  * 8192^2 heightmap / material PNGs are absent upstream): n*n u16 heights with

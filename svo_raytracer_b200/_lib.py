@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_OOM, ERR_NO_DEVICE, ERR_CUDA, ERR_FORMAT, ERR_NO_SCENE = 0,
 PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIMARY_T, PLANE_RADIANCE = range(7)
 PLANE_BACK = 0x100
 # enum svo_option
-OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS, OPT_BAND_ROWS = 1, 2, 3, 4, 5, 6, 7
+OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS, OPT_BAND_ROWS, OPT_GPU_TRANSCODE = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class SvoError(RuntimeError):
@@ -87,6 +87,7 @@ SYMBOLS = {
     "svo_gather_probe": (_i, [_vp, _u64, _i, C.POINTER(C.c_double)]),
     "svo_math_probe": (_i, [_vp, _i, _vp, _vp, _vp, _u64]),
     "svo_terrain_generate": (_i, [_i, _i, _vp, _vp, _i]),
+    "svo_scene_probe": (_i, [_vp, C.POINTER(_u64 * 8)]),
     "svo_transcode_probe": (_i, [_vp, _u64, _i, C.POINTER(_u64 * 8), _vp, _u64]),
     "svo_build_terrain": (_i, [_vp, _vp, _i, _i, _vp, _u64, C.POINTER(_u64), _i]),
 }

@@ -39,7 +39,6 @@ struct svo_ctx {
   uint32_t ndesc = 0, nlevels = 0;
   uint32_t first_word_zero = 1;
   bool have_scene = false;
-  std::vector<uint8_t> h_raw;  // host shadow of the stream (range updates re-transcode from it)
   // planes
   void *own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *bound[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -56,7 +55,7 @@ struct svo_ctx {
   uint64_t sort_cap = 0;
   size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
@@ -235,35 +234,75 @@ int export_handle(svo_ctx *c, void *ptr, uint8_t handle[72]) {
 // that count: not in render mode 1 (iteration heat map, svotrace.comp:561-571) and not with the validation planes.
 bool box_allowed(const svo_ctx *c, const svo_frame *f) { return c->opt_bounds && !c->opt_aux && f->renderMode != 1; }
 
-// (re)build the device descriptor arrays from the host shadow of the stream
+// (re)build the device descriptor arrays from the node stream in d_raw
 int retranscode(svo_ctx *c) {
-  Transcoded t;
-  std::string err;
-  if (!transcode_stream(c->h_raw.data(), c->nbytes, t, err)) return fail(c, SVO_ERR_FORMAT, err);
-  const uint64_t nd = t.desc.size();
-  if (nd > c->desc_cap) {
-    if (c->d_desc) cudaFree(c->d_desc);
-    if (c->d_refbase) cudaFree(c->d_refbase);
-    c->d_desc = nullptr;
-    c->d_refbase = nullptr;
-    c->desc_cap = 0;
-    const uint64_t cap = nd + nd / 8 + 64;
-    SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, cap * sizeof(uint2)));
-    SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, cap * sizeof(uint32_t)));
-    c->desc_cap = cap;
-  }
+  uint64_t nd = 0;
+  uint32_t nlevels = 0;
+  CellBox leaf_box, depth_box[24];
+  bool done = false;
   // the kernels may still be reading the previous arrays
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
-  SVO_CUDA(c, cudaMemcpyAsync(c->d_desc, t.desc.data(), nd * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
-  SVO_CUDA(c, cudaMemcpyAsync(c->d_refbase, t.refbase.data(), nd * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // t goes out of scope
+  if (c->opt_gpu_transcode) {
+    // a tree has at most one interior record per 7 bytes; anything larger is aliased/cyclic and goes to the host
+    // path, which reports it
+    const uint64_t cap = c->nbytes / 7 + 4096;
+    DevBuf tmp_desc, tmp_ref;
+    SVO_CUDA(c, tmp_desc.alloc(cap * sizeof(uint2)));
+    SVO_CUDA(c, tmp_ref.alloc(cap * sizeof(uint32_t)));
+    bool overflow = false;
+    SVO_CUDA(c, gpu_transcode(c->d_raw, c->nbytes, tmp_desc.as<uint2>(), tmp_ref.as<uint32_t>(), cap, &nd, &nlevels, &leaf_box, depth_box,
+                              &overflow, c->stream));
+    c->launches += 2 + 3 * (uint64_t)nlevels;
+    if (!overflow) {
+      if (nd > c->desc_cap) {
+        if (c->d_desc) cudaFree(c->d_desc);
+        if (c->d_refbase) cudaFree(c->d_refbase);
+        c->d_desc = nullptr;
+        c->d_refbase = nullptr;
+        c->desc_cap = 0;
+        const uint64_t want = nd + nd / 8 + 64;
+        SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, want * sizeof(uint2)));
+        SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, want * sizeof(uint32_t)));
+        c->desc_cap = want;
+      }
+      SVO_CUDA(c, cudaMemcpyAsync(c->d_desc, tmp_desc.p, nd * sizeof(uint2), cudaMemcpyDeviceToDevice, c->stream));
+      SVO_CUDA(c, cudaMemcpyAsync(c->d_refbase, tmp_ref.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+      SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+      done = true;
+    }
+  }
+  if (!done) {  // host path (SVO_OPT_GPU_TRANSCODE 0, or a stream the device pass refused)
+    std::vector<uint8_t> h_raw(c->nbytes);
+    if (c->nbytes) SVO_CUDA(c, cudaMemcpy(h_raw.data(), c->d_raw, c->nbytes, cudaMemcpyDeviceToHost));
+    Transcoded t;
+    std::string err;
+    if (!transcode_stream(h_raw.data(), c->nbytes, t, err)) return fail(c, SVO_ERR_FORMAT, err);
+    nd = t.desc.size();
+    if (nd > c->desc_cap) {
+      if (c->d_desc) cudaFree(c->d_desc);
+      if (c->d_refbase) cudaFree(c->d_refbase);
+      c->d_desc = nullptr;
+      c->d_refbase = nullptr;
+      c->desc_cap = 0;
+      const uint64_t cap = nd + nd / 8 + 64;
+      SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, cap * sizeof(uint2)));
+      SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, cap * sizeof(uint32_t)));
+      c->desc_cap = cap;
+    }
+    SVO_CUDA(c, cudaMemcpyAsync(c->d_desc, t.desc.data(), nd * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    SVO_CUDA(c, cudaMemcpyAsync(c->d_refbase, t.refbase.data(), nd * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // t goes out of scope
+    nlevels = (uint32_t)t.level_start.size();
+    leaf_box = t.leaf_box;
+    for (int d = 0; d < 24; d++) depth_box[d] = t.depth_box[d];
+  }
   c->ndesc = (uint32_t)nd;
-  c->nlevels = (uint32_t)t.level_start.size();
+  c->nlevels = nlevels;
   uint32_t w0 = 0;
-  for (uint64_t i = 0; i < 4 && i < c->nbytes; i++) w0 |= c->h_raw[i];
+  if (c->nbytes) SVO_CUDA(c, cudaMemcpy(&w0, c->d_raw, c->nbytes < 4 ? c->nbytes : 4, cudaMemcpyDeviceToHost));
   c->first_word_zero = (w0 == 0);
-  c->leaf_box = t.leaf_box;
-  for (int d = 0; d < 24; d++) c->depth_box[d] = t.depth_box[d];
+  c->leaf_box = leaf_box;
+  for (int d = 0; d < 24; d++) c->depth_box[d] = depth_box[d];
   c->have_scene = true;
 
   // L2 access-policy window over the hot upper levels (a prefix of the BFS array)
@@ -404,6 +443,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
     case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
+    case SVO_OPT_GPU_TRANSCODE: c->opt_gpu_transcode = value != 0; return SVO_OK;
     case SVO_OPT_BAND_ROWS:
       if (value < 8 || value > 4096 || value % 8) return fail(c, SVO_ERR_INVALID, "band rows must be a multiple of 8");
       c->opt_band_rows = (int)value;
@@ -421,6 +461,7 @@ int svo_get_option(const svo_ctx *c, int option, int64_t *value) {
     case SVO_OPT_RAY_SORT: *value = c->opt_sort; return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: *value = c->opt_bounds; return SVO_OK;
     case SVO_OPT_BAND_ROWS: *value = c->opt_band_rows; return SVO_OK;
+    case SVO_OPT_GPU_TRANSCODE: *value = c->opt_gpu_transcode; return SVO_OK;
     default: return fail(const_cast<svo_ctx *>(c), SVO_ERR_INVALID, "unknown option");
   }
 }
@@ -447,7 +488,6 @@ int svo_upload(svo_ctx *c, const uint8_t *nodes, uint64_t nbytes) {
     SVO_CUDA(c, cudaMalloc((void **)&c->d_raw, cap));
     c->raw_cap = cap;
   }
-  c->h_raw.assign(nodes, nodes + nbytes);
   c->nbytes = nbytes;
   if (nbytes) SVO_CUDA(c, cudaMemcpyAsync(c->d_raw, nodes, nbytes, cudaMemcpyHostToDevice, c->stream));
   return retranscode(c);
@@ -471,13 +511,10 @@ int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t 
     c->raw_cap = cap;
   }
   if (end > c->nbytes) {
-    // bytes between the old end and `start` were never uploaded: they are zero on the
-    // host shadow and must be zero on the device too
+    // bytes between the old end and `start` were never uploaded: they read as zero
     if (start > c->nbytes) SVO_CUDA(c, cudaMemsetAsync(c->d_raw + c->nbytes, 0, start - c->nbytes, c->stream));
-    c->h_raw.resize(end, 0);
     c->nbytes = end;
   }
-  memcpy(c->h_raw.data() + start, nodes + start, end - start);
   SVO_CUDA(c, cudaMemcpyAsync(c->d_raw + start, nodes + start, end - start, cudaMemcpyHostToDevice, c->stream));
   return retranscode(c);
 }
@@ -834,6 +871,32 @@ int svo_transcode_probe(const uint8_t *nodes, uint64_t nbytes, int nthreads, uin
     for (size_t i = 0; i < t.desc.size() && 3 * i + 2 < desc_cap; i++) {
       desc_out[3 * i] = t.desc[i].x; desc_out[3 * i + 1] = t.desc[i].y; desc_out[3 * i + 2] = t.refbase[i];
     }
+  return SVO_OK;
+}
+
+int svo_scene_probe(svo_ctx *c, uint64_t out[8]) {
+  if (!c || !out) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_scene_probe before svo_upload");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint2> desc(c->ndesc);
+  std::vector<uint32_t> ref(c->ndesc);
+  SVO_CUDA(c, cudaMemcpy(desc.data(), c->d_desc, (size_t)c->ndesc * sizeof(uint2), cudaMemcpyDeviceToHost));
+  SVO_CUDA(c, cudaMemcpy(ref.data(), c->d_refbase, (size_t)c->ndesc * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](uint32_t v) { for (int i = 0; i < 4; i++) { h ^= (v >> (8 * i)) & 0xFFu; h *= 1099511628211ull; } };
+  for (size_t i = 0; i < desc.size(); i++) { mix(desc[i].x); mix(desc[i].y); mix(ref[i]); }
+  out[0] = c->ndesc;
+  out[1] = c->nlevels;
+  out[2] = h;
+  CellBox b = c->leaf_box;
+  for (const CellBox &d : c->depth_box) b.add(d);
+  out[3] = b.empty();
+  out[4] = ((uint64_t)c->leaf_box.lo[0] << 32) | c->leaf_box.hi[0];
+  out[5] = ((uint64_t)c->leaf_box.lo[1] << 32) | c->leaf_box.hi[1];
+  out[6] = ((uint64_t)c->leaf_box.lo[2] << 32) | c->leaf_box.hi[2];
+  out[7] = 0;
+  for (const CellBox &d : c->depth_box) out[7] = out[7] * 31 + d.lo[1] + 7 * d.hi[1];
   return SVO_OK;
 }
 

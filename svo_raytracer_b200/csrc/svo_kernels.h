@@ -72,6 +72,9 @@ cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d
                         void *d_out, int maxDepth, cudaStream_t stream);
 cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, float *beam, int W, int H,
                         cudaStream_t stream);
+struct CellBox;
+cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, uint32_t *refbase, uint64_t cap, uint64_t *ndesc,
+                          uint32_t *nlevels, CellBox *leaf_box, CellBox *depth_box, bool *overflow, cudaStream_t stream);
 size_t ray_sort_temp_bytes(uint64_t n);
 cudaError_t launch_ray_sort(const void *d_rays, uint64_t n, uint32_t *keys, uint32_t *keys_alt, uint32_t *idx, uint32_t *order_out,
                             void *temp, size_t temp_bytes, cudaStream_t stream);

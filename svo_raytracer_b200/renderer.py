@@ -112,6 +112,12 @@ class SvoContext:
             raise ValueError("end beyond the buffer")
         self._check(self._lib.svo_upload_range(self._h, nodes.ctypes.data_as(C.c_void_p), int(start), int(end)))
 
+    def scene_probe(self):
+        """Hash / counts / bounds of the descriptors held on the device (same 8 words as svo_transcode_probe)."""
+        out = (C.c_uint64 * 8)()
+        self._check(self._lib.svo_scene_probe(self._h, C.byref(out)))
+        return [int(v) for v in out]
+
     def scene_info(self) -> dict:
         info = (C.c_uint64 * 4)()
         self._check(self._lib.svo_scene_info(self._h, C.byref(info)))

@@ -466,3 +466,32 @@ def test_pipelined_readback(svo, oracle, terrain128):
         want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=9, render_mode=0, max_depth=7), W, H,
                                 nthreads=4, planes=("rgba8",))
         assert np.array_equal(c.read_color_rgba8(), want["rgba8"])
+
+
+def test_gpu_transcode_equals_host_transcode(svo, oracle, terrain128, terrain512):
+    """svo_upload builds the traversal descriptors on the device (svo_gpu_transcode.cu); the host version
+    (svo_transcode.cpp) must give the same descriptors, reference offsets, level count and content bounds."""
+    from test_transcode import probe
+    import svo_stream as S
+    kat = S.serialise(S.interior(1, [S.interior(5, [S.nonsurf(1 if i in (0, 7) else 0) for i in range(8)]), S.surface(2, 955), S.subdiv(0),
+                                     S.nonsurf(3)] + [S.nonsurf(0)] * 4))
+    streams = [terrain128, terrain512, kat, np.zeros(0, np.uint8), np.zeros(7, np.uint8), np.array([1, 0, 0, 0, 0, 0, 0], np.uint8),
+               _blob_world(oracle)]
+    with svo.SvoContext(64, 64) as c:
+        for nodes in streams:
+            want, _ = probe(svo, nodes, 4)
+            for gpu in (1, 0):
+                c.set_option(svo._lib.OPT_GPU_TRANSCODE, gpu)
+                c.upload(nodes)
+                assert c.scene_probe() == want, (len(nodes), gpu)
+        # partial upload re-transcodes on the device as well
+        edited = terrain128.copy()
+        edited[100:200] = terrain128[300:400]
+        c.set_option(svo._lib.OPT_GPU_TRANSCODE, 1)
+        c.upload(terrain128)
+        try:
+            c.upload_range(edited, 100, 200)
+            want, _ = probe(svo, edited, 2)
+            assert c.scene_probe() == want
+        except svo.SvoError as e:  # a scrambled stream may legitimately be refused, but then by both paths
+            assert e.code == svo._lib.ERR_FORMAT
