@@ -495,3 +495,47 @@ def test_gpu_transcode_equals_host_transcode(svo, oracle, terrain128, terrain512
             assert c.scene_probe() == want
         except svo.SvoError as e:  # a scrambled stream may legitimately be refused, but then by both paths
             assert e.code == svo._lib.ERR_FORMAT
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_worlds_random_cameras(svo, oracle, seed):
+    """Fuzz: random sparse 32^3 / 64^3 voxel worlds (all four record types, deep empty regions, big solid blocks),
+    random camera poses inside and outside the cube, random frame parameters -- every plane bit-exact, with the
+    validation planes (no shortcuts) and without them (content-bounds shortcut on)."""
+    rng = np.random.default_rng(seed)
+    n = 32 if seed % 2 else 64
+    vox = np.zeros((n, n, n), np.uint8)
+    pts = rng.integers(0, n, size=(rng.integers(50, 600), 3))
+    vox[pts[:, 2], pts[:, 1], pts[:, 0]] = rng.integers(1, 5, size=len(pts))
+    for _ in range(3):
+        lo = rng.integers(0, n - 10, 3)
+        sz = rng.integers(3, 10, 3)
+        vox[lo[2]:lo[2] + sz[2], lo[1]:lo[1] + sz[1], lo[0]:lo[0] + sz[0]] = rng.integers(1, 4)
+    nodes, _ = oracle.build_dense(vox)
+    W, H = 96, 64
+    depth = int(np.log2(n))
+    with svo.SvoContext(W, H) as c:
+        c.upload(nodes)
+        for trial in range(6):
+            pos = rng.uniform(0.7, 2.3, 3) if trial % 2 else rng.uniform(1.1, 1.9, 3)
+            fwd = rng.normal(size=3)
+            fwd /= np.linalg.norm(fwd)
+            up = np.cross(fwd, rng.normal(size=3))
+            up /= np.linalg.norm(up)
+            right = np.cross(fwd, up)
+            corners = [fwd + sx * 1.2 * right + sy * 0.8 * up for sx in (-1, 1) for sy in (-1, 1)]
+            kw = dict(frame_number=int(rng.integers(1, 50)), render_mode=int(rng.choice([0, 0, 2, 2, 1, 3])),
+                      max_depth=int(rng.integers(max(1, depth - 2), depth + 1)), casts=int(rng.integers(1, 4)),
+                      cone_depth=int(rng.integers(1, depth + 1)), mirror_value=int(rng.choice([0, 4])))
+            of = oracle.make_frame(pos, *corners, **kw)
+            want, st = oracle.render(nodes, of, W, H, nthreads=4)
+            assert st.stale_pops == 0
+            f = svo.make_frame(pos, *corners, **kw)
+            c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+            _assert_planes_equal(_render_gpu(svo, c, f), want, "seed %d trial %d %s" % (seed, trial, kw))
+            c.set_option(svo._lib.OPT_AUX_PLANES, 0)
+            c.render(f)
+            assert np.array_equal(c.read_color_rgba8(), want["rgba8"]), (seed, trial, kw)
+            d = c.read_depth()
+            same = (d.view(np.uint32) == want["depth"].view(np.uint32)) | (np.isnan(d) & np.isnan(want["depth"]))
+            assert same.all(), (seed, trial, kw)
