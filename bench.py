@@ -62,12 +62,12 @@ def parse():
     return ap.parse_args()
 
 
-def world(size: int):
-    """Synthetic heightmap world, built by the product's own generator (host code)."""
+def world(size: int, nthreads: int = 0):
+    """Synthetic heightmap world, built by the product's own generator (host code; every rank builds its replica)."""
     import svo_raytracer_b200 as svo
     t0 = time.time()
-    hm, mm = svo.terrain_inputs(size)
-    nodes = svo.build_terrain(hm, mm, size, min(size, 1024))
+    hm, mm = svo.terrain_inputs(size, nthreads=nthreads)
+    nodes = svo.build_terrain(hm, mm, size, min(size, 1024), nthreads=nthreads)
     return nodes, time.time() - t0
 
 
@@ -202,7 +202,7 @@ def main():
     dev = local_rank if world_size > 1 else 0
     torch.cuda.set_device(dev)
 
-    nodes, build_s = world(a.size)
+    nodes, build_s = world(a.size, max(1, cores // world_size))
     ctx = svo.SvoContext(W, H, device=dev)
     ctx.set_option(L.OPT_FAST_MATH, a.fast_math)
     ctx.set_option(L.OPT_KERNEL, a.kernel)

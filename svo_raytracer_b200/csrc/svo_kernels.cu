@@ -108,9 +108,7 @@ __global__ void __launch_bounds__(128) k_render_persistent(SceneView sc, FramePa
     }
     // ---- shade finished casts; they either cast again or release the lane ----------
     if (state == CAST_DONE) {
-      uint32_t loops;
-      const bool hit = T.finish(sc, status, P.res, loops);
-      if (pixel_after_cast(f, P, hit, loops)) state = NEED_SETUP;
+      if (pixel_finish_cast(sc, f, P, T.export_hit(status))) state = NEED_SETUP;
       else {
         pixel_store<AUX>(sc, f, pl, W, P);
         state = NEED_PIXEL;
@@ -190,11 +188,7 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
         hs.t_min = __uint_as_float(s_hit[5][tid]); hs.iter = s_hit[6][tid];
       }
     }
-    if (wants) {
-      uint32_t loops;
-      const bool hit = finish_hit(sc, hs, P.res, loops);
-      wants = pixel_after_cast(f, P, hit, loops);
-    }
+    if (wants) wants = pixel_finish_cast(sc, f, P, hs);
   }
   if (valid) pixel_store<AUX>(sc, f, pl, W, P);
 }

@@ -121,7 +121,9 @@ struct HitState {
 };
 
 // after the loop (svotrace.comp:371-431).  Returns hit; `loops` = iterations run.
-SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uint32_t &loops) {
+// `attrs` = false skips the reads of the hit record (value, packed normal) and everything derived from them: used
+// for casts whose shading provably never looks at them (cast_needs_attrs).
+SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uint32_t &loops, bool attrs = true) {
   const uint32_t iter = hs.iter;
   loops = iter;
   if ((hs.meta & 3u) != (uint32_t)TRAV_HIT) {
@@ -133,10 +135,19 @@ SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uin
     }
     return false;
   }
-  // hit: extractChild again (:381) on the ORIGINAL bytes
   const uint32_t cs = (hs.meta >> 2) & 7u, oct = (hs.meta >> 5) & 7u;
   const int scale = (int)((hs.meta >> 8) & 31u);
   const float scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);
+  if (!attrs) {  // only what trace() reads after a cast whose hit record it ignores: t, scale, iter, depth
+    res.t = hs.t_min;
+    res.iter = iter;
+    res.scale = scale_exp2;
+    res.depth = (uint32_t)(kMaxScale - scale);
+    res.dbg = fmul(0.005f, (float)iter);
+    res.dbg_init = 0;
+    return true;
+  }
+  // hit: extractChild again (:381) on the ORIGINAL bytes
   const uint32_t codes = __ldg(sc.desc + hs.pidx).y & 0xFFFFu;
   const uint32_t ptr = __ldg(sc.refbase + hs.pidx) + child_offset(codes, cs);
   const uint32_t code = (codes >> (2u * cs)) & 3u;
@@ -389,20 +400,20 @@ struct Trav {
     hs.iter = iter;
     return hs;
   }
-  __device__ __forceinline__ bool finish(const SceneView &sc, int status, CastRes &res, uint32_t &loops) const {
-    return finish_hit(sc, export_hit(status), res, loops);
+  __device__ __forceinline__ bool finish(const SceneView &sc, int status, CastRes &res, uint32_t &loops, bool attrs = true) const {
+    return finish_hit(sc, export_hit(status), res, loops, attrs);
   }
 };
 
 // intersectOctree run to completion.
 template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
-                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr) {
+                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr, bool attrs = true) {
   uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
   Trav<FAST, STATS, BOX, TOP> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
-  if (T.outside_box()) return T.finish(sc, TRAV_MISS, res, loops);  // the ray never reaches the content box
-  return T.finish(sc, T.run(sc, stk, rs), res, loops);
+  if (T.outside_box()) return T.finish(sc, TRAV_MISS, res, loops, attrs);  // the ray never reaches the content box
+  return T.finish(sc, T.run(sc, stk, rs), res, loops, attrs);
 }
 
 SVO_DI void matcolor_table(uint32_t value, vec3 &mc) {  // :514-522, :578-586
@@ -580,6 +591,33 @@ SVO_DI bool pixel_after_cast(const FrameParams &f, Pixel &P, bool intersect, uin
   return false;
 }
 
+// Does trace() read the hit record (value / normal / voxelPos) of the cast that is about to run?  Not for the
+// LAST cast of the mode-0 loop -- a hit there only sets depth and multiplies a mask nobody reads again (:531-535;
+// accum is returned as is) -- and not for the shadow ray of mode 2 (:607-619 reads t, scale and iter only).
+SVO_DI bool cast_needs_attrs(const FrameParams &f, const Pixel &P) {
+  if (f.renderMode == 0) return !(P.cast_i > 0 && P.cast_i + 1 >= f.casts);
+  if (f.renderMode == 2) return P.cast_i == 0;
+  return true;
+}
+// The code of trace() after the last cast of the mode-0 loop when that cast HIT, with the dead parts removed:
+// depth = res.t; accum += mask * matemi (matemi = 0, kept because it propagates a NaN/inf mask); return accum.
+SVO_DI void pixel_after_last_hit(Pixel &P) {
+  P.depth = P.res.t;
+  P.acc = mk3(fadd(P.acc.x, fmul(P.mask.x, 0.0f)), fadd(P.acc.y, fmul(P.mask.y, 0.0f)), fadd(P.acc.z, fmul(P.mask.z, 0.0f)));
+  P.color = P.acc;
+}
+// finish one cast of pixel P (status known): returns true if the pixel wants another cast
+SVO_DI bool pixel_finish_cast(const SceneView &sc, const FrameParams &f, Pixel &P, const HitState hs) {
+  const bool attrs = cast_needs_attrs(f, P);
+  uint32_t loops;
+  const bool hit = finish_hit(sc, hs, P.res, loops, attrs);
+  if (!attrs && hit && f.renderMode == 0) {
+    pixel_after_last_hit(P);
+    return false;
+  }
+  return pixel_after_cast(f, P, hit, loops);
+}
+
 SVO_DI unsigned char quant8(float c) {  // imageStore to rgba8 (:726), DESIGN.md U5
   if (c != c) return 0;
   c = fminf(fmaxf(c, 0.0f), 1.0f);
@@ -626,8 +664,14 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
     bool more;
     do {
       uint32_t loops = 0;
-      const bool hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs);
-      more = pixel_after_cast(f, P, hit, loops);
+      const bool attrs = cast_needs_attrs(f, P);
+      const bool hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+      if (!attrs && hit && f.renderMode == 0) {
+        pixel_after_last_hit(P);
+        more = false;
+      } else {
+        more = pixel_after_cast(f, P, hit, loops);
+      }
     } while (more);
   }
   pixel_store<AUX>(sc, f, pl, W, P);

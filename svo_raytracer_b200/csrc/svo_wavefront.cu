@@ -192,9 +192,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(SceneView sc, FrameParams f, P
       HitState hs;
       hs.pidx = ha.x; hs.meta = ha.y; hs.ipx = ha.z; hs.ipy = ha.w;
       hs.ipz = hb.x; hs.t_min = __uint_as_float(hb.y); hs.iter = hb.z;
-      uint32_t loops;
-      const bool hit = finish_hit(sc, hs, P.res, loops);
-      more = pixel_after_cast(f, P, hit, loops);
+      more = pixel_finish_cast(sc, f, P, hs);
       if (STAGE0 && AUX) {  // the primary-cast planes
         const size_t p = (size_t)P.y * (size_t)W + (size_t)P.x;
         pl.hit_id[p] = P.hit_id;
