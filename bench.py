@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--casts", type=int, default=2, help="mode-0 loop count (reference: 2 = primary + 1 diffuse bounce)")
+    ap.add_argument("--mode", type=int, default=0, help="render mode (0 = the GI path of the metric; 2 = the engine's default)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
@@ -71,11 +73,14 @@ def world(size: int, nthreads: int = 0):
     return nodes, time.time() - t0
 
 
+CASTS, MODE = 2, 0
+
+
 def frame_for(step: int, size: int):
     import svo_raytracer_b200 as svo
     depth = min(13, max(1, int(np.log2(size))))  # MAX_DEPTH = log2 N (13 for the reference's 8192^3, svotrace.comp:40)
-    return svo.camera_frame(CAM_CYCLE[step % len(CAM_CYCLE)], frame_number=step + 1, render_mode=0,
-                            max_depth=depth, casts=2, cone_depth=11)
+    return svo.camera_frame(CAM_CYCLE[step % len(CAM_CYCLE)], frame_number=step + 1, render_mode=MODE,
+                            max_depth=depth, casts=CASTS, cone_depth=11)
 
 
 class ClockSampler:
@@ -169,13 +174,14 @@ def cpu_arm(nodes, size, steps, warmup, budget_s, cores):
 
 def main():
     a = parse()
-    global W, H
-    W, H = a.width, a.height
+    global W, H, CASTS, MODE
+    W, H, CASTS, MODE = a.width, a.height, a.casts, a.mode
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    workload = "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode 0 (primary + 1 diffuse bounce), cameras A/B/C cycled" % (a.size, W, H)
+    what = "primary + %d diffuse bounce%s" % (CASTS - 1, "s" if CASTS > 2 else "") if MODE == 0 else "render mode %d" % MODE
+    workload = "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode %d (%s), cameras A/B/C cycled" % (a.size, W, H, MODE, what)
 
     if a.impl == "reference":
         if rank != 0:
@@ -420,7 +426,7 @@ def main():
     # dram__bytes_write.sum, mean of the three camera frames), profiles/r01_tile_full.json
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_tile_full.json")
-    if os.path.exists(tpath) and a.size == 8192 and a.kernel == 0 and world_size == 1 and (W, H) == (1920, 1080):
+    if os.path.exists(tpath) and a.size == 8192 and a.kernel == 0 and world_size == 1 and (W, H, CASTS, MODE) == (1920, 1080, 2, 0):
         caps = json.load(open(tpath))
         traffic = float(np.mean([c["dram_traffic_MB"] for c in caps])) * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
