@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--camera", default="cycle", choices=["cycle", "A", "B", "C"], help="camera pose per step (default: A, B, C cycled)")
     ap.add_argument("--casts", type=int, default=2, help="mode-0 loop count (reference: 2 = primary + 1 diffuse bounce)")
     ap.add_argument("--mode", type=int, default=0, help="render mode (0 = the GI path of the metric; 2 = the engine's default)")
     ap.add_argument("--width", type=int, default=1920)
@@ -174,14 +175,17 @@ def cpu_arm(nodes, size, steps, warmup, budget_s, cores):
 
 def main():
     a = parse()
-    global W, H, CASTS, MODE
+    global W, H, CASTS, MODE, CAM_CYCLE
     W, H, CASTS, MODE = a.width, a.height, a.casts, a.mode
+    if a.camera != "cycle":
+        CAM_CYCLE = (a.camera,) * 3
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
     what = "primary + %d diffuse bounce%s" % (CASTS - 1, "s" if CASTS > 2 else "") if MODE == 0 else "render mode %d" % MODE
-    workload = "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode %d (%s), cameras A/B/C cycled" % (a.size, W, H, MODE, what)
+    workload = "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode %d (%s), %s" % (
+        a.size, W, H, MODE, what, "cameras A/B/C cycled" if a.camera == "cycle" else "camera " + a.camera)
 
     if a.impl == "reference":
         if rank != 0:
