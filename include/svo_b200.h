@@ -78,18 +78,20 @@ enum svo_plane {
 };
 
 enum svo_option {
-  SVO_OPT_AUX_PLANES = 1,  /* 0/1: also write planes 3..6 (validation outputs); default 0 */
-  SVO_OPT_FAST_MATH = 2,   /* 0: --fmad=false validation kernels (default, bit-exact contract); 1: fma-contracted build */
-  SVO_OPT_KERNEL = 3,      /* traversal kernel variant; default 0 = best measured */
-  SVO_OPT_L2_PERSIST = 4,  /* 0/1: pin the upper octree levels with an L2 access-policy window; default 1 */
-  SVO_OPT_RAY_SORT = 5,    /* 0/1: bin ray streams (>= 65536 rays) by direction octant + origin Morton code before tracing; default 1 */
-  SVO_OPT_CONTENT_BOUNDS = 6 /* 0/1: end casts that cannot hit anything once they are outside the bounding box of the
-                              * octree's non-empty leaves (computed at upload).  Outputs are unchanged; only the
-                              * iteration count of MISSING casts differs, so it is ignored in render mode 1 and with
-                              * SVO_OPT_AUX_PLANES.  default 1 */
-  ,SVO_OPT_BAND_ROWS = 7     /* image rows per band of svo_render_interleaved (multiple of 8); default 8 */
-  ,SVO_OPT_GPU_TRANSCODE = 8 /* 0/1: build the traversal descriptors from the uploaded stream on the device (default 1)
-                              * or on the host; same result bit for bit */
+  SVO_OPT_AUX_PLANES = 1,     /* 0/1: also write planes 3..6 (validation outputs); default 0 */
+  SVO_OPT_FAST_MATH = 2,      /* 0: separately rounded arithmetic = the --fmad=false validation semantics (default, the bit-exact
+                               * contract); 1: t arithmetic contracted into FFMA (not bit-exact, measured slower) */
+  SVO_OPT_KERNEL = 3,         /* kernel variant: 0 tile kernel (default, fastest), 1 persistent megakernel,
+                               * 2 wavefront, 4 tile + shared-memory upper levels, 5 64-thread CTAs, 6 tile + per-CTA octant binning */
+  SVO_OPT_L2_PERSIST = 4,     /* 0/1: L2 access-policy window (persisting) over the upper octree levels, applied at the next
+                               * upload; default 0 (measured: no effect, the path is not memory bound) */
+  SVO_OPT_RAY_SORT = 5,       /* 0/1: trace ray streams of >= 65536 rays in (direction octant, origin Morton code) order; default 1 */
+  SVO_OPT_CONTENT_BOUNDS = 6, /* 0/1: end casts that cannot hit anything once they are outside the bounding box of the octree's
+                               * non-empty leaves (computed at upload).  Outputs are unchanged; only the iteration count of
+                               * MISSING casts differs, so it is ignored in render mode 1 and with SVO_OPT_AUX_PLANES.  default 1 */
+  SVO_OPT_BAND_ROWS = 7,      /* image rows per band of svo_render_interleaved (multiple of 8); default 8 */
+  SVO_OPT_GPU_TRANSCODE = 8   /* 0/1: build the traversal descriptors from the uploaded stream on the device (default 1) or on
+                               * the host; same result bit for bit */
 };
 
 /* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and

@@ -113,10 +113,8 @@ typedef struct {
 
 static inline int find_msb(uint32_t v) { return v ? 31 - __builtin_clz(v) : -1; }
 
-/* svotrace.comp:211-432.  `beam_variant` selects the three svobeam.comp
- * differences used by svo_oracle_beam (no code-2 in extractChild is NOT
- * reproduced: the beam pass reads the same tree and code 2 only changes a
- * record's size there, svobeam.comp:124-143 -- documented as upstream bug). */
+/* svotrace.comp:211-432.  Returns 1 on hit; on miss -(loop iterations) - 1, so that callers can fill the iter
+ * plane (U7) without a castResult field the shader does not have.  `st` is the invocation's octstack (U3). */
 static int intersect_octree(const buf_t *b, stack_t *st, const float origin[3], const float dir_in[3],
                             svo_o_cast_result *res, int maxDepth, int coneTrace, int coneDepth,
                             svo_o_stats *stats) {
