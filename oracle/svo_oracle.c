@@ -8,7 +8,7 @@
  *
  * Interpretation choices where GLSL leaves behaviour undefined (each is
  * mirrored by the CUDA validation build and listed in DESIGN.md):
- *   U1  out-of-range SSBO reads return 0 (robust buffer access);
+ *   U1  out-of-range SSBO reads and out-of-image beam-buffer loads return 0 (robust buffer / image access);
  *   U2  `castResult res` and `matcolor` start zeroed (uninitialised upstream);
  *   U3  `octstack` starts zeroed per invocation and persists across the casts
  *       of one pixel (it is a global in the shader);
@@ -518,7 +518,10 @@ typedef struct {
 static void shade_pixel(render_job_t *j, int x, int y) {
   const svo_o_frame *f = j->f;
   float beamDist = 0.0f;
-  if (f->useBeam && j->beam) beamDist = j->beam[(size_t)(y / 4) * (size_t)(j->width / 4) + (size_t)(x / 4)]; /* :656-658 */
+  /* :656-658.  The beam image is (W/4) x (H/4) texels (Main.java:82-83, integer division); imageLoad outside an image
+   * returns 0 (GL robust image access), which happens for the last rows/columns when W or H is not a multiple of 4 */
+  if (f->useBeam && j->beam && x / 4 < j->width / 4 && y / 4 < j->height / 4)
+    beamDist = j->beam[(size_t)(y / 4) * (size_t)(j->width / 4) + (size_t)(x / 4)];
   float px = ((float)x + 0.5f) / (float)j->width;                                   /* :662 */
   float py = ((float)y + 0.5f) / (float)j->height;
   float dir[3], nd[3];

@@ -447,7 +447,9 @@ SVO_DI bool pixel_begin(const FrameParams &f, const Planes &pl, int W, int H, in
   P.x = x;
   P.y = y;
   P.beamDist = 0.0f;
-  if (f.useBeam && pl.beam) P.beamDist = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));  // :656-658
+  // :656-658.  The beam image has (W/4) x (H/4) texels (Main.java:82-83); imageLoad outside an image returns 0
+  if (f.useBeam && pl.beam && (x >> 2) < (W >> 2) && (y >> 2) < (H >> 2))
+    P.beamDist = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));
   const float fx = fdiv(fadd((float)x, 0.5f), (float)W);  // :662
   const float fy = fdiv(fadd((float)y, 0.5f), (float)H);
   vec3 dir;  // :664
