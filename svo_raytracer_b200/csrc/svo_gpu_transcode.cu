@@ -128,17 +128,17 @@ cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, ui
   auto cleanup = [&]() {
     cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(counts); cudaFree(offsets); cudaFree(bounds); cudaFree(scan_tmp);
   };
-  auto ensure = [&](size_t n) -> cudaError_t {  // work lists and scan buffers for a level of n nodes (children <= 8n)
+  // work lists and scan buffers for levels of up to n nodes; the `live` entries of buf[keep] survive a regrow
+  auto ensure = [&](size_t n, int keep, size_t live) -> cudaError_t {
     if (n <= work_cap) return cudaSuccess;
     cudaError_t s = cudaStreamSynchronize(stream);
     if (s != cudaSuccess) return s;
     Work *old[2] = {buf[0], buf[1]};
-    const size_t old_cap = work_cap;
     work_cap = n + n / 2 + 1024;
     for (int k = 0; k < 2; k++) {
       Work *nb = nullptr;
       if ((s = cudaMalloc((void **)&nb, work_cap * sizeof(Work))) != cudaSuccess) return s;
-      if (old[k] && old_cap) cudaMemcpy(nb, old[k], old_cap * sizeof(Work), cudaMemcpyDeviceToDevice);
+      if (k == keep && old[k] && live) cudaMemcpy(nb, old[k], live * sizeof(Work), cudaMemcpyDeviceToDevice);
       cudaFree(old[k]);
       buf[k] = nb;
     }
@@ -153,7 +153,7 @@ cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, ui
   };
   if ((e = cudaMalloc((void **)&bounds, 25 * 6 * sizeof(uint32_t))) != cudaSuccess) { cleanup(); return e; }
   k_init_bounds<<<1, 256, 0, stream>>>(bounds, 25);
-  if ((e = ensure(1 << 16)) != cudaSuccess) { cleanup(); return e; }
+  if ((e = ensure(1 << 16, 0, 0)) != cudaSuccess) { cleanup(); return e; }
   const Work root = {0u, 0u, 0u, 0u};
   if ((e = cudaMemcpyAsync(buf[0], &root, sizeof root, cudaMemcpyHostToDevice, stream)) != cudaSuccess) { cleanup(); return e; }
   if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) { cleanup(); return e; }  // `root` is a stack variable
@@ -175,7 +175,7 @@ cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, ui
     if (level_base + n + total > cap) { *overflow = true; break; }
     if (total > work_cap) {
       // grow the NEXT list only (the current one is still needed): simplest is to regrow both, preserving contents
-      if ((e = ensure(total)) != cudaSuccess) break;
+      if ((e = ensure(total, cur, n)) != cudaSuccess) break;
       // counts/offsets were reallocated: recompute them for this level
       k_transcode_level<false><<<grid, 256, 0, stream>>>(d_raw, nbytes, buf[cur], n, depth, counts, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
       sb = scan_bytes;
