@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
       if (wants) {
         Trav<FAST, false, BOX> T;
         T.setup(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, nullptr);
-        hs = T.export_hit(T.outside_box() ? TRAV_MISS : T.run(sc, stk, nullptr));
+        hs = T.export_hit((T.outside_box() || T.nan_ray(nullptr)) ? TRAV_MISS : T.run(sc, stk, nullptr));
       }
     } else {
       // ---- counting sort of the CTA's rays by octant (key 8 = no ray) ----
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
         Trav<FAST, false, BOX> T;
         T.setup(sc, mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]), f.maxDepth,
                 s_ray[6][tid] != 0.0f, f.coneDepth, nullptr);
-        const HitState r = T.export_hit(T.outside_box() ? TRAV_MISS : T.run(sc, stk, nullptr));
+        const HitState r = T.export_hit((T.outside_box() || T.nan_ray(nullptr)) ? TRAV_MISS : T.run(sc, stk, nullptr));
         const unsigned o = s_owner[tid];
         s_hit[0][o] = r.pidx; s_hit[1][o] = r.meta; s_hit[2][o] = r.ipx; s_hit[3][o] = r.ipy; s_hit[4][o] = r.ipz;
         s_hit[5][o] = __float_as_uint(r.t_min); s_hit[6][o] = r.iter;

@@ -261,12 +261,26 @@ struct Trav {
   }
   // true if the cast can end now: nothing can be hit any more
   __device__ __forceinline__ bool outside_box() const { return BOX && t_min > tb_out; }
+  // All three corner times NaN (NaN direction from a zero or 555 normal, NaN origin, or a zero direction): that does
+  // not depend on pos, so it holds for the whole cast; no child ever passes t_min <= t_max, ADVANCE never steps,
+  // and the reference spins to the iteration cap (:264).  Callers of run() test it once instead of every iteration.
+  __device__ __forceinline__ bool nan_ray(RayStats *rs) {
+    const float a = M::msub(px, cx, bx), b = M::msub(py, cy, by), c = M::msub(pz, cz, bz);
+    if (!((a != a) && (b != b) && (c != c))) return false;
+    if (STATS) {  // the reference fetches the same child record 1500 times
+      const uint32_t code = (pd.y >> (2u * (idx ^ oct))) & 3u;
+      rs->iters += (uint32_t)kMaxIterations;
+      rs->record_bytes += (uint32_t)kMaxIterations * (code == 1u ? 3u : (code == 3u ? 1u : 7u));
+    }
+    iter = (uint32_t)kMaxIterations + 1u;
+    return true;
+  }
 
   // The body of one loop iteration (:262-369), shared by run() and step().  `EXIT(status)` leaves the loop,
   // `NEXT` starts the next iteration.  The iteration cap (:264-266) is enforced where it is cheap -- on the
   // POP path, plus once after the loop (cap_fixup) -- instead of on every iteration: a cast that ends with
   // iter > 1500 is exactly a cast the reference capped, and a cast cannot run long without a POP.
-#define SVO_TRAV_BODY(EXIT, NEXT)                                                                                    \
+#define SVO_TRAV_BODY(EXIT, NEXT, NANCHECK)                                                                                  \
   iter++;                                                                                                            \
   if (STATS && iter <= (uint32_t)kMaxIterations) rs->iters += 1u;                                                    \
   const float tx_corner = M::msub(px, cx, bx); /* :280-283 */                                                        \
@@ -309,9 +323,9 @@ struct Trav {
   }                                                                                                                  \
   /* ADVANCE :337-344 */                                                                                             \
   const bool sx = tx_corner <= tc_max, sy = ty_corner <= tc_max, sz = tz_corner <= tc_max;                           \
-  if (!(sx || sy || sz)) {                                                                                           \
+  if (NANCHECK && !(sx || sy || sz)) {                                                                               \
     /* all three corners are NaN (NaN direction from a zero or 555 normal): nothing changes any more and the   */    \
-    /* reference spins to the cap (:264)                                                                        */    \
+    /* reference spins to the cap (:264).  run() callers test this once, before the loop (nan_ray()).           */    \
     if (STATS && iter <= (uint32_t)kMaxIterations) {                                                                 \
       const uint32_t code = (pd.y >> (2u * cs)) & 3u, left = (uint32_t)kMaxIterations - iter;                        \
       rs->iters += left;                                                                                             \
@@ -331,11 +345,11 @@ struct Trav {
     /* The iteration cap (:264-266) is tested here only: every run of ADVANCEs ends in a POP after at most 3   */    \
     /* steps, so the test is at most ~26 iterations late, and cap_fixup() turns any cast that ends with        */    \
     /* iter > 1500 into exactly what the reference returns at iteration 1501.                                   */    \
-    if (iter >= (uint32_t)kMaxIterations) {                                                                          \
-      iter = (uint32_t)kMaxIterations + 1u;                                                                          \
+    /* ... and so is "the ray has left the content box for good" (BOX).                                         */    \
+    if (iter >= (uint32_t)kMaxIterations || (BOX && t_min > tb_out)) {                                               \
+      if (iter >= (uint32_t)kMaxIterations) iter = (uint32_t)kMaxIterations + 1u;                                    \
       EXIT(TRAV_MISS);                                                                                               \
     }                                                                                                                \
-    if (BOX && t_min > tb_out) { EXIT(TRAV_MISS); } /* the ray has left the content box for good */                  \
     uint32_t differing_bits = 0;                                                                                     \
     if (sx) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));                           \
     if (sy) differing_bits |= __float_as_uint(py) ^ __float_as_uint(fadd(py, scale_exp2));                           \
@@ -371,7 +385,7 @@ struct Trav {
   __device__ __forceinline__ int run(const SceneView &sc, uint2 *stk, RayStats *rs) {
 #define SVO_EXIT(s) { if ((s) == TRAV_HIT) goto hit; else goto miss; }
     for (;;) {
-      SVO_TRAV_BODY(SVO_EXIT, continue)
+      SVO_TRAV_BODY(SVO_EXIT, continue, false)
     }
 #undef SVO_EXIT
   hit:
@@ -383,7 +397,7 @@ struct Trav {
   // one iteration; returns TRAV_CONTINUE until the cast is over
   __device__ __forceinline__ int step(const SceneView &sc, uint2 *stk, RayStats *rs) {
 #define SVO_EXIT(s) return cap_fixup(s)
-    SVO_TRAV_BODY(SVO_EXIT, return TRAV_CONTINUE)
+    SVO_TRAV_BODY(SVO_EXIT, return TRAV_CONTINUE, true)
 #undef SVO_EXIT
     return TRAV_CONTINUE;
   }
@@ -412,7 +426,7 @@ __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, cons
   uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
   Trav<FAST, STATS, BOX, TOP> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
-  if (T.outside_box()) return T.finish(sc, TRAV_MISS, res, loops, attrs);  // the ray never reaches the content box
+  if (T.outside_box() || T.nan_ray(rs)) return T.finish(sc, TRAV_MISS, res, loops, attrs);  // no iteration can change anything
   return T.finish(sc, T.run(sc, stk, rs), res, loops, attrs);
 }
 
