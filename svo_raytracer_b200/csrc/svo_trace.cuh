@@ -23,10 +23,17 @@
 //    pixel_store): the tile kernel runs them back to back, the persistent
 //    kernel interleaves pixels so that a lane whose ray has finished is
 //    refilled instead of idling until the slowest ray of its warp is done.
-//  * The cube position is kept as the raw IEEE bit pattern of the reference's
-//    `pos` floats: inside [1,2) adding/subtracting scale_exp2 IS setting /
-//    subtracting bit `scale` of the mantissa, so PUSH/ADVANCE/POP are integer
-//    ops and the POP test is "did the subtraction borrow above bit `scale`".
+//  * Work that the reference repeats every iteration but that only matters
+//    at certain points runs at those points: the sticky LOD-cut test where
+//    t_min changes (ADVANCE), the 1500-iteration cap on the POP path (plus one
+//    fix-up after the loop), the NaN-ray test once before the loop; position
+//    updates are predicated FADDs (FMA pipe: the kernel is ALU-pipe bound),
+//    the stack holds 8-byte (parent, t_max) entries.
+//  * Casts that cannot hit anything end early: a ray outside the bounding box
+//    of everything hittable (computed at upload) is a miss without walking the
+//    reference's 256^3 empty cells (only where the iteration count of a miss
+//    is unobservable, see Trav), and casts whose hit record trace() never
+//    reads skip its decoding and the dead shading (cast_needs_attrs).
 //  * The control flow (iteration count, PUSH/ADVANCE/POP order, the 1500
 //    iteration cap, the sticky cone LOD cut, every quirk listed in DESIGN.md)
 //    is reproduced exactly; Ops<false> rounds every operation separately
