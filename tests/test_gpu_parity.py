@@ -539,3 +539,71 @@ def test_random_worlds_random_cameras(svo, oracle, seed):
             d = c.read_depth()
             same = (d.view(np.uint32) == want["depth"].view(np.uint32)) | (np.isnan(d) & np.isnan(want["depth"]))
             assert same.all(), (seed, trial, kw)
+
+
+@pytest.fixture(scope="module")
+def world2048(svo):
+    """BASELINE configs[1] world: 2048^3 terrain (built by the product's generator; ~1 s)."""
+    hm, mm = svo.terrain_inputs(2048)
+    return svo.build_terrain(hm, mm, 2048, 1024)
+
+
+def test_full_size_properties(svo, oracle, world2048):
+    """BASELINE configs[1] at full size (2048^3, 1920x1080) through size-independent properties: hit ids are offsets
+    of non-empty records of the stream, all kernel variants and the band partition produce the same frame, the
+    content-bounds shortcut changes nothing, rendering is deterministic, and a random sample of pixels agrees with
+    the oracle bit for bit."""
+    W, H, depth = 1920, 1080, 11
+    nodes = world2048
+    rng = np.random.default_rng(5)
+    with svo.SvoContext(W, H) as c:
+        c.upload(nodes)
+        for cam in ("B", "C"):
+            f3 = svo.camera_frame(cam, frame_number=1, render_mode=3, max_depth=depth)
+            f0 = svo.camera_frame(cam, frame_number=2, render_mode=0, max_depth=depth)
+            c.set_option(svo._lib.OPT_KERNEL, 0)
+            c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+            c.render(f3)
+            ids, it, t, dep = c.read_hit_id(), c.read_iter(), c.read_primary_t(), c.read_depth()
+            hit = ids != svo.NO_HIT
+            assert 0.2 < hit.mean() <= 1.0
+            assert (ids[hit] < nodes.size).all() and (nodes[ids[hit]] != 0).all()   # ids name non-empty records
+            assert np.isfinite(t[hit]).all() and (t[hit] >= 0).all() and (t[hit] < 4).all()
+            assert np.array_equal(dep[hit].view(np.uint32), t[hit].view(np.uint32)) and (dep[~hit] == 0).all()  # mode 3: depth = res.t
+            assert it.min() >= 1 and it.max() <= 1501
+            # a random sample of primary rays against the oracle (hit id, iteration count, t)
+            ys, xs = rng.integers(0, H, 3000), rng.integers(0, W, 3000)
+            pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+            fx, fy = ((xs + 0.5) / W).astype(np.float32), ((ys + 0.5) / H).astype(np.float32)
+            mix = lambda a, b, w: (np.float32(a) * (np.float32(1) - w) + np.float32(b) * w).astype(np.float32)
+            d = np.stack([mix(mix(l1[k], l2[k], fy), mix(r1[k], r2[k], fy), fx) for k in range(3)], 1).astype(np.float32)
+            ln = np.sqrt(((d[:, 0] * d[:, 0]) + (d[:, 1] * d[:, 1])) + (d[:, 2] * d[:, 2])).astype(np.float32)
+            rays = np.zeros(3000, dtype=svo.RAY_DTYPE)
+            rays["o"] = np.asarray(pos, np.float32)
+            rays["d"] = (d / ln[:, None]).astype(np.float32)
+            want, _ = oracle.cast_rays(nodes, rays, max_depth=depth, nthreads=8)
+            assert np.array_equal(ids[ys, xs], want["id"]) and np.array_equal(it[ys, xs], want["iter"])
+            assert np.array_equal(t[ys, xs].view(np.uint32), want["t"].view(np.uint32))
+            # the frame every variant / partition / option must reproduce
+            c.set_option(svo._lib.OPT_AUX_PLANES, 0)
+            c.render(f0)
+            ref_rgba, ref_depth = c.read_color_rgba8(), c.read_depth()
+            c.render(f0)
+            assert np.array_equal(c.read_color_rgba8(), ref_rgba)  # deterministic
+            for kernel in (2, 6, 1):
+                c.set_option(svo._lib.OPT_KERNEL, kernel)
+                c.render(f0)
+                assert np.array_equal(c.read_color_rgba8(), ref_rgba), (cam, kernel)
+                assert np.array_equal(c.read_depth().view(np.uint32), ref_depth.view(np.uint32)), (cam, kernel)
+            c.set_option(svo._lib.OPT_KERNEL, 0)
+            c.set_option(svo._lib.OPT_CONTENT_BOUNDS, 0)
+            c.render(f0)
+            assert np.array_equal(c.read_color_rgba8(), ref_rgba) and np.array_equal(c.read_depth().view(np.uint32), ref_depth.view(np.uint32))
+            c.set_option(svo._lib.OPT_CONTENT_BOUNDS, 1)
+            c.render(svo.camera_frame("A", frame_number=1, render_mode=3, max_depth=depth))  # scribble
+            for part in range(8):
+                c.render_interleaved(f0, part, 8)
+            assert np.array_equal(c.read_color_rgba8(), ref_rgba) and np.array_equal(c.read_depth().view(np.uint32), ref_depth.view(np.uint32))
+            # counters of the instrumented kernel: casts = pixels + primary hits (a bounce is cast iff the primary hit)
+            st = c.render_stats(f0)
+            assert st["casts"] == W * H + int(hit.sum()) and st["iters"] >= st["casts"]
