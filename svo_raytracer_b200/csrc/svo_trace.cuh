@@ -254,15 +254,19 @@ struct Trav {
     if (BOX) {
       // slab test in the mirrored coordinates of the traversal (the ray moves towards smaller coordinates on every
       // axis): it enters the box through the high faces and leaves through the low ones.  The box is padded by
-      // 2^-9 and rays with a direction component below 2^-8 are exempt (their t arithmetic is too ill-conditioned
-      // to bound how far the reference's cell walk strays from the true ray), see DESIGN.md.
+      // 2^-9; rays with a direction component below 2^-8 or an origin coordinate beyond 8 are exempt (their t
+      // arithmetic is too ill-conditioned to bound how far the reference's cell walk strays from the true ray: with
+      // |coef| <= 256 and |origin| <= 8 every t is exact to ~2.4e-4, an order of magnitude inside the padding).
       const float hx = (oct & 1u) ? 3.0f - sc.box_lo[0] : sc.box_hi[0], lx = (oct & 1u) ? 3.0f - sc.box_hi[0] : sc.box_lo[0];
       const float hy = (oct & 2u) ? 3.0f - sc.box_lo[1] : sc.box_hi[1], ly = (oct & 2u) ? 3.0f - sc.box_hi[1] : sc.box_lo[1];
       const float hz = (oct & 4u) ? 3.0f - sc.box_lo[2] : sc.box_hi[2], lz = (oct & 4u) ? 3.0f - sc.box_hi[2] : sc.box_lo[2];
       const float tb_in = fmaxf(fmaxf(hx * cx - bx, hy * cy - by), fmaxf(hz * cz - bz, 0.0f));
       tb_out = fminf(fminf(lx * cx - bx, ly * cy - by), lz * cz - bz);
       const float dmin = fminf(fminf(fabsf(d.x), fabsf(d.y)), fabsf(d.z));
-      if (!(dmin >= 0.00390625f)) tb_out = __uint_as_float(0x7f800000u);  // exempt (also NaN directions)
+      const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+      // exempt: ill-conditioned directions, far-away origins (|t_bias| grows with |o| and so does the rounding
+      // error of every t), NaNs
+      if (!(dmin >= 0.00390625f) || !(omax <= 8.0f)) tb_out = __uint_as_float(0x7f800000u);
       else if (!(tb_in <= tb_out)) tb_out = -1.0f;                         // never inside the box: ends at the first POP/ADVANCE test
     }
   }

@@ -350,7 +350,11 @@ def test_content_bounds_inside_camera_and_shallow_depths(svo, oracle, terrain128
     W, H = 160, 96
     cams = [((1.5, 1.05, 1.5), (-1, 0.2, -1), (-1, 1.5, -1), (1, 0.2, -1), (1, 1.5, -1)),
             ((1.2, 1.12, 1.8), (-1.6, -0.9, -1), (-1.6, 0.9, -1), (1.6, -0.9, -1), (1.6, 0.9, -1)),
-            ((1.5, 1.5, 2.0), (-1.6, -0.9, -1), (-1.6, 0.9, -1), (1.6, -0.9, -1), (1.6, 0.9, -1))]
+            ((1.5, 1.5, 2.0), (-1.6, -0.9, -1), (-1.6, 0.9, -1), (1.6, -0.9, -1), (1.6, 0.9, -1)),
+            # far-away origins: t arithmetic loses precision with |origin| (exempt from the shortcut beyond 8)
+            ((1.5, 30.0, 1.5), (-0.02, -1, -0.015), (-0.02, -1, 0.015), (0.02, -1, -0.015), (0.02, -1, 0.015)),
+            ((7.9, 7.5, 7.7), (-1.05, -1, -0.95), (-1.05, -0.9, -1.0), (-0.95, -1, -1.05), (-0.9, -0.95, -1.0)),
+            ((3001.5, 4001.5, 5001.5), (-3.0004, -4.0, -5.0004), (-3.0004, -3.9996, -5.0), (-2.9996, -4.0, -5.0), (-3.0, -4.0004, -4.9996))]
     with svo.SvoContext(W, H) as c:
         c.upload(terrain128)
         for cam in cams:
