@@ -50,3 +50,47 @@ def test_empty_and_degenerate_streams(svo):
     # a root whose child pointer points at itself (cp = 0 reads the root's own bytes as children)
     out, _ = probe(svo, np.array([1, 0, 0, 0, 0, 0, 0], np.uint8))
     assert out[0] >= 1
+
+
+def _python_transcode(nodes):
+    """Independent restatement of the transcode in Python (breadth-first, struct-based decoding)."""
+    import struct
+    b = bytes(nodes) + b"\0" * 16
+    n = len(nodes)
+    rd = lambda p: b[p] if p < n else 0
+    be32 = lambda p: (rd(p) << 24) | (rd(p + 1) << 16) | (rd(p + 2) << 8) | rd(p + 3)
+    be16 = lambda p: (rd(p) << 8) | rd(p + 1)
+    cur = [(0, be32(1), be16(5))]
+    out, base = [], 0
+    for depth in range(23):
+        if not cur:
+            break
+        nxt = []
+        for off, cp, codes in cur:
+            ref = (off + cp) & 0xFFFFFFFF
+            p, nz, hd, first = ref, 0, 0, base + len(cur) + len(nxt)
+            for c in range(8):
+                code = (codes >> (2 * c)) & 3
+                if rd(p):
+                    nz |= 1 << c
+                    ccp = be32(p + 1) if code == 0 else 0
+                    if ccp and depth < 22:
+                        hd |= 1 << c
+                        nxt.append((p, ccp, be16(p + 5)))
+                p = (p + (3 if code == 1 else 1 if code == 3 else 7)) & 0xFFFFFFFF
+            out.append((first, codes | (nz << 16) | (hd << 24), ref))
+        base += len(cur)
+        cur = nxt
+    return np.array(out, dtype=np.uint64)
+
+
+def test_transcode_against_python_restatement(svo, oracle):
+    rng = np.random.default_rng(21)
+    for n in (8, 16, 32):
+        vox = (rng.random((n, n, n)) < 0.25).astype(np.uint8) * rng.integers(1, 4, (n, n, n)).astype(np.uint8)
+        vox[: n // 2, : n // 4] = 2
+        nodes, _ = oracle.build_dense(vox)
+        want = _python_transcode(nodes)
+        out, desc = probe(svo, nodes, 3, want_desc=len(want))
+        assert out[0] == len(want)
+        assert np.array_equal(desc.astype(np.uint64), want)
