@@ -499,6 +499,13 @@ def test_gpu_transcode_equals_host_transcode(svo, oracle, terrain128, terrain512
             assert c.scene_probe() == want
         except svo.SvoError as e:  # a scrambled stream may legitimately be refused, but then by both paths
             assert e.code == svo._lib.ERR_FORMAT
+        # appended bytes (Octree.subdivideNode appends new nodes at memOffset): the range may end beyond the old length
+        grown = np.concatenate([terrain128, np.zeros(5000, np.uint8)])
+        grown[-7:] = terrain128[:7]
+        c.upload(terrain128)
+        c.upload_range(grown, terrain128.size, grown.size)
+        want, _ = probe(svo, grown, 2)
+        assert c.scene_probe() == want and c.scene_info()["stream_bytes"] == grown.size
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
@@ -545,20 +552,20 @@ def test_random_worlds_random_cameras(svo, oracle, seed):
             assert same.all(), (seed, trial, kw)
 
 
-@pytest.fixture(scope="module")
-def world2048(svo):
-    """BASELINE configs[1] world: 2048^3 terrain (built by the product's generator; ~1 s)."""
-    hm, mm = svo.terrain_inputs(2048)
-    return svo.build_terrain(hm, mm, 2048, 1024)
+import os as _os
+
+FULL_SIZES = [2048] + ([8192] if _os.environ.get("SVO_TEST_8192") == "1" else [])  # 8192^3 (the bench world): opt-in, ~1 min
 
 
-def test_full_size_properties(svo, oracle, world2048):
-    """BASELINE configs[1] at full size (2048^3, 1920x1080) through size-independent properties: hit ids are offsets
+@pytest.mark.parametrize("size", FULL_SIZES)
+def test_full_size_properties(svo, oracle, size):
+    """BASELINE configs[1] (2048^3) -- and with SVO_TEST_8192=1 the bench world (8192^3) -- at 1920x1080 through size-independent properties: hit ids are offsets
     of non-empty records of the stream, all kernel variants and the band partition produce the same frame, the
     content-bounds shortcut changes nothing, rendering is deterministic, and a random sample of pixels agrees with
     the oracle bit for bit."""
-    W, H, depth = 1920, 1080, 11
-    nodes = world2048
+    W, H, depth = 1920, 1080, min(13, int(np.log2(size)))
+    hm, mm = svo.terrain_inputs(size)
+    nodes = svo.build_terrain(hm, mm, size, 1024)  # the product's generator (byte-equal to the oracle's, test_builder.py)
     rng = np.random.default_rng(5)
     with svo.SvoContext(W, H) as c:
         c.upload(nodes)
