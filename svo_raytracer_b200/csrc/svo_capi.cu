@@ -240,6 +240,7 @@ int retranscode(svo_ctx *c) {
   uint32_t nlevels = 0;
   CellBox leaf_box, depth_box[24];
   bool done = false;
+  c->have_scene = false;  // until the descriptor arrays match d_raw again (a refused stream leaves the context without a scene)
   // the kernels may still be reading the previous arrays
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->opt_gpu_transcode) {
@@ -439,7 +440,10 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
   switch (option) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
-    case SVO_OPT_KERNEL: c->opt_kernel = (int)value; return SVO_OK;
+    case SVO_OPT_KERNEL:
+      if (value != 0 && value != 1 && value != 2 && value != 4 && value != 5 && value != 6) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      c->opt_kernel = (int)value;
+      return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
     case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
@@ -479,6 +483,7 @@ int svo_upload(svo_ctx *c, const uint8_t *nodes, uint64_t nbytes) {
   if (!nodes && nbytes) return fail(c, SVO_ERR_INVALID, "nodes is NULL");
   if (nbytes >= (1ull << 32)) return fail(c, SVO_ERR_INVALID, "node stream must be < 4 GiB");
   SVO_CUDA(c, cudaSetDevice(c->device));
+  c->have_scene = false;
   if (nbytes + 16 > c->raw_cap) {
     SVO_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->d_raw) cudaFree(c->d_raw);
@@ -778,13 +783,7 @@ int svo_cast_device(svo_ctx *c, const void *d_rays, uint64_t n, void *d_out, int
   if (c->opt_sort && n >= 65536 && n < (1ull << 31)) {  // bin by octant + origin Morton code; results go back to the caller's order
     if (n > c->sort_cap) {
       SVO_CUDA(c, cudaStreamSynchronize(c->stream));
-      for (int p = 0; p < 2; p++)
-    if (c->back[p]) cudaFree(c->back[p]);
-  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-  if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
-  for (int p = 0; p < 2; p++)
-    if (c->ev_copied[p]) cudaEventDestroy(c->ev_copied[p]);
-  if (c->d_sort) cudaFree(c->d_sort);
+      if (c->d_sort) cudaFree(c->d_sort);
       if (c->d_sort_temp) cudaFree(c->d_sort_temp);
       c->d_sort = nullptr;
       c->d_sort_temp = nullptr;

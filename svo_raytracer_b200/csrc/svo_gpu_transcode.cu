@@ -162,7 +162,8 @@ cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, ui
   uint32_t n = 1;
   int cur = 0;
   for (int depth = 0; depth <= 22 && n > 0; depth++) {
-    if (level_base + n > cap) { *overflow = true; break; }
+    // (8 children per node: from 2^29 nodes on, the 32-bit prefix sum below could wrap -- leave such a level to the host pass)
+    if (level_base + n > cap || n >= (1u << 29)) { *overflow = true; break; }
     const unsigned grid = (n + 255) / 256;
     k_transcode_level<false><<<grid, 256, 0, stream>>>(d_raw, nbytes, buf[cur], n, depth, counts, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
     size_t sb = scan_bytes;

@@ -393,7 +393,8 @@ struct Trav {
   }
 
   // the whole loop (:262-369); returns TRAV_HIT or TRAV_MISS
-  __device__ __forceinline__ int run(const SceneView &sc, uint2 *stk, RayStats *rs) {
+  template <class Stk>
+  __device__ __forceinline__ int run(const SceneView &sc, Stk stk, RayStats *rs) {
 #define SVO_EXIT(s) { if ((s) == TRAV_HIT) goto hit; else goto miss; }
     for (;;) {
       SVO_TRAV_BODY(SVO_EXIT, continue, false)
@@ -406,7 +407,8 @@ struct Trav {
   }
 
   // one iteration; returns TRAV_CONTINUE until the cast is over
-  __device__ __forceinline__ int step(const SceneView &sc, uint2 *stk, RayStats *rs) {
+  template <class Stk>
+  __device__ __forceinline__ int step(const SceneView &sc, Stk stk, RayStats *rs) {
 #define SVO_EXIT(s) return cap_fixup(s)
     SVO_TRAV_BODY(SVO_EXIT, return TRAV_CONTINUE, true)
 #undef SVO_EXIT

@@ -223,6 +223,19 @@ def test_errors_are_codes_not_crashes(svo, terrain128):
         assert e.value.code == svo._lib.ERR_INVALID
         with pytest.raises(svo.SvoError):
             c.render(svo.camera_frame("A"), 10, 200)
+        # a stream that is not a tree is refused, and leaves the context without a scene rather than with a stale one
+        from test_transcode import cyclic_stream
+        with pytest.raises(svo.SvoError) as e:
+            c.upload(cyclic_stream())
+        assert e.value.code == svo._lib.ERR_FORMAT
+        with pytest.raises(svo.SvoError) as e:
+            c.render(svo.camera_frame("A"))
+        assert e.value.code == svo._lib.ERR_NO_SCENE
+        with pytest.raises(svo.SvoError) as e:
+            c.set_option(svo._lib.OPT_KERNEL, 3)
+        assert e.value.code == svo._lib.ERR_INVALID
+        c.upload(terrain128)
+        c.render(svo.camera_frame("A"))
         c.upload(np.zeros(0, np.uint8))  # an empty stream is legal: everything misses
         c.set_option(svo._lib.OPT_AUX_PLANES, 1)
         c.render(svo.camera_frame("A", render_mode=3))
@@ -465,6 +478,23 @@ def test_pipelined_readback(svo, oracle, terrain128):
                                         W, H, nthreads=4, planes=("rgba8", "depth"))
                 assert np.array_equal(sets[k][0].numpy(), want["rgba8"]), (base, k)
                 assert np.array_equal(sets[k][1].numpy().view(np.uint32), want["depth"].view(np.uint32)), (base, k)
+        # a large ray stream in between (its sort scratch is allocated on first use) leaves the frame pipeline intact
+        rng = np.random.default_rng(3)
+        rays = np.zeros(70000, dtype=svo.RAY_DTYPE)
+        rays["o"] = rng.uniform(1.0, 2.0, (rays.size, 3)).astype(np.float32)
+        rays["d"] = rng.normal(size=(rays.size, 3)).astype(np.float32)
+        got = c.cast(rays, 7)
+        want_hits, _ = oracle.cast_rays(terrain128, rays, 7, nthreads=4)
+        assert np.array_equal(got["id"], want_hits["id"]) and np.array_equal(got["iter"], want_hits["iter"])
+        for k in range(2):
+            c.render(svo.camera_frame("B", frame_number=20 + k, render_mode=0, max_depth=7))
+            c.read_planes_async(sets[k][0].data_ptr(), sets[k][1].data_ptr())
+            c.swap_buffers()
+        c.read_wait()
+        for k in range(2):
+            want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=20 + k, render_mode=0, max_depth=7),
+                                    W, H, nthreads=4, planes=("rgba8",))
+            assert np.array_equal(sets[k][0].numpy(), want["rgba8"]), k
         # the blocking readers follow the current set
         c.render(svo.camera_frame("B", frame_number=9, render_mode=0, max_depth=7))
         want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=9, render_mode=0, max_depth=7), W, H,

@@ -52,6 +52,23 @@ def test_empty_and_degenerate_streams(svo):
     assert out[0] >= 1
 
 
+def cyclic_stream():
+    """Eight interior children whose child pointers all lead back to their own sibling block: not a tree."""
+    import struct
+    b = bytes([1]) + struct.pack(">i", 7) + struct.pack(">H", 0)
+    for i in range(8):
+        b += bytes([1]) + struct.pack(">i", -7 * i) + struct.pack(">H", 0)
+    return np.frombuffer(b, np.uint8).copy()
+
+
+def test_cyclic_stream_is_refused(svo):
+    import ctypes as C
+    nodes = cyclic_stream()
+    out = (C.c_uint64 * 8)()
+    rc = svo._lib.lib().svo_transcode_probe(nodes.ctypes.data_as(C.c_void_p), nodes.size, 2, out, None, 0)
+    assert rc == svo._lib.ERR_FORMAT
+
+
 def _python_transcode(nodes):
     """Independent restatement of the transcode in Python (breadth-first, struct-based decoding)."""
     import struct

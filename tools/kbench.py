@@ -12,8 +12,13 @@ variants = (sys.argv[2] if len(sys.argv) > 2 else "0,2").split(",")
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 W, H = 1920, 1080
 t0 = time.time()
-hm, mm = svo.terrain_inputs(size)
-nodes = svo.build_terrain(hm, mm, size, min(size, 1024))
+cache = "/tmp/kbench_world_%d.npy" % size  # several libraries (SVO_B200_LIB=...) are compared on one box: build once
+if os.path.exists(cache):
+    nodes = np.load(cache)
+else:
+    hm, mm = svo.terrain_inputs(size)
+    nodes = svo.build_terrain(hm, mm, size, min(size, 1024))
+    np.save(cache, nodes)
 print("world %d^3: %.1f MB in %.1fs" % (size, nodes.size / 1e6, time.time() - t0), flush=True)
 depth = min(13, int(np.log2(size)))
 ctx = svo.SvoContext(W, H)
