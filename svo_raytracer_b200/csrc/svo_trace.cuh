@@ -212,7 +212,9 @@ struct Trav {
   int scale;
   int stop_scale;           // MAX_SCALE - maxDepth
   int cone_stop;            // what stop_scale becomes once t_min > 0.05 (== stop_scale when !coneTrace)
-  uint32_t idx, oct, pidx, iter;
+  uint32_t idx, oct, pidx;
+  float iter;               // loop iterations so far, counted in binary32 (exact: the cap is 1500) so that the
+                            // increment runs on the FMA pipe -- the loop is bound by the ALU pipe
   uint2 pd;
 
   __device__ __forceinline__ void setup(const SceneView &sc, const vec3 o, vec3 d, int maxDepth, bool coneTrace,
@@ -244,7 +246,7 @@ struct Trav {
     if (M::msub(1.5f, cz, bz) > t_min) { idx ^= 4u; pz = 1.5f; }
     pidx = 0;               // parent = root (:222)
     pd = fetch(sc, 0u);
-    iter = 0;
+    iter = 0.0f;
     stop_scale = kMaxScale - maxDepth;
     cone_stop = coneTrace ? kMaxScale - coneDepth : stop_scale;
     // the sticky LOD cut (:275-277) is tested at the top of every iteration upstream; t_min only changes here
@@ -283,7 +285,7 @@ struct Trav {
       rs->iters += (uint32_t)kMaxIterations;
       rs->record_bytes += (uint32_t)kMaxIterations * (code == 1u ? 3u : (code == 3u ? 1u : 7u));
     }
-    iter = (uint32_t)kMaxIterations + 1u;
+    iter = (float)(kMaxIterations + 1);
     return true;
   }
 
@@ -292,30 +294,30 @@ struct Trav {
   // POP path, plus once after the loop (cap_fixup) -- instead of on every iteration: a cast that ends with
   // iter > 1500 is exactly a cast the reference capped, and a cast cannot run long without a POP.
 #define SVO_TRAV_BODY(EXIT, NEXT, NANCHECK)                                                                                  \
-  iter++;                                                                                                            \
-  if (STATS && iter <= (uint32_t)kMaxIterations) rs->iters += 1u;                                                    \
+  iter = fadd(iter, 1.0f);                                                                                           \
+  if (STATS && iter <= (float)kMaxIterations) rs->iters += 1u;                                                       \
   const float tx_corner = M::msub(px, cx, bx); /* :280-283 */                                                        \
   const float ty_corner = M::msub(py, cy, by);                                                                       \
   const float tz_corner = M::msub(pz, cz, bz);                                                                       \
   const float tc_max = fminf(fminf(tx_corner, ty_corner), tz_corner);                                                \
   const uint32_t cs = idx ^ oct; /* child_shift :286 */                                                              \
-  if (STATS && iter <= (uint32_t)kMaxIterations) { /* size of the child record fetched here (extractChild :294) */  \
+  if (STATS && iter <= (float)kMaxIterations) { /* size of the child record fetched here (extractChild :294) */     \
     const uint32_t code = (pd.y >> (2u * cs)) & 3u;                                                                  \
     rs->record_bytes += code == 1u ? 3u : (code == 3u ? 1u : 7u);                                                    \
   }                                                                                                                  \
-  const uint32_t bit16 = 0x10000u << cs;                                                                             \
+  const uint32_t m = pd.y >> cs;                                                                                     \
   /* child.value != 0 (:295) is bit 16+child of the parent's descriptor */                                           \
-  if ((pd.y & bit16) != 0u && t_min <= t_max) {                                                                      \
+  if ((m & 0x10000u) != 0u && t_min <= t_max) {                                                                      \
     if (scale == stop_scale) { EXIT(TRAV_HIT); } /* MAX_SCALE - scale == maxDepth (:300-302) */                      \
     const float tv_max = fminf(t_max, tc_max);   /* :304 */                                                          \
     if (t_min <= tv_max) {                       /* :310 */                                                          \
-      const uint32_t bit24 = bit16 << 8;                                                                             \
-      if ((pd.y & bit24) == 0u) { EXIT(TRAV_HIT); } /* child.cp == 0 (:311-313) */                                   \
+      if ((m & 0x01000000u) == 0u) { EXIT(TRAV_HIT); } /* child.cp == 0 (:311-313) */                                \
       if (tc_max < h) { /* PUSH :316-319 */                                                                          \
         stk[scale] = make_uint2(pidx, __float_as_uint(t_max));                                                       \
       }                                                                                                              \
       h = tc_max;                                                                                                    \
-      pidx = pd.x + __popc(pd.y & (bit24 - 0x01000000u)); /* descriptors of the interior siblings below */           \
+      /* descriptors of the interior siblings below: bits [24, 24+cs) -- the funnel shift leaves exactly those */    \
+      pidx = pd.x + __popc(__funnelshift_r(0u, pd.y >> 24, cs));                                                     \
       pd = fetch(sc, pidx);                                /* parent = child (:322) */                               \
       const float half = M::mul(scale_exp2, 0.5f);                                                                   \
       const float tx_center = M::madd(half, cx, tx_corner); /* :306-308 */                                           \
@@ -337,12 +339,12 @@ struct Trav {
   if (NANCHECK && !(sx || sy || sz)) {                                                                               \
     /* all three corners are NaN (NaN direction from a zero or 555 normal): nothing changes any more and the   */    \
     /* reference spins to the cap (:264).  run() callers test this once, before the loop (nan_ray()).           */    \
-    if (STATS && iter <= (uint32_t)kMaxIterations) {                                                                 \
-      const uint32_t code = (pd.y >> (2u * cs)) & 3u, left = (uint32_t)kMaxIterations - iter;                        \
+    if (STATS && iter <= (float)kMaxIterations) {                                                                    \
+      const uint32_t code = (pd.y >> (2u * cs)) & 3u, left = (uint32_t)kMaxIterations - (uint32_t)iter;              \
       rs->iters += left;                                                                                             \
       rs->record_bytes += left * (code == 1u ? 3u : (code == 3u ? 1u : 7u));                                         \
     }                                                                                                                \
-    iter = (uint32_t)kMaxIterations + 1u;                                                                            \
+    iter = (float)(kMaxIterations + 1);                                                                              \
     EXIT(TRAV_MISS);                                                                                                 \
   }                                                                                                                  \
   px = sx ? fsub(px, scale_exp2) : px;                                                                               \
@@ -355,11 +357,11 @@ struct Trav {
   if ((idx & step_mask) != 0u) { /* POP :347-368 */                                                                  \
     /* The iteration cap (:264-266) is tested here only: every run of ADVANCEs ends in a POP after at most 3   */    \
     /* steps, so the test is at most ~26 iterations late, and cap_fixup() turns any cast that ends with        */    \
-    /* iter > 1500 into exactly what the reference returns at iteration 1501.                                   */    \
+    /* iter > 1500 into exactly what the reference returns at iteration 1501.  (iter == 1500 must go on: this   */    \
+    /* POP may leave the cube, and then the reference ends the cast as an ordinary miss at iteration 1500.)     */    \
     /* ... and so is "the ray has left the content box for good" (BOX).                                         */    \
-    if (iter >= (uint32_t)kMaxIterations || (BOX && t_min > tb_out)) {                                               \
-      if (iter >= (uint32_t)kMaxIterations) iter = (uint32_t)kMaxIterations + 1u;                                    \
-      EXIT(TRAV_MISS);                                                                                               \
+    if (iter > (float)kMaxIterations || (BOX && t_min > tb_out)) {                                                   \
+      EXIT(TRAV_MISS); /* cap_fixup() normalises iter */                                                             \
     }                                                                                                                \
     uint32_t differing_bits = 0;                                                                                     \
     if (sx) differing_bits |= __float_as_uint(px) ^ __float_as_uint(fadd(px, scale_exp2));                           \
@@ -385,8 +387,8 @@ struct Trav {
   // A hit found after iteration 1500 (only possible through a run of PUSHes right after the last ADVANCE
   // check) is a cast the reference abandoned at iteration 1501 (:264-266).
   __device__ __forceinline__ int cap_fixup(int status) {
-    if (iter > (uint32_t)kMaxIterations) {
-      iter = (uint32_t)kMaxIterations + 1u;
+    if (iter > (float)kMaxIterations) {
+      iter = (float)(kMaxIterations + 1);
       return TRAV_MISS;
     }
     return status;
@@ -424,7 +426,7 @@ struct Trav {
     hs.ipy = __float_as_uint(py);
     hs.ipz = __float_as_uint(pz);
     hs.t_min = t_min;
-    hs.iter = iter;
+    hs.iter = (uint32_t)iter;
     return hs;
   }
   __device__ __forceinline__ bool finish(const SceneView &sc, int status, CastRes &res, uint32_t &loops, bool attrs = true) const {

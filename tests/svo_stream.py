@@ -76,6 +76,33 @@ def serialise(root: Node) -> np.ndarray:
     return np.frombuffer(bytes(buf), dtype=np.uint8).copy()
 
 
+def tube(depth: int) -> Node:
+    """Only the row of cells along x at y = z = 0 is subdivided, down to `depth`; every leaf is empty.  A ray sent
+    along the row walks ~2.9 iterations per cell without ever hitting: the way to reach the 1500-iteration cap
+    (svotrace.comp:264-266) and its neighbourhood with ordinary rays."""
+    def build(d, iy, iz):
+        kids = []
+        for n in range(8):
+            cy, cz = 2 * iy + ((n >> 1) & 1), 2 * iz + ((n >> 2) & 1)
+            kids.append(build(d + 1, cy, cz) if (cy == 0 and cz == 0 and d + 1 < depth) else nonsurf(0))
+        return interior(1, kids)
+    return build(0, 0, 0)
+
+
+def tube_rays(depth: int, n: int, seed: int = 7) -> np.ndarray:
+    """Rays inside the tube, nearly parallel to it, from random start points (so their iteration counts cover a range)."""
+    rng = np.random.default_rng(seed)
+    rays = np.zeros(n, dtype=np.dtype([("o", np.float32, 3), ("d", np.float32, 3)]))
+    h = 2.0 ** -depth
+    rays["o"][:, 0] = rng.uniform(1.0, 2.0, n)
+    rays["o"][:, 1] = 1 + h * rng.uniform(0.2, 0.8, n)
+    rays["o"][:, 2] = 1 + h * rng.uniform(0.2, 0.8, n)
+    rays["d"][:, 0] = np.where(rng.random(n) < 0.5, -1, 1)
+    rays["d"][:, 1] = rng.uniform(-1e-4, 1e-4, n)
+    rays["d"][:, 2] = rng.uniform(-1e-4, 1e-4, n)
+    return rays
+
+
 def decode_voxels(nodes: np.ndarray, n: int) -> np.ndarray:
     """Walk a stream and paint every leaf into an n^3 grid [z,y,x] (interior nodes without children paint their value)."""
     out = np.zeros((n, n, n), np.uint8)

@@ -648,3 +648,37 @@ def test_full_size_properties(svo, oracle, size):
             # counters of the instrumented kernel: casts = pixels + primary hits (a bounce is cast iff the primary hit)
             st = c.render_stats(f0)
             assert st["casts"] == W * H + int(hit.sum()) and st["iters"] >= st["casts"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_iteration_cap_boundary(svo, oracle, kernel):
+    """Casts that end exactly at, just below and beyond the 1500-iteration cap (svotrace.comp:264-266): the device
+    tests the cap only on the POP path, so the boundary needs its own case.  Ray stream + iteration heat map."""
+    import svo_stream as S
+    nodes = S.serialise(S.tube(10))
+    rays = S.tube_rays(10, 100000)
+    want, _ = oracle.cast_rays(nodes, rays, 13, nthreads=4)
+    assert (want["iter"] == 1500).sum() > 0 and (want["iter"] == 1501).sum() > 0
+    W, H = 96, 64
+    h = 2.0 ** -10
+    cam = ((1.9, 1 + h / 2, 1 + h / 2), (-1, -1e-4, -1e-4), (-1, 1e-4, -1e-4), (-1, -1e-4, 1e-4), (-1, 1e-4, 1e-4))
+    with svo.SvoContext(W, H) as c:
+        c.upload(nodes)
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
+        for sort in (0, 1):
+            c.set_option(svo._lib.OPT_RAY_SORT, sort)
+            got = c.cast(rays, 13)
+            for k in ("id", "iter", "value"):
+                assert np.array_equal(got[k], want[k]), (k, sort)
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        seen = set()
+        for x0 in (1.9, 1.732, 1.7305, 1.73):  # every pixel capped / capped / exactly 1500 iterations / 1497
+            pos = (x0,) + cam[0][1:]
+            for mode in (1, 0):
+                wantp, _ = oracle.render(nodes, oracle.make_frame(pos, *cam[1:], frame_number=3, render_mode=mode, max_depth=13), W, H, nthreads=4)
+                c.render(svo.make_frame(pos, *cam[1:], frame_number=3, render_mode=mode, max_depth=13))
+                assert np.array_equal(c.read_iter(), wantp["iter"]), (x0, mode)
+                assert np.array_equal(c.read_color_rgba8(), wantp["rgba8"]), (x0, mode)
+                assert np.array_equal(c.read_radiance().view(np.uint32), wantp["radiance"].view(np.uint32)), (x0, mode)
+                seen |= set(np.unique(wantp["iter"]).tolist())
+        assert {1497, 1500, 1501} <= seen

@@ -233,3 +233,23 @@ def test_oracle_math_accuracy(oracle):
     assert ulps(ex, np.exp(e.astype(np.float64))).max() < 4
     r = np.array([L.svo_oracle_rand(float(p), float(q)) for p, q in zip(big[:500], big[500:1000])], np.float32)
     assert ((r >= 0) & (r < 1)).all()
+
+
+def test_iteration_cap_boundary(oracle):
+    """svotrace.comp:263-266: `iter++; if (iter > 1500) return false`.  A ray that leaves the cube during iteration
+    1500 is an ordinary miss with iter = 1500; one that would need iteration 1501 is capped (iter = 1501, the entry
+    colour kept).  Long walks through an all-empty subdivided row give both kinds."""
+    import svo_stream as S
+    nodes = S.serialise(S.tube(10))
+    rays = S.tube_rays(10, 20000)
+    out, st = oracle.cast_rays(nodes, rays, 13, nthreads=4)
+    assert (out["id"] == 0xFFFFFFFF).all()
+    it = out["iter"]
+    assert it.max() == 1501 and st.capped == (it == 1501).sum() > 0
+    assert (it == 1500).sum() > 0 and ((it > 1480) & (it < 1500)).sum() > 0
+    # one of each through the single-cast entry point: debugColor tells the two exits apart
+    i_cap, i_last = int(np.flatnonzero(it == 1501)[0]), int(np.flatnonzero(it == 1500)[0])
+    hit, res, s1 = oracle.cast(nodes, rays["o"][i_cap], rays["d"][i_cap])
+    assert not hit and s1.capped == 1 and list(res.debugColor) == pytest.approx([0.3, 0.3, 0.6])
+    hit, res, s1 = oracle.cast(nodes, rays["o"][i_last], rays["d"][i_last])
+    assert not hit and s1.capped == 0 and s1.iters == 1500 and list(res.debugColor) == pytest.approx([15.0, 15.0, 15.0])
