@@ -147,20 +147,8 @@ int ensure_wavefront(svo_ctx *c) {
 
 SceneView scene_view(const svo_ctx *c, const svo_frame *frame = nullptr) {
   SceneView v;
-  // content box of the frame: leaves at any depth, plus every non-empty record at the depths where this frame's
-  // casts stop (maxDepth, and coneDepth for the cone-traced bounces), padded by 2^-9 (see Trav::setup)
-  CellBox b = c->leaf_box;
-  if (frame) {
-    b.add(c->depth_box[frame->maxDepth]);
-    b.add(c->depth_box[frame->coneDepth]);
-  } else {
-    for (const CellBox &d : c->depth_box) b.add(d);
-  }
-  for (int a = 0; a < 3; a++) {
-    if (b.empty()) { v.box_lo[a] = 4.0f; v.box_hi[a] = -4.0f; continue; }
-    v.box_lo[a] = 1.0f + (float)b.lo[a] * (1.0f / 16777216.0f) - 0.001953125f;
-    v.box_hi[a] = 1.0f + (float)b.hi[a] * (1.0f / 16777216.0f) + 0.001953125f;
-  }
+  // content box of the frame (svo_transcode.h)
+  content_box(c->leaf_box, c->depth_box, frame ? frame->maxDepth : -1, frame ? frame->coneDepth : -1, v.box_lo, v.box_hi);
   v.desc = c->d_desc;
   v.refbase = c->d_refbase;
   v.raw = c->d_raw;

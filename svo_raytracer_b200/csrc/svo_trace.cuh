@@ -105,9 +105,13 @@ SVO_DI uint32_t child_offset(uint32_t codes, uint32_t c) {
 }
 
 SVO_DI uint32_t find_msb(uint32_t x) {  // GLSL findMSB for x != 0
+#ifdef __CUDA_ARCH__
   uint32_t r;
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
   return r;
+#else  // host pass of nvcc (never called) and the g++ build of this header in tests/hostemu
+  return x ? 31u - (uint32_t)__builtin_clz(x) : 0xFFFFFFFFu;
+#endif
 }
 
 SVO_DI float sign_glsl(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }

@@ -43,6 +43,24 @@ struct Transcoded {
   CellBox depth_box[24];
 };
 
+// Content box of a frame in cube coordinates [1,2], padded by 2^-9 (see Trav::setup): leaves at any depth, plus
+// every non-empty record at the depths where the frame's casts stop (maxDepth, and coneDepth for the cone-traced
+// bounces); depths < 0 = all depths.  An empty box comes out as lo > hi.
+inline void content_box(const CellBox &leaf_box, const CellBox *depth_box, int maxDepth, int coneDepth, float lo[3], float hi[3]) {
+  CellBox b = leaf_box;
+  if (maxDepth >= 0 && maxDepth < 24 && coneDepth >= 0 && coneDepth < 24) {
+    b.add(depth_box[maxDepth]);
+    b.add(depth_box[coneDepth]);
+  } else {
+    for (int d = 0; d < 24; d++) b.add(depth_box[d]);
+  }
+  for (int a = 0; a < 3; a++) {
+    if (b.empty()) { lo[a] = 4.0f; hi[a] = -4.0f; continue; }
+    lo[a] = 1.0f + (float)b.lo[a] * (1.0f / 16777216.0f) - 0.001953125f;
+    hi[a] = 1.0f + (float)b.hi[a] * (1.0f / 16777216.0f) + 0.001953125f;
+  }
+}
+
 // Returns false (with `err` set) if the stream cannot be a tree (more
 // descriptors than bytes: cyclic or heavily aliased child pointers).
 bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std::string &err, int nthreads = 0);

@@ -1,0 +1,120 @@
+"""ctypes binding of tests/hostemu/libsvo_hostemu.so (TEST INFRASTRUCTURE): the DEVICE source of the trace path
+(svo_trace.cuh) compiled for the host by g++ through cuda_host_shim.h.  See emu.cpp."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.normpath(os.path.join(_HERE, "..", "..", "svo_raytracer_b200", "csrc"))
+_LIB_PATH = os.path.join(_HERE, "libsvo_hostemu.so")
+_SRCS = [os.path.join(_HERE, "emu.cpp"), os.path.join(_HERE, "cuda_host_shim.h"), os.path.join(_CSRC, "svo_trace.cuh"),
+         os.path.join(_CSRC, "detmath.cuh"), os.path.join(_CSRC, "svo_kernels.h"), os.path.join(_CSRC, "svo_transcode.cpp"),
+         os.path.join(_CSRC, "svo_transcode.h")]
+CUDA_INCLUDE = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+
+def build(force: bool = False) -> str:
+    stale = force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in _SRCS)
+    if stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall",
+                               "-I" + CUDA_INCLUDE, "-o", _LIB_PATH, os.path.join(_HERE, "emu.cpp"),
+                               os.path.join(_CSRC, "svo_transcode.cpp"), "-lpthread"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.emu_scene_create.restype = C.c_void_p
+        L.emu_scene_create.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int]
+        L.emu_scene_destroy.argtypes = [C.c_void_p]
+        L.emu_scene_ndesc.restype = C.c_uint64
+        L.emu_scene_ndesc.argtypes = [C.c_void_p]
+        L.emu_render.restype = C.c_int
+        L.emu_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_cast.restype = C.c_int
+        L.emu_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
+        L.emu_beam.restype = C.c_int
+        L.emu_beam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.emu_math.restype = C.c_float
+        L.emu_math.argtypes = [C.c_int, C.c_float, C.c_float]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+PATH_RUN, PATH_STEP, PATH_STATS = 0, 1, 2
+
+
+class Scene:
+    """A node stream transcoded by the product's host transcoder, viewed through the device structs."""
+
+    def __init__(self, nodes: np.ndarray):
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint8)
+        err = C.create_string_buffer(256)
+        self._h = lib().emu_scene_create(_ptr(nodes), nodes.size, err, 256)
+        if not self._h:
+            raise ValueError(err.value.decode())
+
+    def close(self):
+        if self._h:
+            lib().emu_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def ndesc(self):
+        return int(lib().emu_scene_ndesc(self._h))
+
+    def render(self, frame, width, height, y0=0, y1=None, path=PATH_RUN, box=False, aux=True, beam=None, prev_rgba8=None,
+               nthreads=8):
+        """`frame`: any ctypes struct laid out like svo_frame (oracle.Frame or the product's).  Returns the planes
+        (and the counters of k_render_stats for path=PATH_STATS)."""
+        y1 = height if y1 is None else y1
+        out = {"rgba8": np.zeros((height, width, 4), np.uint8) if prev_rgba8 is None else np.ascontiguousarray(prev_rgba8, np.uint8).copy(),
+               "depth": np.zeros((height, width), np.float32)}
+        want_aux = aux or path == PATH_STATS
+        if want_aux:
+            out["radiance"] = np.zeros((height, width, 4), np.float32)
+            out["hit_id"] = np.zeros((height, width), np.uint32)
+            out["iter"] = np.zeros((height, width), np.uint32)
+            out["primary_t"] = np.zeros((height, width), np.float32)
+        if beam is not None:
+            beam = np.ascontiguousarray(beam, dtype=np.float32)
+        counters = np.zeros(3, np.uint64)
+        rc = lib().emu_render(self._h, C.byref(frame), width, height, y0, y1, path, int(box), int(aux), _ptr(beam),
+                              _ptr(out["rgba8"]), _ptr(out["depth"]), _ptr(out.get("hit_id")), _ptr(out.get("iter")),
+                              _ptr(out.get("primary_t")), _ptr(out.get("radiance")), _ptr(counters), nthreads)
+        assert rc == 0
+        if path == PATH_STATS:
+            return out, {"casts": int(counters[0]), "iters": int(counters[1]), "record_bytes": int(counters[2])}
+        return out
+
+    def cast(self, rays, max_depth=13, nthreads=8):
+        from oracle import oracle as O
+        rays = np.ascontiguousarray(rays, dtype=O.RAY_DTYPE)
+        out = np.zeros(rays.shape[0], dtype=O.HIT_DTYPE)
+        lib().emu_cast(self._h, _ptr(rays), rays.shape[0], _ptr(out), max_depth, nthreads)
+        return out
+
+    def beam(self, frame, width, height):
+        out = np.zeros((height // 4, width // 4), np.float32)
+        lib().emu_beam(self._h, C.byref(frame), _ptr(out), width, height)
+        return out
+
+
+def math(fn: int, x: float, y: float = 0.0) -> float:
+    return float(lib().emu_math(fn, float(x), float(y)))

@@ -1,0 +1,194 @@
+"""CPU check of the DEVICE source: svo_trace.cuh compiled for the host (tests/hostemu) against the oracle.
+
+The build container has no GPU, so the `-m gpu` parity tests cannot run there.  These tests run the very statements
+of the sm_100a kernels -- same headers, same template instances, same launch-time selection -- on the CPU and
+demand the same bit-exact agreement with the oracle.  What they cannot see is nvcc's code generation and the
+__global__ wrappers; `pytest -m gpu` on the B200 covers those through the C ABI."""
+import numpy as np
+import pytest
+
+from hostemu import emu as E
+
+PLANES = ("rgba8", "depth", "radiance", "hit_id", "iter", "primary_t")
+
+
+def _same(g, w):
+    if g.dtype.kind == "f":
+        return (g.view(np.uint32) == w.view(np.uint32)) | (np.isnan(g) & np.isnan(w))
+    return g == w
+
+
+def _assert_planes_equal(got, want, what, planes=PLANES):
+    for k in planes:
+        same = _same(got[k], want[k])
+        assert same.all(), "%s: plane %s differs in %d of %d elements" % (what, k, int((~same).sum()), same.size)
+
+
+@pytest.fixture(scope="module")
+def scene512(terrain512):
+    s = E.Scene(terrain512)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def scene128(terrain128):
+    s = E.Scene(terrain128)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("cam", ["A", "B", "C"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_device_source_config1_all_modes(svo, oracle, terrain512, scene512, cam, mode):
+    """BASELINE configs[0] (512^3, 640x360): Trav::run (tile kernel) and Trav::step (persistent / wavefront state
+    machine), every plane, every render mode."""
+    pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+    f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=3, render_mode=mode)
+    want, _ = oracle.render(terrain512, f, 640, 360, nthreads=8)
+    _assert_planes_equal(scene512.render(f, 640, 360, path=E.PATH_RUN), want, "run cam %s mode %d" % (cam, mode))
+    if cam == "B":
+        _assert_planes_equal(scene512.render(f, 640, 360, path=E.PATH_STEP), want, "step cam %s mode %d" % (cam, mode))
+    # production instance (content box on, no validation planes): colour and depth unchanged
+    if mode != 1:
+        _assert_planes_equal(scene512.render(f, 640, 360, box=True, aux=False), want, "box cam %s mode %d" % (cam, mode),
+                             planes=("rgba8", "depth"))
+
+
+def test_device_source_stats_counters(svo, oracle, terrain512, scene512):
+    """k_render_stats' counters (the algorithmic bytes of bench.py's roofline) equal the oracle's."""
+    for cam, mode in (("A", 0), ("B", 2), ("C", 0)):
+        pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+        f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=mode)
+        _, st = oracle.render(terrain512, f, 640, 360, nthreads=8, planes=("depth",))
+        _, got = scene512.render(f, 640, 360, path=E.PATH_STATS)
+        assert got == {"casts": st.casts, "iters": st.iters, "record_bytes": st.record_bytes}, (cam, mode)
+
+
+def test_device_source_ray_stream(svo, oracle, terrain512, scene512):
+    rng = np.random.default_rng(42)
+    n = 100000
+    rays = np.zeros(n, dtype=oracle.RAY_DTYPE)
+    rays["o"] = rng.uniform(0.9, 2.1, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["d"][:50, 0] = 0.0
+    rays["d"][50:60] = 0.0
+    rays["d"][60:70] = np.nan
+    rays["d"][70:80, 1] = np.nan
+    rays["o"][80:90] = np.nan
+    for depth in (13, 9, 5):
+        want, _ = oracle.cast_rays(terrain512, rays, max_depth=depth, nthreads=8)
+        got = scene512.cast(rays, max_depth=depth)
+        for k in ("id", "value", "iter"):
+            assert np.array_equal(got[k], want[k]), (depth, k)
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+
+
+def test_device_source_multichunk_rows_beam_accumulate(svo, oracle, terrain128, scene128):
+    """Chunk splices + fill level, uneven row bands, the beam pre-pass feeding a frame, progressive accumulation."""
+    W, H = 200, 120
+    for cam in ("A", "B", "C"):
+        pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+        f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=0, max_depth=7)
+        want, _ = oracle.render(terrain128, f, W, H, nthreads=8)
+        got = None
+        for y0, y1 in ((0, 37), (37, 38), (38, H)):
+            part = scene128.render(f, W, H, y0, y1)
+            got = part if got is None else {k: np.where((np.arange(H) >= y0)[(slice(None),) + (None,) * (part[k].ndim - 1)], part[k], got[k]) for k in part}
+        _assert_planes_equal(got, want, "bands cam " + cam)
+    pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+    fb = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, use_beam=1, max_depth=7)
+    beam_want = oracle.beam(terrain128, fb, W, H)
+    beam_got = scene128.beam(fb, W, H)
+    assert np.array_equal(beam_got.view(np.uint32), beam_want.view(np.uint32))
+    want, _ = oracle.render(terrain128, fb, W, H, beam=beam_want, nthreads=8)
+    _assert_planes_equal(scene128.render(fb, W, H, beam=beam_got), want, "beam frame")
+    prev = None
+    pos, l1, l2, r1, r2 = svo.CAMERAS["C"]
+    for frame in (1, 2, 3):
+        f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=frame, render_mode=0, max_depth=7, flags=1)
+        want, _ = oracle.render(terrain128, f, 160, 90, nthreads=4, planes=("rgba8", "depth"), prev_rgba8=prev)
+        got = scene128.render(f, 160, 90, box=True, aux=False, prev_rgba8=prev)
+        assert np.array_equal(got["rgba8"], want["rgba8"]), frame
+        prev = want["rgba8"]
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_device_source_random_worlds_random_cameras(svo, oracle, seed):
+    """The fuzz of test_gpu_parity.test_random_worlds_random_cameras on the host build of the device source."""
+    rng = np.random.default_rng(seed)
+    n = 32 if seed % 2 else 64
+    vox = np.zeros((n, n, n), np.uint8)
+    pts = rng.integers(0, n, size=(rng.integers(50, 600), 3))
+    vox[pts[:, 2], pts[:, 1], pts[:, 0]] = rng.integers(1, 5, size=len(pts))
+    for _ in range(3):
+        lo = rng.integers(0, n - 10, 3)
+        sz = rng.integers(3, 10, 3)
+        vox[lo[2]:lo[2] + sz[2], lo[1]:lo[1] + sz[1], lo[0]:lo[0] + sz[0]] = rng.integers(1, 4)
+    nodes, _ = oracle.build_dense(vox)
+    W, H = 96, 64
+    depth = int(np.log2(n))
+    sc = E.Scene(nodes)
+    for trial in range(6):
+        pos = rng.uniform(0.7, 2.3, 3) if trial % 2 else rng.uniform(1.1, 1.9, 3)
+        fwd = rng.normal(size=3)
+        fwd /= np.linalg.norm(fwd)
+        up = np.cross(fwd, rng.normal(size=3))
+        up /= np.linalg.norm(up)
+        right = np.cross(fwd, up)
+        corners = [fwd + sx * 1.2 * right + sy * 0.8 * up for sx in (-1, 1) for sy in (-1, 1)]
+        kw = dict(frame_number=int(rng.integers(1, 50)), render_mode=int(rng.choice([0, 0, 2, 2, 1, 3])),
+                  max_depth=int(rng.integers(max(1, depth - 2), depth + 1)), casts=int(rng.integers(1, 4)),
+                  cone_depth=int(rng.integers(1, depth + 1)), mirror_value=int(rng.choice([0, 4])))
+        f = oracle.make_frame(pos, *corners, **kw)
+        want, _ = oracle.render(nodes, f, W, H, nthreads=4)
+        _assert_planes_equal(sc.render(f, W, H, path=E.PATH_RUN), want, "seed %d trial %d %s" % (seed, trial, kw))
+        _assert_planes_equal(sc.render(f, W, H, path=E.PATH_STEP), want, "step seed %d trial %d %s" % (seed, trial, kw))
+        if kw["render_mode"] != 1:
+            _assert_planes_equal(sc.render(f, W, H, box=True, aux=False), want, "box seed %d trial %d %s" % (seed, trial, kw),
+                                 planes=("rgba8", "depth"))
+    sc.close()
+
+
+def test_device_source_iteration_cap_boundary(oracle):
+    """Casts ending exactly at, just below and beyond the 1500-iteration cap: the device tests the cap on the POP
+    path only (Trav), so the boundary is its own case."""
+    import svo_stream as S
+    nodes = S.serialise(S.tube(10))
+    rays = S.tube_rays(10, 100000)
+    want, _ = oracle.cast_rays(nodes, rays, 13, nthreads=4)
+    assert (want["iter"] == 1500).sum() > 0 and (want["iter"] == 1501).sum() > 0
+    sc = E.Scene(nodes)
+    got = sc.cast(rays, 13)
+    for k in ("id", "iter", "value"):
+        assert np.array_equal(got[k], want[k]), k
+    W, H = 96, 64
+    h = 2.0 ** -10
+    cam = ((1.9, 1 + h / 2, 1 + h / 2), (-1, -1e-4, -1e-4), (-1, 1e-4, -1e-4), (-1, -1e-4, 1e-4), (-1, 1e-4, 1e-4))
+    seen = set()
+    for x0 in (1.9, 1.732, 1.7305, 1.73):
+        pos = (x0,) + cam[0][1:]
+        for mode in (1, 0):
+            f = oracle.make_frame(pos, *cam[1:], frame_number=3, render_mode=mode, max_depth=13)
+            wantp, _ = oracle.render(nodes, f, W, H, nthreads=4)
+            _assert_planes_equal(sc.render(f, W, H, path=E.PATH_RUN), wantp, "cap run %s mode %d" % (x0, mode))
+            _assert_planes_equal(sc.render(f, W, H, path=E.PATH_STEP), wantp, "cap step %s mode %d" % (x0, mode))
+            seen |= set(np.unique(wantp["iter"]).tolist())
+    assert {1497, 1500, 1501} <= seen
+    sc.close()
+
+
+def test_device_math_equals_oracle_math(oracle):
+    rng = np.random.default_rng(7)
+    L = oracle.lib()
+    cases = {0: np.concatenate([rng.uniform(-7, 7, 3000), rng.uniform(-2e6, 2e6, 3000), [0.0, -0.0, np.inf, np.nan, 1e9, 3e38]]),
+             1: np.concatenate([rng.uniform(-7, 7, 3000), rng.uniform(-2e6, 2e6, 3000), [0.0, -0.0, np.inf, np.nan]]),
+             2: np.concatenate([rng.uniform(-1, 1, 5000), [-1.0, 1.0, 0.5, -0.5, 1.0000001, np.nan]]),
+             3: np.concatenate([rng.uniform(-20, 5, 5000), rng.uniform(-110, 90, 1000), [0.0, np.nan, -np.inf, np.inf]])}
+    names = {0: "sin", 1: "cos", 2: "acos", 3: "exp"}
+    for fn, xs in cases.items():
+        f = getattr(L, "svo_oracle_" + names[fn])
+        for v in xs.astype(np.float32):
+            a, b = np.float32(E.math(fn, v)), np.float32(f(float(v)))
+            assert a.view(np.uint32) == b.view(np.uint32) or (np.isnan(a) and np.isnan(b)), (names[fn], v)
