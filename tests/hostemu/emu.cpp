@@ -186,3 +186,226 @@ float emu_math(int fn, float x, float y) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// SIMT divergence model.  A warp of the tile kernel owns an 8x4 pixel tile; its 32 lanes run the traversal loop in
+// lockstep and the hardware re-converges them at the end of every iteration (BSSY/BSYNC around the loop body in
+// the SASS), so a warp iteration issues the loop head once plus every path -- PUSH, ADVANCE, POP -- that at
+// least one lane takes.  The sequence of paths a ray takes does not depend on the schedule, so it is recorded
+// once per ray (from the device source, Trav::step) and replayed under different loop organisations with the
+// per-path instruction counts read off the SASS.  Output: issue slots per organisation, to rank designs offline
+// and to compare with ncu's smsp__inst_executed of the real kernel.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+enum Op : uint8_t { OP_PUSH = 0, OP_ADV = 1, OP_POP = 2, OP_EXIT_HIT = 3, OP_EXIT_MISS = 4 };
+
+struct LaneCast {
+  std::vector<uint8_t> ops;  // one entry per loop iteration (the last one is an exit)
+  bool early = false;        // ended before the loop (outside the content box / NaN ray)
+};
+
+// costs[]: 0 head, 1 push, 2 advance, 3 pop, 4 loop tail (re-convergence + back branch), 5 exit on the head/push side (hit),
+//          6 exit on the pop side (miss), 7 per-cast code outside the loop (setup + finish + shading; issued once per warp cast)
+struct Costs { double head, push, adv, pop, tail, exit_hit, exit_miss, outside; };
+
+struct Tally {
+  double slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per organisation
+  double thread_ops = 0;                       // sum over lanes of their own path costs (what 100 % lane utilisation would issue x32)
+  double longest_lane = 0;                     // per warp cast: the most expensive lane alone (trip-count divergence only)
+  uint64_t iters = 0, casts = 0, warp_casts = 0, pushes = 0, advs = 0, pops = 0;
+  uint64_t warp_iters0 = 0, warp_iters_any[3] = {0, 0, 0};
+};
+
+inline double own_cost(const Costs &c, uint8_t op) {
+  switch (op) {
+    case OP_PUSH: return c.head + c.push + c.tail;
+    case OP_ADV: return c.head + c.adv + c.tail;
+    case OP_POP: return c.head + c.adv + c.pop + c.tail;
+    case OP_EXIT_HIT: return c.head + c.exit_hit;
+    default: return c.head + c.adv + c.exit_miss;
+  }
+}
+
+// organisation 0: the shipped loop -- every lane does one iteration per warp iteration
+double org_if_if(const Costs &c, const std::vector<const LaneCast *> &lanes, Tally &t) {
+  size_t pos[32] = {0};
+  double s = 0;
+  for (;;) {
+    bool any[5] = {false, false, false, false, false};
+    bool alive = false;
+    for (size_t l = 0; l < lanes.size(); l++)
+      if (pos[l] < lanes[l]->ops.size()) { any[lanes[l]->ops[pos[l]++]] = true; alive = true; }
+    if (!alive) break;
+    t.warp_iters0++;
+    if (any[OP_PUSH]) t.warp_iters_any[0]++;
+    if (any[OP_ADV] || any[OP_POP]) t.warp_iters_any[1]++;
+    if (any[OP_POP]) t.warp_iters_any[2]++;
+    s += c.head + c.tail;
+    if (any[OP_PUSH]) s += c.push;
+    if (any[OP_EXIT_HIT]) s += c.exit_hit;
+    if (any[OP_ADV] || any[OP_POP] || any[OP_EXIT_MISS]) s += c.adv;
+    if (any[OP_POP]) s += c.pop;
+    if (any[OP_EXIT_MISS]) s += c.exit_miss;
+  }
+  return s;
+}
+
+// organisation 1: while-while -- an inner loop of PUSHes (lanes that want to ADVANCE wait), then an inner loop of
+// ADVANCE/POPs (lanes that want to PUSH wait); `max_push` / `max_adv` bound the inner trip counts (0 = unbounded)
+double org_while_while(const Costs &c, const std::vector<const LaneCast *> &lanes, int max_push, int max_adv) {
+  size_t pos[32] = {0};
+  double s = 0;
+  const double phase = 2;  // ballot/branch per inner-loop trip
+  for (;;) {
+    bool alive = false;
+    for (size_t l = 0; l < lanes.size(); l++) alive |= pos[l] < lanes[l]->ops.size();
+    if (!alive) break;
+    for (int trip = 0; max_push == 0 || trip < max_push; trip++) {  // PUSH phase (hit exits are found on this side)
+      bool any = false, any_exit = false;
+      for (size_t l = 0; l < lanes.size(); l++)
+        if (pos[l] < lanes[l]->ops.size()) {
+          const uint8_t op = lanes[l]->ops[pos[l]];
+          if (op == OP_PUSH) { any = true; pos[l]++; }
+          else if (op == OP_EXIT_HIT) { any_exit = true; pos[l]++; }
+        }
+      if (!any && !any_exit) { s += trip == 0 ? c.head + phase : 0; break; }
+      s += c.head + phase + (any ? c.push : 0) + (any_exit ? c.exit_hit : 0);
+    }
+    for (int trip = 0; max_adv == 0 || trip < max_adv; trip++) {  // ADVANCE / POP phase
+      bool any = false, any_pop = false, any_exit = false;
+      for (size_t l = 0; l < lanes.size(); l++)
+        if (pos[l] < lanes[l]->ops.size()) {
+          const uint8_t op = lanes[l]->ops[pos[l]];
+          if (op == OP_ADV) { any = true; pos[l]++; }
+          else if (op == OP_POP) { any = any_pop = true; pos[l]++; }
+          else if (op == OP_EXIT_MISS) { any = any_exit = true; pos[l]++; }
+        }
+      if (!any) { s += trip == 0 ? c.head + phase : 0; break; }
+      s += c.head + phase + c.adv + (any_pop ? c.pop : 0) + (any_exit ? c.exit_miss : 0);
+    }
+    s += c.tail;
+  }
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Replays rows [y0, y1) of a frame warp by warp (8x4 pixel tiles, the tile kernel's mapping).  out[0..7] = issue slots
+// of the loop organisations (0 shipped if-if, 1 while-while unbounded, 2 while-while 1 push trip / 1 advance trip
+// (alternating), 3 while-while unbounded pushes / 1 advance, 4 while-while 1 push / unbounded advances, 5 bounded
+// 4/2), out[8] = thread ops / 32 (perfect lane utilisation), out[9] = longest lane per warp cast (trip-count
+// divergence only), out[10..] = counts: casts, iterations, pushes, advances, pops, warp casts, warp iterations of
+// the shipped loop, and of those the ones that issue PUSH / ADVANCE / POP.
+int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, int y1, int box, const double *costs, double *out,
+             int nthreads) {
+  const FrameParams &f = *fp;
+  const SceneView sc = view_of(s, fp);
+  Costs c{costs[0], costs[1], costs[2], costs[3], costs[4], costs[5], costs[6], costs[7]};
+  const int tiles_x = (W + 7) / 8, tiles_y0 = y0 / 4, tiles_y1 = (y1 + 3) / 4;
+  std::vector<Tally> tallies((size_t)std::max(1, nthreads));
+  std::atomic<int> next(tiles_y0);
+  std::vector<uint8_t> rgba((size_t)W * H * 4);
+  std::vector<float> depth((size_t)W * H);
+  Planes pl;
+  pl.rgba8 = (uchar4 *)rgba.data();
+  pl.depth = depth.data();
+  pl.beam = nullptr;
+  pl.hit_id = nullptr; pl.iter = nullptr; pl.primary_t = nullptr; pl.radiance = nullptr;
+  auto work = [&](int tid) {
+    Tally &t = tallies[(size_t)tid];
+    for (;;) {
+      const int ty = next.fetch_add(1);
+      if (ty >= tiles_y1) break;
+      for (int tx = 0; tx < tiles_x; tx++) {
+        std::vector<std::vector<LaneCast>> lane_casts(32);  // [lane][cast]
+        for (int l = 0; l < 32; l++) {
+          const int x = tx * 8 + (l & 7), y = ty * 4 + (l >> 3);
+          if (x >= W || y < y0 || y >= y1) continue;
+          Pixel P;
+          if (!pixel_begin(f, pl, W, H, x, y, P)) continue;
+          bool more;
+          do {
+            lane_casts[l].emplace_back();
+            LaneCast &lc = lane_casts[l].back();
+            uint2 stk[kMaxScale + 1];
+            int status;
+            if (box) {
+              Trav<false, false, true> T;
+              T.setup(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, nullptr);
+              if (T.outside_box() || T.nan_ray(nullptr)) { status = TRAV_MISS; lc.early = true; }
+              else for (;;) {
+                const int s0 = T.scale;
+                status = T.step(sc, stk, nullptr);
+                if (status != TRAV_CONTINUE) { lc.ops.push_back(status == TRAV_HIT ? OP_EXIT_HIT : OP_EXIT_MISS); break; }
+                lc.ops.push_back(T.scale < s0 ? OP_PUSH : (T.scale > s0 ? OP_POP : OP_ADV));
+              }
+              more = pixel_finish_cast(sc, f, P, T.export_hit(status));
+            } else {
+              Trav<false> T;
+              T.setup(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, nullptr);
+              if (T.nan_ray(nullptr)) { status = TRAV_MISS; lc.early = true; }
+              else for (;;) {
+                const int s0 = T.scale;
+                status = T.step(sc, stk, nullptr);
+                if (status != TRAV_CONTINUE) { lc.ops.push_back(status == TRAV_HIT ? OP_EXIT_HIT : OP_EXIT_MISS); break; }
+                lc.ops.push_back(T.scale < s0 ? OP_PUSH : (T.scale > s0 ? OP_POP : OP_ADV));
+              }
+              more = pixel_finish_cast(sc, f, P, T.export_hit(status));
+            }
+          } while (more);
+        }
+        for (size_t k = 0;; k++) {
+          std::vector<const LaneCast *> lanes;
+          for (int l = 0; l < 32; l++)
+            if (lane_casts[l].size() > k) lanes.push_back(&lane_casts[l][k]);
+          if (lanes.empty()) break;
+          t.warp_casts++;
+          double longest = 0;
+          for (const LaneCast *lc : lanes) {
+            double own = 0;
+            for (uint8_t op : lc->ops) {
+              own += own_cost(c, op);
+              t.pushes += op == OP_PUSH; t.advs += op == OP_ADV; t.pops += op == OP_POP;
+            }
+            t.iters += lc->ops.size();
+            t.casts++;
+            t.thread_ops += own + c.outside;
+            longest = std::max(longest, own);
+          }
+          t.longest_lane += longest + c.outside;
+          t.slots[0] += org_if_if(c, lanes, t) + c.outside;
+          t.slots[1] += org_while_while(c, lanes, 0, 0) + c.outside;
+          t.slots[2] += org_while_while(c, lanes, 1, 1) + c.outside;
+          t.slots[3] += org_while_while(c, lanes, 0, 1) + c.outside;
+          t.slots[4] += org_while_while(c, lanes, 1, 0) + c.outside;
+          t.slots[5] += org_while_while(c, lanes, 4, 2) + c.outside;
+        }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; i++) th.emplace_back(work, i);
+  work(0);
+  for (auto &x : th) x.join();
+  Tally sum;
+  for (const Tally &t : tallies) {
+    for (int i = 0; i < 8; i++) sum.slots[i] += t.slots[i];
+    sum.thread_ops += t.thread_ops; sum.longest_lane += t.longest_lane;
+    sum.iters += t.iters; sum.casts += t.casts; sum.warp_casts += t.warp_casts;
+    sum.pushes += t.pushes; sum.advs += t.advs; sum.pops += t.pops;
+    sum.warp_iters0 += t.warp_iters0;
+    for (int i = 0; i < 3; i++) sum.warp_iters_any[i] += t.warp_iters_any[i];
+  }
+  for (int i = 0; i < 8; i++) out[i] = sum.slots[i];
+  out[8] = sum.thread_ops / 32.0;
+  out[9] = sum.longest_lane;
+  out[10] = (double)sum.casts; out[11] = (double)sum.iters; out[12] = (double)sum.pushes; out[13] = (double)sum.advs;
+  out[14] = (double)sum.pops; out[15] = (double)sum.warp_casts; out[16] = (double)sum.warp_iters0;
+  out[17] = (double)sum.warp_iters_any[0]; out[18] = (double)sum.warp_iters_any[1]; out[19] = (double)sum.warp_iters_any[2];
+  return 0;
+}
+
+}  // extern "C"
