@@ -203,6 +203,8 @@ enum Op : uint8_t { OP_PUSH = 0, OP_ADV = 1, OP_POP = 2, OP_EXIT_HIT = 3, OP_EXI
 struct LaneCast {
   std::vector<uint8_t> ops;  // one entry per loop iteration (the last one is an exit)
   bool early = false;        // ended before the loop (outside the content box / NaN ray)
+  float dy = 0.0f;           // direction of the ray (regrouping keys of the what-if model)
+  uint8_t oct = 0;
 };
 
 // costs[]: 0 head, 1 push, 2 advance, 3 pop, 4 loop tail (re-convergence + back branch), 5 exit on the head/push side (hit),
@@ -213,9 +215,16 @@ struct Tally {
   double slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per organisation
   double thread_ops = 0;                       // sum over lanes of their own path costs (what 100 % lane utilisation would issue x32)
   double longest_lane = 0;                     // per warp cast: the most expensive lane alone (trip-count divergence only)
-  uint64_t iters = 0, casts = 0, warp_casts = 0, pushes = 0, advs = 0, pops = 0;
+  uint64_t iters = 0, casts = 0, warp_casts = 0, pushes = 0, advs = 0, pops = 0, early = 0;
   uint64_t warp_iters0 = 0, warp_iters_any[3] = {0, 0, 0};
+  // what-if: the casts after the first (bounce / shadow rays) of a group of G neighbouring tiles re-dealt to warps
+  // [g][0] as shipped, [g][1] sorted by true iteration count (bound), [g][2] by dir.y, [g][3] by (octant, dir.y), [g][4] by octant
+  double regroup[3][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+  double refill[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // [g][variant]: dynamic refill, see kRefillVariants
 };
+constexpr int kGroupSizes[3] = {4, 16, 64};
+// {workers as a fraction of the group's warps (1/x), idle-lane threshold}
+constexpr int kRefillVariants[4][2] = {{2, 8}, {2, 16}, {4, 8}, {4, 16}};
 
 inline double own_cost(const Costs &c, uint8_t op) {
   switch (op) {
@@ -289,6 +298,53 @@ double org_while_while(const Costs &c, const std::vector<const LaneCast *> &lane
   return s;
 }
 
+// what-if organisation: `workers` warps share a queue of rays (the bounce casts of a group of tiles); a warp whose idle
+// lanes reach `threshold` leaves the loop, takes rays from the queue (costs `refill` slots: loop exit/entry + Trav::setup
+// for the new lanes; the finished lanes' end states are parked for their owners) and goes on.  Returns issue slots.
+double org_refill(const Costs &c, const std::vector<const LaneCast *> &queue, int workers, int threshold, double refill) {
+  struct Lane { const LaneCast *lc = nullptr; size_t pos = 0; };
+  struct Worker { Lane lane[32]; double t = 0; bool done = false; };
+  std::vector<Worker> w((size_t)workers);
+  size_t head = 0;
+  double total = 0;
+  auto fill = [&](Worker &k) {
+    int taken = 0;
+    for (int l = 0; l < 32 && head < queue.size(); l++)
+      if (!k.lane[l].lc) { k.lane[l].lc = queue[head++]; k.lane[l].pos = 0; taken++; }
+    return taken;
+  };
+  for (auto &k : w) if (fill(k)) { k.t += refill; total += refill; } else k.done = true;
+  for (;;) {
+    Worker *k = nullptr;
+    for (auto &x : w) if (!x.done && (!k || x.t < k->t)) k = &x;
+    if (!k) break;
+    bool any[5] = {false, false, false, false, false};
+    int active = 0;
+    for (int l = 0; l < 32; l++) {
+      Lane &ln = k->lane[l];
+      if (!ln.lc) continue;
+      if (ln.pos < ln.lc->ops.size()) { any[ln.lc->ops[ln.pos++]] = true; active++; }
+      if (ln.pos >= ln.lc->ops.size()) ln.lc = nullptr;
+    }
+    double s = 0;
+    if (active) {
+      s = c.head + c.tail;
+      if (any[OP_PUSH]) s += c.push;
+      if (any[OP_EXIT_HIT]) s += c.exit_hit;
+      if (any[OP_ADV] || any[OP_POP] || any[OP_EXIT_MISS]) s += c.adv;
+      if (any[OP_POP]) s += c.pop;
+      if (any[OP_EXIT_MISS]) s += c.exit_miss;
+    }
+    int idle = 0, busy = 0;
+    for (int l = 0; l < 32; l++) (k->lane[l].lc ? busy : idle)++;
+    if ((idle >= threshold || busy == 0) && head < queue.size()) { fill(*k); s += refill; }
+    else if (busy == 0) k->done = true;
+    k->t += s;
+    total += s;
+  }
+  return total;
+}
+
 }  // namespace
 
 extern "C" {
@@ -300,11 +356,13 @@ extern "C" {
 // divergence only), out[10..] = counts: casts, iterations, pushes, advances, pops, warp casts, warp iterations of
 // the shipped loop, and of those the ones that issue PUSH / ADVANCE / POP.
 int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, int y1, int box, const double *costs, double *out,
-             int nthreads) {
+             int nthreads, int tile_w) {
+  if (tile_w != 4 && tile_w != 8 && tile_w != 16 && tile_w != 32) tile_w = 8;  // warp = tile_w x (32 / tile_w) pixels; the kernel uses 8x4
+  const int tile_h = 32 / tile_w, tw_shift = tile_w == 4 ? 2 : tile_w == 8 ? 3 : tile_w == 16 ? 4 : 5;
   const FrameParams &f = *fp;
   const SceneView sc = view_of(s, fp);
   Costs c{costs[0], costs[1], costs[2], costs[3], costs[4], costs[5], costs[6], costs[7]};
-  const int tiles_x = (W + 7) / 8, tiles_y0 = y0 / 4, tiles_y1 = (y1 + 3) / 4;
+  const int tiles_x = (W + tile_w - 1) / tile_w, tiles_y0 = y0 / tile_h, tiles_y1 = (y1 + tile_h - 1) / tile_h;
   std::vector<Tally> tallies((size_t)std::max(1, nthreads));
   std::atomic<int> next(tiles_y0);
   std::vector<uint8_t> rgba((size_t)W * H * 4);
@@ -319,10 +377,43 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
     for (;;) {
       const int ty = next.fetch_add(1);
       if (ty >= tiles_y1) break;
+      std::vector<std::vector<LaneCast>> pool[3];  // per group size: [cast index - 1] -> rays of the group so far
+      int pooled[3] = {0, 0, 0};
+      auto flush = [&](int g) {
+        for (auto &rays : pool[g]) {
+          if (rays.empty()) continue;
+          Tally scratch;
+          for (int order = 0; order < 5; order++) {
+            std::vector<const LaneCast *> v;
+            for (const LaneCast &lc : rays) v.push_back(&lc);
+            if (order == 1) std::stable_sort(v.begin(), v.end(), [](const LaneCast *a, const LaneCast *b) { return a->ops.size() < b->ops.size(); });
+            if (order == 2) std::stable_sort(v.begin(), v.end(), [](const LaneCast *a, const LaneCast *b) { return a->dy < b->dy; });
+            if (order == 3) std::stable_sort(v.begin(), v.end(), [](const LaneCast *a, const LaneCast *b) { return a->oct != b->oct ? a->oct < b->oct : a->dy < b->dy; });
+            if (order == 4) std::stable_sort(v.begin(), v.end(), [](const LaneCast *a, const LaneCast *b) { return a->oct < b->oct; });
+            for (size_t i = 0; i < v.size(); i += 32) {
+              std::vector<const LaneCast *> w(v.begin() + (long)i, v.begin() + (long)std::min(v.size(), i + 32));
+              t.regroup[g][order] += org_if_if(c, w, scratch) + c.outside;
+            }
+          }
+        }
+        for (auto &rays : pool[g]) {
+          if (rays.empty()) continue;
+          std::vector<const LaneCast *> v;
+          for (const LaneCast &lc : rays) v.push_back(&lc);
+          for (int r = 0; r < 4; r++) {
+            const int warps = (int)((v.size() + 31) / 32);
+            const int workers = std::max(1, warps / kRefillVariants[r][0]);
+            // code outside the loop: the shipped kernel pays c.outside per warp cast; here the shading still runs once per 32 rays
+            t.refill[g][r] += org_refill(c, v, workers, kRefillVariants[r][1], 110.0) + c.outside * warps;
+          }
+        }
+        pool[g].clear();
+        pooled[g] = 0;
+      };
       for (int tx = 0; tx < tiles_x; tx++) {
         std::vector<std::vector<LaneCast>> lane_casts(32);  // [lane][cast]
         for (int l = 0; l < 32; l++) {
-          const int x = tx * 8 + (l & 7), y = ty * 4 + (l >> 3);
+          const int x = tx * tile_w + (l & (tile_w - 1)), y = ty * tile_h + (l >> tw_shift);
           if (x >= W || y < y0 || y >= y1) continue;
           Pixel P;
           if (!pixel_begin(f, pl, W, H, x, y, P)) continue;
@@ -330,6 +421,8 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
           do {
             lane_casts[l].emplace_back();
             LaneCast &lc = lane_casts[l].back();
+            lc.dy = P.dir.y;
+            lc.oct = (uint8_t)((P.dir.x > 0.0f ? 1 : 0) | (P.dir.y > 0.0f ? 2 : 0) | (P.dir.z > 0.0f ? 4 : 0));
             uint2 stk[kMaxScale + 1];
             int status;
             if (box) {
@@ -372,6 +465,7 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
             }
             t.iters += lc->ops.size();
             t.casts++;
+            t.early += lc->early;
             t.thread_ops += own + c.outside;
             longest = std::max(longest, own);
           }
@@ -382,6 +476,14 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
           t.slots[3] += org_while_while(c, lanes, 0, 1) + c.outside;
           t.slots[4] += org_while_while(c, lanes, 1, 0) + c.outside;
           t.slots[5] += org_while_while(c, lanes, 4, 2) + c.outside;
+        }
+        for (int g = 0; g < 3; g++) {
+          for (int l = 0; l < 32; l++)
+            for (size_t k = 1; k < lane_casts[l].size(); k++) {
+              if (pool[g].size() < k) pool[g].resize(k);
+              pool[g][k - 1].push_back(lane_casts[l][k]);
+            }
+          if (++pooled[g] == kGroupSizes[g] || tx + 1 == tiles_x) flush(g);
         }
       }
     }
@@ -395,7 +497,9 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
     for (int i = 0; i < 8; i++) sum.slots[i] += t.slots[i];
     sum.thread_ops += t.thread_ops; sum.longest_lane += t.longest_lane;
     sum.iters += t.iters; sum.casts += t.casts; sum.warp_casts += t.warp_casts;
-    sum.pushes += t.pushes; sum.advs += t.advs; sum.pops += t.pops;
+    sum.pushes += t.pushes; sum.advs += t.advs; sum.pops += t.pops; sum.early += t.early;
+    for (int g = 0; g < 3; g++) for (int o = 0; o < 5; o++) sum.regroup[g][o] += t.regroup[g][o];
+    for (int g = 0; g < 3; g++) for (int o = 0; o < 4; o++) sum.refill[g][o] += t.refill[g][o];
     sum.warp_iters0 += t.warp_iters0;
     for (int i = 0; i < 3; i++) sum.warp_iters_any[i] += t.warp_iters_any[i];
   }
@@ -405,7 +509,46 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
   out[10] = (double)sum.casts; out[11] = (double)sum.iters; out[12] = (double)sum.pushes; out[13] = (double)sum.advs;
   out[14] = (double)sum.pops; out[15] = (double)sum.warp_casts; out[16] = (double)sum.warp_iters0;
   out[17] = (double)sum.warp_iters_any[0]; out[18] = (double)sum.warp_iters_any[1]; out[19] = (double)sum.warp_iters_any[2];
+  for (int g = 0; g < 3; g++) for (int o = 0; o < 5; o++) out[20 + g * 5 + o] = sum.regroup[g][o];
+  for (int g = 0; g < 3; g++) for (int o = 0; o < 4; o++) out[35 + g * 4 + o] = sum.refill[g][o];
+  out[47] = (double)sum.early;  // casts that ended before the loop (outside the content box, NaN rays)
   return 0;
 }
 
 }  // extern "C"
+
+// Path string of every cast of pixel (x, y): 'P' PUSH, 'A' ADVANCE, 'Q' ADVANCE+POP, 'H' exit hit, 'M' exit miss, '|' between casts;
+// each op is followed by the scale digit-letter ('a' + scale) it ran at.  For eyeballing what rays do (tools/simt_model.py --pixel).
+extern "C" int emu_pixel_ops(const emu_scene *s, const FrameParams *fp, int W, int H, int x, int y, int box, char *buf, int cap) {
+  const FrameParams &f = *fp;
+  const SceneView sc = view_of(s, fp);
+  std::vector<uint8_t> rgba((size_t)W * H * 4);
+  std::vector<float> depth((size_t)W * H);
+  Planes pl;
+  pl.rgba8 = (uchar4 *)rgba.data(); pl.depth = depth.data(); pl.beam = nullptr;
+  pl.hit_id = nullptr; pl.iter = nullptr; pl.primary_t = nullptr; pl.radiance = nullptr;
+  std::string out;
+  Pixel P;
+  if (pixel_begin(f, pl, W, H, x, y, P)) {
+    bool more;
+    do {
+      uint2 stk[kMaxScale + 1];
+      int status;
+      Trav<false, false, true> T;
+      T.setup(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, nullptr);
+      if ((box && T.outside_box()) || T.nan_ray(nullptr)) { status = TRAV_MISS; out += "X"; }
+      else for (;;) {
+        if (!box) T.tb_out = __uint_as_float(0x7f800000u);
+        const int s0 = T.scale;
+        status = T.step(sc, stk, nullptr);
+        if (status != TRAV_CONTINUE) { out += status == TRAV_HIT ? 'H' : 'M'; out += (char)('a' + s0); break; }
+        out += T.scale < s0 ? 'P' : (T.scale > s0 ? 'Q' : 'A');
+        out += (char)('a' + s0);
+      }
+      more = pixel_finish_cast(sc, f, P, T.export_hit(status));
+      out += '|';
+    } while (more);
+  }
+  snprintf(buf, (size_t)cap, "%s", out.c_str());
+  return (int)out.size();
+}

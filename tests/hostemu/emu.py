@@ -46,7 +46,9 @@ def lib():
         L.emu_beam.restype = C.c_int
         L.emu_beam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emu_simt.restype = C.c_int
-        L.emu_simt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_simt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.emu_pixel_ops.restype = C.c_int
+        L.emu_pixel_ops.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.emu_math.restype = C.c_float
         L.emu_math.argtypes = [C.c_int, C.c_float, C.c_float]
         _lib = L
@@ -112,19 +114,30 @@ class Scene:
         lib().emu_cast(self._h, _ptr(rays), rays.shape[0], _ptr(out), max_depth, nthreads)
         return out
 
-    def simt(self, frame, width, height, costs, y0=0, y1=None, box=True, nthreads=8):
+    def simt(self, frame, width, height, costs, y0=0, y1=None, box=True, nthreads=8, tile_w=8):
         """The SIMT divergence model of emu.cpp: issue slots of the traversal under several loop organisations."""
         y1 = height if y1 is None else y1
         costs = np.ascontiguousarray(costs, dtype=np.float64)
         assert costs.size == 8
-        out = np.zeros(32, np.float64)
-        lib().emu_simt(self._h, C.byref(frame), width, height, y0, y1, int(box), _ptr(costs), _ptr(out), nthreads)
+        out = np.zeros(48, np.float64)
+        lib().emu_simt(self._h, C.byref(frame), width, height, y0, y1, int(box), _ptr(costs), _ptr(out), nthreads, tile_w)
         names = ("if_if", "while_while", "ww_1_1", "ww_inf_1", "ww_1_inf", "ww_4_2")
         r = {n: float(out[i]) for i, n in enumerate(names)}
         r.update(ideal=float(out[8]), longest_lane=float(out[9]), casts=int(out[10]), iters=int(out[11]), pushes=int(out[12]),
                  advances=int(out[13]), pops=int(out[14]), warp_casts=int(out[15]), warp_iters=int(out[16]),
-                 warp_iters_push=int(out[17]), warp_iters_adv=int(out[18]), warp_iters_pop=int(out[19]))
+                 warp_iters_push=int(out[17]), warp_iters_adv=int(out[18]), warp_iters_pop=int(out[19]), early=int(out[47]))
+        for g, G in enumerate((4, 16, 64)):
+            for o, name in enumerate(("as_is", "by_length", "by_dy", "by_oct_dy", "by_oct")):
+                r["regroup%d_%s" % (G, name)] = float(out[20 + g * 5 + o])
+            for o, name in enumerate(("half_warps_idle8", "half_warps_idle16", "quarter_warps_idle8", "quarter_warps_idle16")):
+                r["refill%d_%s" % (G, name)] = float(out[35 + g * 4 + o])
         return r
+
+    def pixel_ops(self, frame, width, height, x, y, box=True):
+        """Path string of pixel (x, y): op letter (P/A/Q/H/M, X = ended before the loop) + scale letter per iteration."""
+        buf = C.create_string_buffer(1 << 16)
+        lib().emu_pixel_ops(self._h, C.byref(frame), width, height, x, y, int(box), buf, len(buf))
+        return buf.value.decode()
 
     def beam(self, frame, width, height):
         out = np.zeros((height // 4, width // 4), np.float32)

@@ -192,3 +192,25 @@ def test_device_math_equals_oracle_math(oracle):
         for v in xs.astype(np.float32):
             a, b = np.float32(E.math(fn, v)), np.float32(f(float(v)))
             assert a.view(np.uint32) == b.view(np.uint32) or (np.isnan(a) and np.isnan(b)), (names[fn], v)
+
+
+def test_simt_model_invariants(svo, oracle, terrain128, scene128):
+    """The divergence model of tools/simt_model.py: its counters equal the oracle's, and the bounds order as they must
+    (32 busy lanes <= slowest lane per warp <= every real loop organisation)."""
+    W, H = 200, 120
+    pos, l1, l2, r1, r2 = svo.CAMERAS["C"]
+    f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=0, max_depth=7)
+    costs = [14, 40, 18, 34, 2, 8, 10, 700]
+    r = scene128.simt(f, W, H, costs, box=False)
+    _, st = oracle.render(terrain128, f, W, H, nthreads=4, planes=("depth",))
+    # every iteration of every cast is replayed, none invented; NaN rays (zero-normal bounces) leave before the loop on
+    # the device where the reference spins 1500 iterations
+    assert r["casts"] == st.casts and r["iters"] + 1500 * r["early"] == st.iters
+    assert r["pushes"] + r["advances"] + r["pops"] + r["casts"] - r["early"] == r["iters"]  # one exit iteration per cast
+    assert r["ideal"] <= r["longest_lane"] <= min(r[k] for k in ("if_if", "while_while", "ww_1_1", "ww_inf_1", "ww_1_inf", "ww_4_2"))
+    for G in (4, 16, 64):
+        assert r["regroup%d_by_length" % G] <= r["regroup%d_as_is" % G] * 1.0001
+    rb = scene128.simt(f, W, H, costs, box=True)
+    assert rb["casts"] == r["casts"] and rb["iters"] <= r["iters"]  # the content box only ever removes iterations
+    # the warp tile the kernel uses (8x4) is what the model replays by default
+    assert scene128.simt(f, W, H, costs, box=False, tile_w=8)["if_if"] == r["if_if"]
