@@ -5,6 +5,14 @@
 #include "svo_kernels.h"
 #include "svo_trace.cuh"
 
+// Kernel launch.  The CPU test suite compiles this file with g++ and runs the __global__ functions on a coroutine
+// SIMT emulator (tests/hostemu/simt_emu.h, SVO_HOST_EMU): same kernels, same launch geometry, no GPU.
+#ifdef SVO_HOST_EMU
+#define SVO_LAUNCH(grid, block, stream, ...) simt::launcher(grid, block, __VA_ARGS__)
+#else
+#define SVO_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<grid, block, 0, stream>>>
+#endif
+
 namespace svo {
 
 // ---------------------------------------------------------------------------
@@ -355,18 +363,18 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
     if (e != cudaSuccess) return e;
     const int grid = cfg.sm_count * cfg.ctas_per_sm;
     if (cfg.fast) {
-      if (cfg.aux) k_render_persistent<true, true><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
-      else k_render_persistent<true, false><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
+      if (cfg.aux) SVO_LAUNCH(grid, 128, stream, k_render_persistent<true, true>)(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
+      else SVO_LAUNCH(grid, 128, stream, k_render_persistent<true, false>)(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
     } else {
-      if (cfg.aux) k_render_persistent<false, true><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
-      else k_render_persistent<false, false><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
+      if (cfg.aux) SVO_LAUNCH(grid, 128, stream, k_render_persistent<false, true>)(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
+      else SVO_LAUNCH(grid, 128, stream, k_render_persistent<false, false>)(sc, f, pl, W, H, y0, y1, cfg.tile_counter);
     }
     return cudaGetLastError();
   }
   if (cfg.kernel == 6 && cfg.band_stride == 0) {
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-#define SVO_LAUNCH_BINNED(F, A, B) k_render_tile_binned<F, A, B><<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1)
+#define SVO_LAUNCH_BINNED(F, A, B) SVO_LAUNCH(grid, 128, stream, k_render_tile_binned<F, A, B>)(sc, f, pl, W, H, y0, y1)
     if (cfg.fast) {
       if (cfg.aux) SVO_LAUNCH_BINNED(true, true, false);
       else if (cfg.box) SVO_LAUNCH_BINNED(true, false, true);
@@ -382,7 +390,7 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
   if (cfg.kernel == 4 && !cfg.aux && !cfg.fast && cfg.box && cfg.band_stride == 0) {
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-    k_render_tile_smem<<<grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1);
+    SVO_LAUNCH(grid, 128, stream, k_render_tile_smem)(sc, f, pl, W, H, y0, y1);
     return cudaGetLastError();
   }
   const dim3 block(cfg.kernel == 5 ? 64 : 128);
@@ -392,7 +400,7 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
   const bool small_cta = cfg.kernel == 5;  // experiment: 64-thread CTAs (8x8 pixels)
   const dim3 grid(small_cta ? (W + 7) / 8 : (W + 15) / 16, bands > offset ? ((bands - offset + stride - 1) / stride) * band_ctas : 0);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-#define SVO_LAUNCH_TILE(F, A, B) k_render_tile<F, A, B><<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas)
+#define SVO_LAUNCH_TILE(F, A, B) SVO_LAUNCH(grid, block, stream, k_render_tile<F, A, B>)(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas)
   if (cfg.fast) {
     if (cfg.aux) SVO_LAUNCH_TILE(true, true, false);
     else if (cfg.box) SVO_LAUNCH_TILE(true, false, true);
@@ -411,21 +419,21 @@ cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const
   const dim3 block(128);
   const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-  k_render_stats<<<grid, block, 0, stream>>>(sc, f, pl, W, H, y0, y1, d_counters);
+  SVO_LAUNCH(grid, block, stream, k_render_stats)(sc, f, pl, W, H, y0, y1, d_counters);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fence_signal(const FenceList &fl, cudaStream_t stream) {
-  k_fence_signal<<<1, 32, 0, stream>>>(fl);
+  SVO_LAUNCH(1, 32, stream, k_fence_signal)(fl);
   return cudaGetLastError();
 }
 cudaError_t launch_fence_wait(unsigned int *fence, unsigned int *dead, unsigned int target, cudaStream_t stream) {
-  k_fence_wait<<<1, 1, 0, stream>>>(fence, dead, target);
+  SVO_LAUNCH(1, 1, stream, k_fence_wait)(fence, dead, target);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int blocks, uint32_t *sink, cudaStream_t stream) {
-  k_gather_probe<<<blocks, 256, 0, stream>>>((const uint2 *)buf, words, loads, sink);
+  SVO_LAUNCH(blocks, 256, stream, k_gather_probe)((const uint2 *)buf, words, loads, sink);
   return cudaGetLastError();
 }
 
@@ -436,8 +444,8 @@ cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d
   uint64_t want = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)cfg.sm_count * 16u * 8u;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (cfg.fast) k_cast_stream<true><<<grid, block, 0, stream>>>(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
-  else k_cast_stream<false><<<grid, block, 0, stream>>>(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
+  if (cfg.fast) SVO_LAUNCH(grid, block, stream, k_cast_stream<true>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
+  else SVO_LAUNCH(grid, block, stream, k_cast_stream<false>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
   return cudaGetLastError();
 }
 
@@ -446,14 +454,14 @@ cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FramePa
   const int bw = W >> 2, bh = H >> 2;
   if (bw == 0 || bh == 0) return cudaSuccess;
   const dim3 block(128), grid((bw + 15) / 16, (bh + 7) / 8);
-  if (cfg.fast) k_beam<true><<<grid, block, 0, stream>>>(sc, f, beam, W, H);
-  else k_beam<false><<<grid, block, 0, stream>>>(sc, f, beam, W, H);
+  if (cfg.fast) SVO_LAUNCH(grid, block, stream, k_beam<true>)(sc, f, beam, W, H);
+  else SVO_LAUNCH(grid, block, stream, k_beam<false>)(sc, f, beam, W, H);
   return cudaGetLastError();
 }
 
 cudaError_t launch_math_probe(int fn, const float *x, const float *y, float *out, uint64_t n, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fn, x, y, out, n);
+  SVO_LAUNCH((unsigned)((n + 255) / 256), 256, stream, k_math_probe)(fn, x, y, out, n);
   return cudaGetLastError();
 }
 

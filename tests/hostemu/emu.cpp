@@ -18,29 +18,11 @@
 
 #include "../../svo_raytracer_b200/csrc/svo_trace.cuh"
 #include "../../svo_raytracer_b200/csrc/svo_transcode.h"
+#include "emu_scene.h"
 
 using namespace svo;
 
-struct emu_scene {
-  std::vector<uint8_t> raw;
-  Transcoded t;
-};
-
-static SceneView view_of(const emu_scene *s, const FrameParams *f) {
-  SceneView v;
-  content_box(s->t.leaf_box, s->t.depth_box, f ? f->maxDepth : -1, f ? f->coneDepth : -1, v.box_lo, v.box_hi);
-  v.desc = s->t.desc.data();
-  v.refbase = s->t.refbase.data();
-  v.raw = s->raw.data();
-  v.nbytes = s->raw.size();
-  v.ndesc = (uint32_t)s->t.desc.size();
-  uint32_t w0 = 0;
-  memcpy(&w0, s->raw.data(), std::min<size_t>(4, s->raw.size()));
-  v.first_word_zero = w0 == 0u;
-  v.top = nullptr;
-  v.ntop = 0;
-  return v;
-}
+static SceneView view_of(const emu_scene *s, const FrameParams *f) { return emu_view_of(s, f); }
 
 template <class F>
 static void parallel_rows(int y0, int y1, int nthreads, F fn) {
@@ -208,8 +190,9 @@ struct LaneCast {
 };
 
 // costs[]: 0 head, 1 push, 2 advance, 3 pop, 4 loop tail (re-convergence + back branch), 5 exit on the head/push side (hit),
-//          6 exit on the pop side (miss), 7 per-cast code outside the loop (setup + finish + shading; issued once per warp cast)
-struct Costs { double head, push, adv, pop, tail, exit_hit, exit_miss, outside; };
+//          6 exit on the pop side (miss), 7 per-cast code outside the loop (setup + finish + shading; issued once per warp cast),
+//          8 one refill event of the dynamic-refill what-if, 9 its extra instructions per warp iteration (ballot + test)
+struct Costs { double head, push, adv, pop, tail, exit_hit, exit_miss, outside, refill, refill_iter; };
 
 struct Tally {
   double slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per organisation
@@ -301,7 +284,8 @@ double org_while_while(const Costs &c, const std::vector<const LaneCast *> &lane
 // what-if organisation: `workers` warps share a queue of rays (the bounce casts of a group of tiles); a warp whose idle
 // lanes reach `threshold` leaves the loop, takes rays from the queue (costs `refill` slots: loop exit/entry + Trav::setup
 // for the new lanes; the finished lanes' end states are parked for their owners) and goes on.  Returns issue slots.
-double org_refill(const Costs &c, const std::vector<const LaneCast *> &queue, int workers, int threshold, double refill) {
+double org_refill(const Costs &c, const std::vector<const LaneCast *> &queue, int workers, int threshold) {
+  const double refill = c.refill;
   struct Lane { const LaneCast *lc = nullptr; size_t pos = 0; };
   struct Worker { Lane lane[32]; double t = 0; bool done = false; };
   std::vector<Worker> w((size_t)workers);
@@ -328,7 +312,7 @@ double org_refill(const Costs &c, const std::vector<const LaneCast *> &queue, in
     }
     double s = 0;
     if (active) {
-      s = c.head + c.tail;
+      s = c.head + c.tail + c.refill_iter;
       if (any[OP_PUSH]) s += c.push;
       if (any[OP_EXIT_HIT]) s += c.exit_hit;
       if (any[OP_ADV] || any[OP_POP] || any[OP_EXIT_MISS]) s += c.adv;
@@ -361,7 +345,7 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
   const int tile_h = 32 / tile_w, tw_shift = tile_w == 4 ? 2 : tile_w == 8 ? 3 : tile_w == 16 ? 4 : 5;
   const FrameParams &f = *fp;
   const SceneView sc = view_of(s, fp);
-  Costs c{costs[0], costs[1], costs[2], costs[3], costs[4], costs[5], costs[6], costs[7]};
+  Costs c{costs[0], costs[1], costs[2], costs[3], costs[4], costs[5], costs[6], costs[7], costs[8], costs[9]};
   const int tiles_x = (W + tile_w - 1) / tile_w, tiles_y0 = y0 / tile_h, tiles_y1 = (y1 + tile_h - 1) / tile_h;
   std::vector<Tally> tallies((size_t)std::max(1, nthreads));
   std::atomic<int> next(tiles_y0);
@@ -404,7 +388,7 @@ int emu_simt(const emu_scene *s, const FrameParams *fp, int W, int H, int y0, in
             const int warps = (int)((v.size() + 31) / 32);
             const int workers = std::max(1, warps / kRefillVariants[r][0]);
             // code outside the loop: the shipped kernel pays c.outside per warp cast; here the shading still runs once per 32 rays
-            t.refill[g][r] += org_refill(c, v, workers, kRefillVariants[r][1], 110.0) + c.outside * warps;
+            t.refill[g][r] += org_refill(c, v, workers, kRefillVariants[r][1]) + c.outside * warps;
           }
         }
         pool[g].clear();

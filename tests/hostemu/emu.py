@@ -11,18 +11,17 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.normpath(os.path.join(_HERE, "..", "..", "svo_raytracer_b200", "csrc"))
 _LIB_PATH = os.path.join(_HERE, "libsvo_hostemu.so")
-_SRCS = [os.path.join(_HERE, "emu.cpp"), os.path.join(_HERE, "cuda_host_shim.h"), os.path.join(_CSRC, "svo_trace.cuh"),
-         os.path.join(_CSRC, "detmath.cuh"), os.path.join(_CSRC, "svo_kernels.h"), os.path.join(_CSRC, "svo_transcode.cpp"),
-         os.path.join(_CSRC, "svo_transcode.h")]
+_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
+_SRCS = _CPP + [os.path.join(_HERE, f) for f in ("cuda_host_shim.h", "simt_emu.h", "emu_scene.h")] + \
+    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_transcode.h")]
 CUDA_INCLUDE = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 
 def build(force: bool = False) -> str:
     stale = force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in _SRCS)
     if stale:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall",
-                               "-I" + CUDA_INCLUDE, "-o", _LIB_PATH, os.path.join(_HERE, "emu.cpp"),
-                               os.path.join(_CSRC, "svo_transcode.cpp"), "-lpthread"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unknown-pragmas", "-Wno-maybe-uninitialized",
+                               "-I" + CUDA_INCLUDE, "-o", _LIB_PATH] + _CPP + ["-lpthread"])
     return _LIB_PATH
 
 
@@ -41,6 +40,10 @@ def lib():
         L.emu_render.restype = C.c_int
         L.emu_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_launch_render.restype = C.c_int
+        L.emu_launch_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int]
         L.emu_cast.restype = C.c_int
         L.emu_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
         L.emu_beam.restype = C.c_int
@@ -107,6 +110,26 @@ class Scene:
             return out, {"casts": int(counters[0]), "iters": int(counters[1]), "record_bytes": int(counters[2])}
         return out
 
+    def launch_render(self, frame, width, height, y0=0, y1=None, kernel=0, box=False, aux=True, beam=None, prev_rgba8=None,
+                      band_stride=0, band_offset=0, band_rows=8, ctas=6, nthreads=8, into=None):
+        """The product's launch_render() -- variant dispatch, grid arithmetic, the __global__ kernels with their warp- and
+        block-level collectives -- on the coroutine SIMT emulator (kernels_emu.cpp).  `into`: planes to draw into."""
+        y1 = height if y1 is None else y1
+        if into is not None:
+            out = into
+        else:
+            out = {"rgba8": np.zeros((height, width, 4), np.uint8) if prev_rgba8 is None else np.ascontiguousarray(prev_rgba8, np.uint8).copy(),
+                   "depth": np.zeros((height, width), np.float32), "radiance": np.zeros((height, width, 4), np.float32),
+                   "hit_id": np.zeros((height, width), np.uint32), "iter": np.zeros((height, width), np.uint32),
+                   "primary_t": np.zeros((height, width), np.float32)}
+        if beam is not None:
+            beam = np.ascontiguousarray(beam, dtype=np.float32)
+        rc = lib().emu_launch_render(self._h, C.byref(frame), width, height, y0, y1, kernel, int(box), int(aux), _ptr(beam),
+                                     _ptr(out["rgba8"]), _ptr(out["depth"]), _ptr(out["hit_id"]), _ptr(out["iter"]),
+                                     _ptr(out["primary_t"]), _ptr(out["radiance"]), band_stride, band_offset, band_rows, ctas, nthreads)
+        assert rc == 0, rc
+        return out
+
     def cast(self, rays, max_depth=13, nthreads=8):
         from oracle import oracle as O
         rays = np.ascontiguousarray(rays, dtype=O.RAY_DTYPE)
@@ -118,7 +141,9 @@ class Scene:
         """The SIMT divergence model of emu.cpp: issue slots of the traversal under several loop organisations."""
         y1 = height if y1 is None else y1
         costs = np.ascontiguousarray(costs, dtype=np.float64)
-        assert costs.size == 8
+        if costs.size == 8:
+            costs = np.concatenate([costs, [110.0, 0.0]])  # refill event, extra instructions per warp iteration of the refill what-if
+        assert costs.size == 10
         out = np.zeros(48, np.float64)
         lib().emu_simt(self._h, C.byref(frame), width, height, y0, y1, int(box), _ptr(costs), _ptr(out), nthreads, tile_w)
         names = ("if_if", "while_while", "ww_1_1", "ww_inf_1", "ww_1_inf", "ww_4_2")

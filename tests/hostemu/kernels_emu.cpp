@@ -1,0 +1,53 @@
+// kernels_emu.cpp -- TEST INFRASTRUCTURE: svo_kernels.cu (the __global__ functions and their launchers) compiled by
+// g++ and run on the coroutine SIMT emulator.  launch_render() below is the product's own launcher -- same variant
+// dispatch, same grid arithmetic -- with <<<>>> routed to simt::run_grid.  Nothing here ships.
+#include "cuda_host_shim.h"
+#include "simt_emu.h"
+
+#define SVO_HOST_EMU 1
+#define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
+#define cudaGetLastError() cudaSuccess
+#include "../../svo_raytracer_b200/csrc/svo_kernels.cu"
+#undef cudaMemsetAsync
+#undef cudaGetLastError
+
+#include <algorithm>
+#include <string>
+
+#include "emu_scene.h"
+
+using namespace svo;
+
+extern "C" {
+
+// svo_render_rows through the product's launch_render on the emulator.  kernel = SVO_OPT_KERNEL, ctas = CTAs of the
+// persistent variant (sm_count * ctas_per_sm on the device).
+int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, int y0, int y1, int kernel, int box, int aux, const float *beam,
+                      uint8_t *rgba8, float *depth, uint32_t *hit_id, uint32_t *iter, float *primary_t, float *radiance, int band_stride,
+                      int band_offset, int band_rows, int ctas, int nthreads) {
+  const SceneView sc = emu_view_of(s, f);
+  Planes pl;
+  pl.rgba8 = (uchar4 *)rgba8;
+  pl.depth = depth;
+  pl.beam = beam;
+  pl.hit_id = hit_id;
+  pl.iter = iter;
+  pl.primary_t = primary_t;
+  pl.radiance = (float4 *)radiance;
+  unsigned int tile_counter = 0;
+  LaunchCfg cfg;
+  cfg.fast = false;
+  cfg.aux = aux != 0;
+  cfg.box = box != 0 && !aux && f->renderMode != 1;  // box_allowed() of svo_capi.cu
+  cfg.kernel = kernel;
+  cfg.sm_count = ctas;
+  cfg.ctas_per_sm = 1;
+  cfg.band_stride = band_stride;
+  cfg.band_offset = band_offset;
+  cfg.band_ctas = band_rows / 8;
+  cfg.tile_counter = &tile_counter;
+  simt::g_os_threads = kernel == 1 ? 1 : nthreads;  // the persistent kernel's queue is consumed by whichever block runs
+  return (int)launch_render(cfg, sc, *f, pl, W, H, y0, y1, nullptr);
+}
+
+}  // extern "C"

@@ -214,3 +214,35 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
     assert rb["casts"] == r["casts"] and rb["iters"] <= r["iters"]  # the content box only ever removes iterations
     # the warp tile the kernel uses (8x4) is what the model replays by default
     assert scene128.simt(f, W, H, costs, box=False, tile_w=8)["if_if"] == r["if_if"]
+
+
+KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem"}
+
+
+@pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))
+def test_global_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kernel):
+    """The __global__ functions of svo_kernels.cu and the product's launch_render() (variant dispatch, grid arithmetic,
+    band interleaving) on the coroutine SIMT emulator: warp ballots / shuffles / atomics of the persistent kernel, the
+    shared-memory counting sort and block-wide votes of the binned kernel, the shared-memory descriptor prefix --
+    every plane bit-exact against the oracle, image sizes that do not divide into CTA tiles, uneven row bands."""
+    W, H = 200, 120
+    for cam, mode in (("B", 0), ("C", 2), ("A", 0)) if kernel != 1 else (("B", 0),):
+        pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+        f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=mode, max_depth=7, casts=3 if cam == "A" else 2)
+        want, _ = oracle.render(terrain128, f, W, H, nthreads=8)
+        if kernel != 4:  # variant 4 exists only as the production instance (no validation planes)
+            got = None
+            for y0, y1 in ((0, 37), (37, 38), (38, H)):
+                got = scene128.launch_render(f, W, H, y0, y1, kernel=kernel, aux=True, into=got)
+            _assert_planes_equal(got, want, "kernel %d cam %s aux" % (kernel, cam))
+        got = scene128.launch_render(f, W, H, kernel=kernel, aux=False, box=True)
+        _assert_planes_equal(got, want, "kernel %d cam %s production" % (kernel, cam), planes=("rgba8", "depth"))
+    if kernel in (0, 5):  # interleaved bands of the multi-GPU tile partition, one launch per part
+        pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+        f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=7)
+        want, _ = oracle.render(terrain128, f, W, H, nthreads=8)
+        for parts, rows in ((3, 8), (2, 16)):
+            got = None
+            for part in range(parts):
+                got = scene128.launch_render(f, W, H, kernel=kernel, aux=True, band_stride=parts, band_offset=part, band_rows=rows, into=got)
+            _assert_planes_equal(got, want, "kernel %d interleaved %d x %d rows" % (kernel, parts, rows))
