@@ -202,6 +202,141 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
 }
 
 // ---------------------------------------------------------------------------
+// Kernel variants 7 / 8: tile kernel for the primary rays + warp-local lane refill for every later cast.
+// The divergence model (tools/simt_model.py) puts the bounce casts of the bench workload at ~29 % lane utilisation,
+// mostly trip-count divergence: a warp waits for its longest ray.  Here a warp owns PIX 8x4 tiles (PIX pixels per
+// thread).  Primary rays run exactly as in variant 0, one tile after the other (they are coherent).  The rays of
+// every later cast go into a queue in the warp's own shared memory; lanes take rays from it, and as soon as
+// kRefillIdle lanes have finished their ray the warp leaves the traversal loop, parks the end states (HitState, 28
+// bytes, in the ray's own queue slot) and hands those lanes the next rays.  When the queue is dry every thread
+// picks up the end states of its own pixels and shades them at full width.  Unlike variant 1 nothing but
+// Trav::setup runs at partial lane utilisation, and unlike variant 6 nothing synchronises wider than a warp.
+// ---------------------------------------------------------------------------
+constexpr int kRefillIdle = 8;   // lanes that must be free before the warp leaves the traversal loop for a refill
+constexpr int kRefillBatch = 8;  // loop iterations between two votes
+
+template <bool FAST, bool AUX, bool BOX, int PIX>
+__global__ void __launch_bounds__(128, 8) k_render_tile_refill(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  constexpr int TX = 2, TY = PIX / 2;        // tiles of one warp: 2 x TY (PIX = 2: 16x4 pixels, PIX = 4: 16x8 pixels)
+  constexpr int SLOTS = PIX * 32;
+  __shared__ uint32_t s_q[4][7][SLOTS];      // per warp: ray (origin, dir, cone flag) on the way in, HitState on the way out
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint32_t(*q)[SLOTS] = s_q[warp];
+  const int wx = (blockIdx.x * 2 + (warp & 1)) * (TX * 8), wy = y0 + (blockIdx.y * 2 + (warp >> 1)) * (TY * 4);
+
+  // Pixel states live in local memory between phases (indexed dynamically: the code of a phase exists once, not PIX
+  // times -- the unrolled kernel was 13 k instructions); the pixel being worked on is in registers.
+  Pixel P[PIX];
+  unsigned valid = 0, wants = 0;  // bit k: pixel k is inside the image / wants another cast
+  uint2 stk[kMaxScale + 1];
+  // ---- primary casts, tile by tile, as in variant 0 ----
+#pragma unroll 1
+  for (int k = 0; k < PIX; k++) {
+    const int x = wx + (k % TX) * 8 + (int)(lane & 7u), y = wy + (k / TX) * 4 + (int)(lane >> 3);
+    if (x < W && y < y1) {
+      valid |= 1u << k;
+      Pixel cur;
+      bool more = pixel_begin(f, pl, W, H, x, y, cur);
+      if (more) {
+        Trav<FAST, false, BOX> T;
+        T.setup(sc, cur.origin, cur.dir, f.maxDepth, cur.cone, f.coneDepth, nullptr);
+        const HitState hs = T.export_hit((T.outside_box() || T.nan_ray(nullptr)) ? TRAV_MISS : T.run(sc, stk, nullptr));
+        more = pixel_finish_cast(sc, f, cur, hs);
+      }
+      if (more) wants |= 1u << k;
+      P[k] = cur;
+    }
+  }
+  // ---- later casts: one round per cast index, rays of the warp's PIX tiles in one queue ----
+  for (;;) {
+    unsigned count = 0;
+    unsigned slots = 0;  // byte k: queue slot of pixel k's ray
+#pragma unroll 1
+    for (int k = 0; k < PIX; k++) {
+      const bool w = ((wants >> k) & 1u) != 0u;
+      const unsigned m = __ballot_sync(0xffffffffu, w);
+      const unsigned s_ = count + __popc(m & lt_mask);
+      count += __popc(m);
+      if (w) {
+        slots |= s_ << (8 * k);
+        q[0][s_] = __float_as_uint(P[k].origin.x); q[1][s_] = __float_as_uint(P[k].origin.y); q[2][s_] = __float_as_uint(P[k].origin.z);
+        q[3][s_] = __float_as_uint(P[k].dir.x); q[4][s_] = __float_as_uint(P[k].dir.y); q[5][s_] = __float_as_uint(P[k].dir.z);
+        q[6][s_] = P[k].cone ? 1u : 0u;
+      }
+    }
+    if (count == 0) break;
+    __syncwarp();
+    unsigned head = 0, mine = 0;
+    int busy = 0;
+    Trav<FAST, false, BOX> T;
+    for (;;) {
+      // hand rays to idle lanes (a ray that ends before the loop -- outside the content box, NaN -- frees its lane at once)
+      unsigned idle = __ballot_sync(0xffffffffu, !busy);
+      while (idle != 0u && head < count) {
+        const unsigned rank = __popc(idle & lt_mask);
+        if (!busy && head + rank < count) {
+          mine = head + rank;
+          T.setup(sc, mk3(__uint_as_float(q[0][mine]), __uint_as_float(q[1][mine]), __uint_as_float(q[2][mine])),
+                  mk3(__uint_as_float(q[3][mine]), __uint_as_float(q[4][mine]), __uint_as_float(q[5][mine])), f.maxDepth, q[6][mine] != 0u,
+                  f.coneDepth, nullptr);
+          if (T.outside_box() || T.nan_ray(nullptr)) {
+            const HitState r = T.export_hit(TRAV_MISS);
+            q[0][mine] = r.pidx; q[1][mine] = r.meta; q[2][mine] = r.ipx; q[3][mine] = r.ipy; q[4][mine] = r.ipz;
+            q[5][mine] = __float_as_uint(r.t_min); q[6][mine] = r.iter;
+          } else {
+            busy = 1;
+          }
+        }
+        head += min(count - head, (unsigned)__popc(idle));
+        idle = __ballot_sync(0xffffffffu, !busy);
+      }
+      const int busy0 = __popc(__ballot_sync(0xffffffffu, busy));
+      if (busy0 == 0) break;  // queue dry and every ray finished
+      // traverse until enough lanes are free to make a refill worth its cost (or, with the queue dry, until all are
+      // done).  The warp votes once per kRefillBatch iterations: a vote per iteration costs 13 instructions on top of
+      // the ~100 of the iteration, a lane that finishes inside a batch idles for < kRefillBatch iterations.
+      const int limit = head < count ? max(busy0 - kRefillIdle, 0) : 0;
+      for (;;) {
+        if (busy) {
+          int status = TRAV_CONTINUE;
+#pragma unroll 1
+          for (int i = 0; i < kRefillBatch && status == TRAV_CONTINUE; i++) status = T.step(sc, stk, nullptr);
+          if (status != TRAV_CONTINUE) {
+            busy = 0;
+            const HitState r = T.export_hit(status);
+            q[0][mine] = r.pidx; q[1][mine] = r.meta; q[2][mine] = r.ipx; q[3][mine] = r.ipy; q[4][mine] = r.ipz;
+            q[5][mine] = __float_as_uint(r.t_min); q[6][mine] = r.iter;
+          }
+        }
+        if (__popc(__ballot_sync(0xffffffffu, busy)) <= limit) break;
+      }
+    }
+    __syncwarp();
+    // ---- every thread shades its own pixels from the parked end states ----
+#pragma unroll 1
+    for (int k = 0; k < PIX; k++) {
+      if ((wants >> k) & 1u) {
+        const unsigned s_ = (slots >> (8 * k)) & 0xFFu;
+        HitState hs;
+        hs.pidx = q[0][s_]; hs.meta = q[1][s_]; hs.ipx = q[2][s_]; hs.ipy = q[3][s_]; hs.ipz = q[4][s_];
+        hs.t_min = __uint_as_float(q[5][s_]); hs.iter = q[6][s_];
+        Pixel cur = P[k];
+        if (!pixel_finish_cast(sc, f, cur, hs)) wants &= ~(1u << k);
+        P[k] = cur;
+      }
+    }
+    __syncwarp();  // the slots are rewritten by the next round
+  }
+#pragma unroll 1
+  for (int k = 0; k < PIX; k++)
+    if ((valid >> k) & 1u) {
+      Pixel cur = P[k];
+      pixel_store<AUX>(sc, f, pl, W, cur);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Kernel variant 4 (experiment): variant 0 with the upper octree levels staged in shared memory.  Every CTA
 // copies the first kTopDescs descriptors (breadth-first array: levels 0..3 and part of 4) before tracing.
 // ---------------------------------------------------------------------------
@@ -385,6 +520,27 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
       else SVO_LAUNCH_BINNED(false, false, false);
     }
 #undef SVO_LAUNCH_BINNED
+    return cudaGetLastError();
+  }
+  if ((cfg.kernel == 7 || cfg.kernel == 8) && cfg.band_stride == 0) {
+    // a CTA covers 32 x 16 pixels (variant 7: 4 pixels per thread) or 32 x 8 (variant 8: 2 per thread)
+    const dim3 grid((W + 31) / 32, cfg.kernel == 7 ? (y1 - y0 + 15) / 16 : (y1 - y0 + 7) / 8);
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+#define SVO_LAUNCH_REFILL(F, A, B)                                                                                    \
+  do {                                                                                                                \
+    if (cfg.kernel == 7) SVO_LAUNCH(grid, 128, stream, k_render_tile_refill<F, A, B, 4>)(sc, f, pl, W, H, y0, y1);     \
+    else SVO_LAUNCH(grid, 128, stream, k_render_tile_refill<F, A, B, 2>)(sc, f, pl, W, H, y0, y1);                     \
+  } while (0)
+    if (cfg.fast) {
+      if (cfg.aux) SVO_LAUNCH_REFILL(true, true, false);
+      else if (cfg.box) SVO_LAUNCH_REFILL(true, false, true);
+      else SVO_LAUNCH_REFILL(true, false, false);
+    } else {
+      if (cfg.aux) SVO_LAUNCH_REFILL(false, true, false);
+      else if (cfg.box) SVO_LAUNCH_REFILL(false, false, true);
+      else SVO_LAUNCH_REFILL(false, false, false);
+    }
+#undef SVO_LAUNCH_REFILL
     return cudaGetLastError();
   }
   if (cfg.kernel == 4 && !cfg.aux && !cfg.fast && cfg.box && cfg.band_stride == 0) {

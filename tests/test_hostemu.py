@@ -148,6 +148,11 @@ def test_device_source_random_worlds_random_cameras(svo, oracle, seed):
         if kw["render_mode"] != 1:
             _assert_planes_equal(sc.render(f, W, H, box=True, aux=False), want, "box seed %d trial %d %s" % (seed, trial, kw),
                                  planes=("rgba8", "depth"))
+        # the __global__ kernels with warp-level protocols, on the SIMT emulator: lane refill (7, 8), octant binning (6)
+        for kernel in (7, 8, 6):
+            _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=True), want, "kernel %d seed %d trial %d %s" % (kernel, seed, trial, kw))
+            _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=False, box=True), want,
+                                 "kernel %d box seed %d trial %d %s" % (kernel, seed, trial, kw), planes=("rgba8", "depth"))
     sc.close()
 
 
@@ -174,6 +179,7 @@ def test_device_source_iteration_cap_boundary(oracle):
             wantp, _ = oracle.render(nodes, f, W, H, nthreads=4)
             _assert_planes_equal(sc.render(f, W, H, path=E.PATH_RUN), wantp, "cap run %s mode %d" % (x0, mode))
             _assert_planes_equal(sc.render(f, W, H, path=E.PATH_STEP), wantp, "cap step %s mode %d" % (x0, mode))
+            _assert_planes_equal(sc.launch_render(f, W, H, kernel=7, aux=True), wantp, "cap refill kernel %s mode %d" % (x0, mode))
             seen |= set(np.unique(wantp["iter"]).tolist())
     assert {1497, 1500, 1501} <= seen
     sc.close()
@@ -216,7 +222,7 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
     assert scene128.simt(f, W, H, costs, box=False, tile_w=8)["if_if"] == r["if_if"]
 
 
-KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem"}
+KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2"}
 
 
 @pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))

@@ -1,0 +1,51 @@
+"""GPU parity of kernel variants 7 / 8 (tile kernel + warp-local lane refill for the casts after the first), through
+the C ABI against the oracle.  The same kernels run in the CPU suite on the SIMT emulator (test_hostemu.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PLANES = ("rgba8", "depth", "radiance", "hit_id", "iter", "primary_t")
+
+
+def _planes(c):
+    return {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(), "hit_id": c.read_hit_id(),
+            "iter": c.read_iter(), "primary_t": c.read_primary_t()}
+
+
+def _assert_equal(got, want, what, planes=PLANES):
+    for k in planes:
+        g, w = got[k], want[k]
+        same = ((g.view(np.uint32) == w.view(np.uint32)) | (np.isnan(g) & np.isnan(w))) if g.dtype.kind == "f" else (g == w)
+        assert same.all(), "%s: plane %s differs in %d of %d elements" % (what, k, int((~same).sum()), same.size)
+
+
+@pytest.mark.parametrize("kernel", [7, 8], ids=["refill4", "refill2"])
+def test_refill_kernels_bit_exact(svo, oracle, terrain512, terrain128, kernel):
+    with svo.SvoContext(640, 360) as c:
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
+        c.upload(terrain512)
+        for cam in ("A", "B", "C"):
+            for mode in (0, 2, 1, 3, 4):
+                pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+                want, _ = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=3, render_mode=mode), 640, 360, nthreads=8)
+                c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+                c.render(svo.camera_frame(cam, frame_number=3, render_mode=mode))
+                _assert_equal(_planes(c), want, "kernel %d cam %s mode %d" % (kernel, cam, mode))
+                c.set_option(svo._lib.OPT_AUX_PLANES, 0)  # production instance: content box on
+                c.render(svo.camera_frame(cam, frame_number=3, render_mode=mode))
+                _assert_equal({"rgba8": c.read_color_rgba8(), "depth": c.read_depth()}, want, "kernel %d cam %s mode %d production" % (kernel, cam, mode),
+                              planes=("rgba8", "depth"))
+    W, H = 200, 120  # not a multiple of the warp's 16x8 / 16x4 pixels; multi-chunk tree; deeper paths; row bands
+    with svo.SvoContext(W, H) as c:
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
+        c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+        c.upload(terrain128)
+        for cam, casts in (("A", 2), ("B", 4), ("C", 3)):
+            pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+            kw = dict(frame_number=1, render_mode=0, max_depth=7, casts=casts)
+            want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, **kw), W, H, nthreads=8)
+            f = svo.camera_frame(cam, **kw)
+            for y0, y1 in ((0, 37), (37, 38), (38, H)):
+                c.render(f, y0, y1)
+            _assert_equal(_planes(c), want, "kernel %d terrain128 cam %s casts %d" % (kernel, cam, casts))
