@@ -202,6 +202,32 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
 }
 
 // ---------------------------------------------------------------------------
+// Kernel variants 9..12: variant 0 with one thing changed each (separately rounded arithmetic only).
+//   9  SmemStack: the parent stack in shared memory (14 levels x 128 threads x 8 B = 14 KB per CTA) instead of local
+//      memory -- stack accesses cannot miss and stop competing with descriptors for L1; frames with maxDepth <= 14
+//  10  WideStack: 16-byte stack entries carrying the parent's descriptor -- a POP is one LDL.128 instead of LDL.64
+//      followed by a dependent descriptor load
+//  11 / 12  __launch_bounds__(128, 7) / (128, 6): 72 / 80 registers per thread instead of 64
+// ---------------------------------------------------------------------------
+template <bool AUX, bool BOX, int STACK>
+__device__ __forceinline__ void tile_body(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1) {
+  __shared__ uint2 s_stack[STACK == 2 ? kSmemStackLevels : 1][kSmemStackStride];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  if (x >= W || y >= y1) return;
+  shade_pixel<false, AUX, false, BOX, false, STACK>(sc, f, pl, W, H, x, y, nullptr, &s_stack[0][threadIdx.x]);
+}
+template <bool AUX, bool BOX, int STACK>
+__global__ void __launch_bounds__(128, 8) k_render_tile_stack(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  tile_body<AUX, BOX, STACK>(sc, f, pl, W, H, y0, y1);
+}
+template <bool AUX, bool BOX, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_render_tile_regs(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  tile_body<AUX, BOX, 0>(sc, f, pl, W, H, y0, y1);
+}
+
+// ---------------------------------------------------------------------------
 // Kernel variants 7 / 8: tile kernel for the primary rays + warp-local lane refill for every later cast.
 // The divergence model (tools/simt_model.py) puts the bounce casts of the bench workload at ~29 % lane utilisation,
 // mostly trip-count divergence: a warp waits for its longest ray.  Here a warp owns PIX 8x4 tiles (PIX pixels per
@@ -520,6 +546,22 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
       else SVO_LAUNCH_BINNED(false, false, false);
     }
 #undef SVO_LAUNCH_BINNED
+    return cudaGetLastError();
+  }
+  if (cfg.kernel >= 9 && cfg.kernel <= 12 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || f.maxDepth <= kSmemStackLevels)) {
+    const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+#define SVO_LAUNCH_X(A, B)                                                                                           \
+  do {                                                                                                               \
+    if (cfg.kernel == 9) SVO_LAUNCH(grid, 128, stream, k_render_tile_stack<A, B, 2>)(sc, f, pl, W, H, y0, y1);        \
+    else if (cfg.kernel == 10) SVO_LAUNCH(grid, 128, stream, k_render_tile_stack<A, B, 1>)(sc, f, pl, W, H, y0, y1);  \
+    else if (cfg.kernel == 11) SVO_LAUNCH(grid, 128, stream, k_render_tile_regs<A, B, 7>)(sc, f, pl, W, H, y0, y1);   \
+    else SVO_LAUNCH(grid, 128, stream, k_render_tile_regs<A, B, 6>)(sc, f, pl, W, H, y0, y1);                         \
+  } while (0)
+    if (cfg.aux) SVO_LAUNCH_X(true, false);
+    else if (cfg.box) SVO_LAUNCH_X(false, true);
+    else SVO_LAUNCH_X(false, false);
+#undef SVO_LAUNCH_X
     return cudaGetLastError();
   }
   if ((cfg.kernel == 7 || cfg.kernel == 8) && cfg.band_stride == 0) {

@@ -193,6 +193,44 @@ SVO_DI bool finish_hit(const SceneView &sc, const HitState hs, CastRes &res, uin
   return true;  // :431 (scale < MAX_SCALE && t_min <= t_max both hold at either break)
 }
 
+// The parent stack (octstack, svotrace.comp:199-208) behind a small policy, so that where and how wide it is stored
+// can be varied without touching the traversal: a per-thread array of 8-byte (parent index, t_max) entries in local
+// memory (default); WideStack: 16-byte entries that also carry the parent's descriptor, so a POP is one load instead
+// of a load followed by a dependent descriptor fetch; SmemStack: the default entries in shared memory, one column
+// per thread (conflict-free), for frames whose maxDepth keeps the stack within kSmemStackLevels entries.
+struct WideStack { uint4 *p; };
+constexpr int kSmemStackLevels = 14, kSmemStackStride = 128;  // scales 9..22 (maxDepth <= 14); CTAs of 128 threads
+struct SmemStack { uint2 *p; };                               // &smem[0][threadIdx.x]; entry of scale s at p[(s - 9) * 128]
+SVO_DI void stk_store(uint2 *s, int scale, uint32_t pidx, float t_max, uint2) { s[scale] = make_uint2(pidx, __float_as_uint(t_max)); }
+SVO_DI void stk_store(WideStack s, int scale, uint32_t pidx, float t_max, uint2 pd) {
+  s.p[scale] = make_uint4(pidx, __float_as_uint(t_max), pd.x, pd.y);
+}
+SVO_DI void stk_store(SmemStack s, int scale, uint32_t pidx, float t_max, uint2) {
+  s.p[(scale - (kMaxScale - kSmemStackLevels)) * kSmemStackStride] = make_uint2(pidx, __float_as_uint(t_max));
+}
+// returns the popped parent's descriptor; FETCH reads it from the descriptor array where the stack does not carry it
+template <class FETCH>
+SVO_DI uint2 stk_load(const uint2 *s, int scale, uint32_t &pidx, float &t_max, const SceneView &sc) {
+  const uint2 se = s[scale];
+  pidx = se.x;
+  t_max = __uint_as_float(se.y);
+  return FETCH::fetch(sc, pidx);
+}
+template <class FETCH>
+SVO_DI uint2 stk_load(WideStack s, int scale, uint32_t &pidx, float &t_max, const SceneView &) {
+  const uint4 se = s.p[scale];
+  pidx = se.x;
+  t_max = __uint_as_float(se.y);
+  return make_uint2(se.z, se.w);
+}
+template <class FETCH>
+SVO_DI uint2 stk_load(SmemStack s, int scale, uint32_t &pidx, float &t_max, const SceneView &sc) {
+  const uint2 se = s.p[(scale - (kMaxScale - kSmemStackLevels)) * kSmemStackStride];
+  pidx = se.x;
+  t_max = __uint_as_float(se.y);
+  return FETCH::fetch(sc, pidx);
+}
+
 // One intersectOctree call (svotrace.comp:211-432) as a resumable state machine.
 // BOX: also use the frame's content box (SceneView::box_*): a cast whose ray never enters the box, or has left
 // it, cannot hit anything and is ended as a miss at once.  Only the iteration count of a MISSING cast differs
@@ -317,7 +355,7 @@ struct Trav {
     if (t_min <= tv_max) {                       /* :310 */                                                          \
       if ((m & 0x01000000u) == 0u) { EXIT(TRAV_HIT); } /* child.cp == 0 (:311-313) */                                \
       if (tc_max < h) { /* PUSH :316-319 */                                                                          \
-        stk[scale] = make_uint2(pidx, __float_as_uint(t_max));                                                       \
+        stk_store(stk, scale, pidx, t_max, pd);                                                                      \
       }                                                                                                              \
       h = tc_max;                                                                                                    \
       /* descriptors of the interior siblings below: bits [24, 24+cs) -- the funnel shift leaves exactly those */    \
@@ -374,10 +412,7 @@ struct Trav {
     scale = (int)find_msb(differing_bits); /* findMSB */                                                             \
     if (scale >= kMaxScale) { EXIT(TRAV_MISS); } /* left the cube: the loop condition fails (:262) */                \
     scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);                                         \
-    const uint2 se = stk[scale];                                                                                     \
-    pidx = se.x;                                                                                                     \
-    t_max = __uint_as_float(se.y);                                                                                   \
-    pd = fetch(sc, pidx);                                                                                            \
+    pd = stk_load<Trav>(stk, scale, pidx, t_max, sc);                                                                \
     const uint32_t shx = __float_as_uint(px) >> scale;                                                               \
     const uint32_t shy = __float_as_uint(py) >> scale;                                                               \
     const uint32_t shz = __float_as_uint(pz) >> scale;                                                               \
@@ -438,15 +473,21 @@ struct Trav {
   }
 };
 
-// intersectOctree run to completion.
-template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
-__device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
-                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr, bool attrs = true) {
-  uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
+// intersectOctree run to completion on the caller's stack.
+template <bool FAST, bool STATS, bool BOX, bool TOP, class Stk>
+__device__ __forceinline__ bool cast_ray_on(Stk stk, const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
+                                            int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs, bool attrs) {
   Trav<FAST, STATS, BOX, TOP> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
   if (T.outside_box() || T.nan_ray(rs)) return T.finish(sc, TRAV_MISS, res, loops, attrs);  // no iteration can change anything
   return T.finish(sc, T.run(sc, stk, rs), res, loops, attrs);
+}
+// ... on the default stack
+template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
+__device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
+                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr, bool attrs = true) {
+  uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
+  return cast_ray_on<FAST, STATS, BOX, TOP>(stk, sc, o, d, maxDepth, coneTrace, coneDepth, res, loops, rs, attrs);
 }
 
 SVO_DI void matcolor_table(uint32_t value, vec3 &mc) {  // :514-522, :578-586
@@ -690,17 +731,30 @@ SVO_DI void pixel_store(const SceneView &sc, const FrameParams &f, const Planes 
   }
 }
 
-// main (svotrace.comp:649-729) for pixel (x, y), run to completion
-template <bool FAST, bool AUX, bool STATS = false, bool BOX = false, bool TOP = false>
+// main (svotrace.comp:649-729) for pixel (x, y), run to completion.  STACK: 0 default, 1 WideStack, 2 SmemStack (`smem_stack` =
+// the thread's column of the CTA's shared-memory stack).
+template <bool FAST, bool AUX, bool STATS = false, bool BOX = false, bool TOP = false, int STACK = 0>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
-                                            int x, int y, RayStats *rs = nullptr) {
+                                            int x, int y, RayStats *rs = nullptr, uint2 *smem_stack = nullptr) {
   Pixel P;
   if (pixel_begin(f, pl, W, H, x, y, P)) {
     bool more;
     do {
       uint32_t loops = 0;
       const bool attrs = cast_needs_attrs(f, P);
-      const bool hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+      bool hit;
+      if (STACK == 1) {
+        uint4 wide[kMaxScale + 1];
+        WideStack ws;
+        ws.p = wide;
+        hit = cast_ray_on<FAST, STATS, BOX, TOP>(ws, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+      } else if (STACK == 2) {
+        SmemStack ss;
+        ss.p = smem_stack;
+        hit = cast_ray_on<FAST, STATS, BOX, TOP>(ss, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+      } else {
+        hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+      }
       if (!attrs && hit && f.renderMode == 0) {
         pixel_after_last_hit(P);
         more = false;

@@ -149,7 +149,7 @@ def test_device_source_random_worlds_random_cameras(svo, oracle, seed):
             _assert_planes_equal(sc.render(f, W, H, box=True, aux=False), want, "box seed %d trial %d %s" % (seed, trial, kw),
                                  planes=("rgba8", "depth"))
         # the __global__ kernels with warp-level protocols, on the SIMT emulator: lane refill (7, 8), octant binning (6)
-        for kernel in (7, 8, 6):
+        for kernel in (7, 8, 6, 9, 10):
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=True), want, "kernel %d seed %d trial %d %s" % (kernel, seed, trial, kw))
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=False, box=True), want,
                                  "kernel %d box seed %d trial %d %s" % (kernel, seed, trial, kw), planes=("rgba8", "depth"))
@@ -222,7 +222,8 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
     assert scene128.simt(f, W, H, costs, box=False, tile_w=8)["if_if"] == r["if_if"]
 
 
-KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2"}
+KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
+              11: "regs72"}
 
 
 @pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))

@@ -1,5 +1,5 @@
-"""GPU parity of kernel variants 7 / 8 (tile kernel + warp-local lane refill for the casts after the first), through
-the C ABI against the oracle.  The same kernels run in the CPU suite on the SIMT emulator (test_hostemu.py)."""
+"""GPU parity of kernel variants 7 / 8 (tile kernel + warp-local lane refill for the casts after the first) and 9..12 (parent
+stack in shared memory, 16-byte stack entries, 72 / 80 registers per thread), through the C ABI against the oracle.  The same kernels run in the CPU suite on the SIMT emulator (test_hostemu.py)."""
 import numpy as np
 import pytest
 
@@ -20,8 +20,8 @@ def _assert_equal(got, want, what, planes=PLANES):
         assert same.all(), "%s: plane %s differs in %d of %d elements" % (what, k, int((~same).sum()), same.size)
 
 
-@pytest.mark.parametrize("kernel", [7, 8], ids=["refill4", "refill2"])
-def test_refill_kernels_bit_exact(svo, oracle, terrain512, terrain128, kernel):
+@pytest.mark.parametrize("kernel", [7, 8, 9, 10, 11, 12], ids=["refill4", "refill2", "smemstack", "widestack", "regs72", "regs80"])
+def test_kernel_variants_bit_exact(svo, oracle, terrain512, terrain128, kernel):
     with svo.SvoContext(640, 360) as c:
         c.set_option(svo._lib.OPT_KERNEL, kernel)
         c.upload(terrain512)
