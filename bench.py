@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=int(os.environ.get("SVO_BENCH_SIZE", "8192")), help="world edge in voxels")
     ap.add_argument("--fast-math", type=int, default=0, help="1: fma-contracted kernels (not bit-exact)")
-    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=10, help="SVO_OPT_KERNEL (10 = the library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--camera", default="cycle", choices=["cycle", "A", "B", "C"], help="camera pose per step (default: A, B, C cycled)")
@@ -429,12 +429,12 @@ def main():
     # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (dram__bytes_read.sum +
     # dram__bytes_write.sum, mean of the three camera frames), profiles/r01_tile_full.json
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_tile_full.json")
-    if os.path.exists(tpath) and a.size == 8192 and a.kernel == 0 and world_size == 1 and (W, H, CASTS, MODE) == (1920, 1080, 2, 0):
+    tpath = os.path.join(ROOT, "profiles", {0: "r01_tile_full.json", 10: "r01_tile_wide_full.json"}.get(a.kernel, "none"))
+    if os.path.exists(tpath) and a.size == 8192 and world_size == 1 and (W, H, CASTS, MODE) == (1920, 1080, 2, 0):
         caps = json.load(open(tpath))
         traffic = float(np.mean([c["dram_traffic_MB"] for c in caps])) * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "k_render_persistent" if a.kernel == 1 else "k_render_tile", "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src, "kernel": {1: "k_render_persistent", 10: "k_render_tile_stack<wide>"}.get(a.kernel, "k_render_tile"), "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": launch_ms, "gather": gather,
                 "note": "the kernel is instruction-issue bound, not memory bound (ncu: issue slots 73 %, ALU pipe 74 %, DRAM 5 %): "
                         "upload-time transcoding removed the per-iteration record fetch the algorithmic-byte count assumes"}

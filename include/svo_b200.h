@@ -81,10 +81,12 @@ enum svo_option {
   SVO_OPT_AUX_PLANES = 1,     /* 0/1: also write planes 3..6 (validation outputs); default 0 */
   SVO_OPT_FAST_MATH = 2,      /* 0: separately rounded arithmetic = the --fmad=false validation semantics (default, the bit-exact
                                * contract); 1: t arithmetic contracted into FFMA (not bit-exact, measured slower) */
-  SVO_OPT_KERNEL = 3,         /* kernel variant: 0 tile kernel (default, fastest), 1 persistent megakernel,
-                               * 2 wavefront, 4 tile + shared-memory upper levels, 5 64-thread CTAs, 6 tile + per-CTA octant binning,
-                               * 7 / 8 tile + warp-local lane refill for bounce rays (4 / 2 pixels per thread), 9 parent stack in shared memory,
-                               * 10 16-byte stack entries carrying the descriptor, 11 / 12 72 / 80 registers per thread */
+  SVO_OPT_KERNEL = 3,         /* kernel variant.  10 (default, fastest): tile kernel, one thread per pixel, 16-byte
+                               * stack entries that carry the parent's descriptor; 0: the same with 8-byte entries (also what
+                               * svo_render_interleaved and SVO_OPT_FAST_MATH run); 1 persistent megakernel, 2 wavefront, 4 tile +
+                               * shared-memory upper levels, 5 64-thread CTAs, 6 tile + per-CTA octant binning, 7 / 8 tile +
+                               * warp-local lane refill for bounce rays (4 / 2 pixels per thread), 9 parent stack in shared
+                               * memory, 11 / 12 72 / 80 registers per thread.  All bit-exact; the others are measured ablations */
   SVO_OPT_L2_PERSIST = 4,     /* 0/1: L2 access-policy window (persisting) over the upper octree levels, applied at the next
                                * upload; default 0 (measured: no effect, the path is not memory bound) */
   SVO_OPT_RAY_SORT = 5,       /* 0/1: trace ray streams of >= 65536 rays in (direction octant, origin Morton code) order; default 1 */

@@ -55,7 +55,7 @@ struct svo_ctx {
   uint64_t sort_cap = 0;
   size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 0, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 10, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)

@@ -17,6 +17,7 @@ with svo.SvoContext(1920, 1080) as ctx:
     ctx.upload(nodes)
     for k in variants:
         ctx.set_option(L.OPT_KERNEL, k)
-        ctx.render(svo.camera_frame(cam, frame_number=3, render_mode=0, max_depth=depth))
-        ctx.sync()
+        for i, c in enumerate(cam):  # e.g. "ABC": the three frames of the bench cycle
+            ctx.render(svo.camera_frame(c, frame_number=i + 1, render_mode=0, max_depth=depth))
+            ctx.sync()
 print("done")
