@@ -155,6 +155,11 @@ SceneView scene_view(const svo_ctx *c, const svo_frame *frame = nullptr) {
   v.nbytes = c->nbytes;
   v.ndesc = c->ndesc;
   v.first_word_zero = c->first_word_zero;
+  v.zero = 0u;
+  v.one = 1u;
+  v.two = 2u;
+  v.four = 4u;
+  v.exp_unit = 1u << 23;
   v.top = nullptr;
   v.ntop = 0;
   return v;
@@ -429,7 +434,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 12)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 13)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       c->opt_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;

@@ -208,15 +208,22 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
 //  10  WideStack: 16-byte stack entries carrying the parent's descriptor -- a POP is one LDL.128 instead of LDL.64
 //      followed by a dependent descriptor load
 //  11 / 12  __launch_bounds__(128, 7) / (128, 6): 72 / 80 registers per thread instead of 64
+//  13  variant 10 with the pipe-balanced loop body (Trav BAL): integer adds, moves, select chains and constant shifts
+//      of the loop as IMADs on the FMA pipe (ncu: ALU pipe 75 % busy, math-pipe throttle stalls, FMA pipe 20 %).
+//      Static count of the loop: ALU-pipe instructions 64 -> 44, FMA-pipe 26 -> 43, 6 more constant loads.
 // ---------------------------------------------------------------------------
-template <bool AUX, bool BOX, int STACK>
+template <bool AUX, bool BOX, int STACK, bool BAL = false>
 __device__ __forceinline__ void tile_body(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1) {
   __shared__ uint2 s_stack[STACK == 2 ? kSmemStackLevels : 1][kSmemStackStride];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
   const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
   if (x >= W || y >= y1) return;
-  shade_pixel<false, AUX, false, BOX, false, STACK>(sc, f, pl, W, H, x, y, nullptr, &s_stack[0][threadIdx.x]);
+  shade_pixel<false, AUX, false, BOX, false, STACK, BAL>(sc, f, pl, W, H, x, y, nullptr, &s_stack[0][threadIdx.x]);
+}
+template <bool AUX, bool BOX>
+__global__ void __launch_bounds__(128, 8) k_render_tile_balanced(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  tile_body<AUX, BOX, 1, true>(sc, f, pl, W, H, y0, y1);
 }
 template <bool AUX, bool BOX, int STACK>
 __global__ void __launch_bounds__(128, 8) k_render_tile_stack(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
@@ -548,7 +555,7 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
 #undef SVO_LAUNCH_BINNED
     return cudaGetLastError();
   }
-  if (cfg.kernel >= 9 && cfg.kernel <= 12 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || f.maxDepth <= kSmemStackLevels)) {
+  if (cfg.kernel >= 9 && cfg.kernel <= 13 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || f.maxDepth <= kSmemStackLevels)) {
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
 #define SVO_LAUNCH_X(A, B)                                                                                           \
@@ -556,7 +563,8 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
     if (cfg.kernel == 9) SVO_LAUNCH(grid, 128, stream, k_render_tile_stack<A, B, 2>)(sc, f, pl, W, H, y0, y1);        \
     else if (cfg.kernel == 10) SVO_LAUNCH(grid, 128, stream, k_render_tile_stack<A, B, 1>)(sc, f, pl, W, H, y0, y1);  \
     else if (cfg.kernel == 11) SVO_LAUNCH(grid, 128, stream, k_render_tile_regs<A, B, 7>)(sc, f, pl, W, H, y0, y1);   \
-    else SVO_LAUNCH(grid, 128, stream, k_render_tile_regs<A, B, 6>)(sc, f, pl, W, H, y0, y1);                         \
+    else if (cfg.kernel == 12) SVO_LAUNCH(grid, 128, stream, k_render_tile_regs<A, B, 6>)(sc, f, pl, W, H, y0, y1);   \
+    else SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<A, B>)(sc, f, pl, W, H, y0, y1);                        \
   } while (0)
     if (cfg.aux) SVO_LAUNCH_X(true, false);
     else if (cfg.box) SVO_LAUNCH_X(false, true);

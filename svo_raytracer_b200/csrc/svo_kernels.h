@@ -12,6 +12,7 @@ struct SceneView {
   uint64_t nbytes;
   uint32_t ndesc;
   uint32_t first_word_zero;  // octreeBuffer[0] == 0 (svotrace.comp:696)
+  uint32_t zero, one, two, four, exp_unit;  // hold 0, 1, 2, 4, 1 << 23: operands ptxas cannot fold (imad() in svo_trace.cuh)
   const uint2 *top;  // shared-memory copy of desc[0, ntop) (kernel variant 4 only)
   uint32_t ntop;
   float box_lo[3], box_hi[3];  // padded bounds of everything a cast of this frame can hit (cube coordinates [1,2])

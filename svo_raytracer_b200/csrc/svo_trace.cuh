@@ -114,6 +114,49 @@ SVO_DI uint32_t find_msb(uint32_t x) {  // GLSL findMSB for x != 0
 #endif
 }
 
+// a * b + c as an IMAD (FMA pipe).  Callers pass `one` -- a kernel-parameter word holding 1 that ptxas cannot fold --
+// as a factor, so that an add or a move survives as a multiply-add instead of being turned back into IADD3 / MOV.
+SVO_DI uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return a * b + c;
+#endif
+}
+// if (a > b) { p += s (one rounding); bits += one * bit; }  -- one FSETP, a predicated FADD and a predicated IMAD.
+// `bit` comes from the kernel parameters too (SceneView::one/two/four): with an immediate power of two ptxas emits LEA (ALU pipe).
+SVO_DI void step_if_gt(float a, float b, float &p, float s, uint32_t &bits, uint32_t one, uint32_t bit) {
+#ifdef __CUDA_ARCH__
+  asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %2, %3;\n\t@q add.rn.f32 %0, %0, %4;\n\t@q mad.lo.u32 %1, %5, %6, %1;\n\t}"
+      : "+f"(p), "+r"(bits)
+      : "f"(a), "f"(b), "f"(s), "r"(one), "r"(bit));
+#else
+  if (a > b) { p = fadd(p, s); bits += one * bit; }
+#endif
+}
+
+SVO_DI float fmove(float x, uint32_t one) { return __uint_as_float(imad(__float_as_uint(x), one, 0u)); }  // a register move as IMAD
+// if (a <= b) { p -= s (one rounding); bits += one * bit; }
+SVO_DI void step_if_le(float a, float b, float &p, float s, uint32_t &bits, uint32_t one, uint32_t bit) {
+#ifdef __CUDA_ARCH__
+  asm("{\n\t.reg .pred q;\n\tsetp.le.f32 q, %2, %3;\n\t@q sub.rn.f32 %0, %0, %4;\n\t@q mad.lo.u32 %1, %5, %6, %1;\n\t}"
+      : "+f"(p), "+r"(bits)
+      : "f"(a), "f"(b), "f"(s), "r"(one), "r"(bit));
+#else
+  if (a <= b) { p = fsub(p, s); bits += one * bit; }
+#endif
+}
+// if (a > b) dst = src  -- FSETP + predicated IMAD instead of FSETP + SEL
+SVO_DI void move_if_gt(float a, float b, int &dst, int src, uint32_t one) {
+#ifdef __CUDA_ARCH__
+  asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, %2;\n\t@q mad.lo.s32 %0, %3, %4, 0;\n\t}" : "+r"(dst) : "f"(a), "f"(b), "r"(src), "r"(one));
+#else
+  if (a > b) dst = src * (int)one;
+#endif
+}
+
 SVO_DI float sign_glsl(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
 struct RayStats {  // per-thread counters of the instrumented build (svo_render_stats)
@@ -238,7 +281,10 @@ SVO_DI uint2 stk_load(SmemStack s, int scale, uint32_t &pidx, float &t_max, cons
 // validation planes, no ray-stream API).
 // TOP: the first sc.ntop descriptors (the upper octree levels: the array is breadth-first) are read from a
 // shared-memory copy (sc.top) instead of global memory.
-template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
+// BAL: pipe-balanced loop body.  ncu puts the ALU pipe (LOP3 / SHF / SEL / FSETP / FMNMX / IADD3 / MOV) at 75 % busy with
+// math-pipe throttle among the top stall reasons while the FMA pipe idles at 20 %; BAL moves the integer adds, moves
+// and select chains of the loop onto the FMA pipe as IMADs (imad() below).  Same values, different instructions.
+template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false, bool BAL = false>
 struct Trav {
   typedef Ops<FAST> M;
   static __device__ __forceinline__ uint2 fetch(const SceneView &sc, uint32_t i) {
@@ -357,22 +403,31 @@ struct Trav {
       if (tc_max < h) { /* PUSH :316-319 */                                                                          \
         stk_store(stk, scale, pidx, t_max, pd);                                                                      \
       }                                                                                                              \
-      h = tc_max;                                                                                                    \
+      h = BAL ? fmove(tc_max, sc.one) : tc_max;                                                                      \
       /* descriptors of the interior siblings below: bits [24, 24+cs) -- the funnel shift leaves exactly those */    \
-      pidx = pd.x + __popc(__funnelshift_r(0u, pd.y >> 24, cs));                                                     \
+      pidx = BAL ? imad((uint32_t)__popc(__funnelshift_r(0u, pd.y >> 24, cs)), sc.one, pd.x)                         \
+                 : pd.x + __popc(__funnelshift_r(0u, pd.y >> 24, cs));                                               \
       pd = fetch(sc, pidx);                                /* parent = child (:322) */                               \
       const float half = M::mul(scale_exp2, 0.5f);                                                                   \
       const float tx_center = M::madd(half, cx, tx_corner); /* :306-308 */                                           \
       const float ty_center = M::madd(half, cy, ty_corner);                                                          \
       const float tz_center = M::madd(half, cz, tz_corner);                                                          \
-      --scale;                                                                                                       \
       scale_exp2 = half;                                                                                             \
-      const bool gx = tx_center > t_min, gy = ty_center > t_min, gz = tz_center > t_min; /* :328-330 */              \
-      px = gx ? fadd(px, scale_exp2) : px; /* exact adds */                                                          \
-      py = gy ? fadd(py, scale_exp2) : py;                                                                           \
-      pz = gz ? fadd(pz, scale_exp2) : pz;                                                                           \
-      idx = (gx ? 1u : 0u) | (gy ? 2u : 0u) | (gz ? 4u : 0u);                                                        \
-      t_max = tv_max;                                                                                                \
+      if (BAL) {                                                                                                     \
+        scale = (int)imad((uint32_t)scale, sc.one, 0xFFFFFFFFu);                                                     \
+        idx = sc.zero; /* a zero the compiler cannot see: keeps the three steps below predicated IMADs */          \
+        step_if_gt(tx_center, t_min, px, scale_exp2, idx, sc.one, sc.one); /* :328-330, exact adds */                \
+        step_if_gt(ty_center, t_min, py, scale_exp2, idx, sc.one, sc.two);                                           \
+        step_if_gt(tz_center, t_min, pz, scale_exp2, idx, sc.one, sc.four);                                          \
+      } else {                                                                                                       \
+        --scale;                                                                                                     \
+        const bool gx = tx_center > t_min, gy = ty_center > t_min, gz = tz_center > t_min; /* :328-330 */            \
+        px = gx ? fadd(px, scale_exp2) : px; /* exact adds */                                                        \
+        py = gy ? fadd(py, scale_exp2) : py;                                                                         \
+        pz = gz ? fadd(pz, scale_exp2) : pz;                                                                         \
+        idx = (gx ? 1u : 0u) | (gy ? 2u : 0u) | (gz ? 4u : 0u);                                                      \
+      }                                                                                                              \
+      t_max = BAL ? fmove(tv_max, sc.one) : tv_max;                                                                  \
       NEXT;                                                                                                          \
     }                                                                                                                \
   }                                                                                                                  \
@@ -389,12 +444,22 @@ struct Trav {
     iter = (float)(kMaxIterations + 1);                                                                              \
     EXIT(TRAV_MISS);                                                                                                 \
   }                                                                                                                  \
-  px = sx ? fsub(px, scale_exp2) : px;                                                                               \
-  py = sy ? fsub(py, scale_exp2) : py;                                                                               \
-  pz = sz ? fsub(pz, scale_exp2) : pz;                                                                               \
-  const uint32_t step_mask = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);                                       \
-  t_min = tc_max;                                                                                                    \
-  if (t_min > 0.05f) stop_scale = cone_stop; /* :275-277 */                                                          \
+  uint32_t step_mask;                                                                                                \
+  if (BAL) {                                                                                                         \
+    step_mask = sc.zero;                                                                                             \
+    step_if_le(tx_corner, tc_max, px, scale_exp2, step_mask, sc.one, sc.one);                                        \
+    step_if_le(ty_corner, tc_max, py, scale_exp2, step_mask, sc.one, sc.two);                                        \
+    step_if_le(tz_corner, tc_max, pz, scale_exp2, step_mask, sc.one, sc.four);                                       \
+    t_min = fmove(tc_max, sc.one);                                                                                   \
+    move_if_gt(t_min, 0.05f, stop_scale, cone_stop, sc.one); /* :275-277 */                                          \
+  } else {                                                                                                           \
+    px = sx ? fsub(px, scale_exp2) : px;                                                                             \
+    py = sy ? fsub(py, scale_exp2) : py;                                                                             \
+    pz = sz ? fsub(pz, scale_exp2) : pz;                                                                             \
+    step_mask = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);                                                    \
+    t_min = tc_max;                                                                                                  \
+    if (t_min > 0.05f) stop_scale = cone_stop; /* :275-277 */                                                        \
+  }                                                                                                                  \
   idx ^= step_mask;                                                                                                  \
   if ((idx & step_mask) != 0u) { /* POP :347-368 */                                                                  \
     /* The iteration cap (:264-266) is tested here only: every run of ADVANCEs ends in a POP after at most 3   */    \
@@ -411,15 +476,24 @@ struct Trav {
     if (sz) differing_bits |= __float_as_uint(pz) ^ __float_as_uint(fadd(pz, scale_exp2));                           \
     scale = (int)find_msb(differing_bits); /* findMSB */                                                             \
     if (scale >= kMaxScale) { EXIT(TRAV_MISS); } /* left the cube: the loop condition fails (:262) */                \
-    scale_exp2 = __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);                                         \
+    scale_exp2 = BAL ? __uint_as_float(imad((uint32_t)scale, sc.exp_unit, (uint32_t)(127 - kMaxScale) << 23))        \
+                     : __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);                                   \
     pd = stk_load<Trav>(stk, scale, pidx, t_max, sc);                                                                \
     const uint32_t shx = __float_as_uint(px) >> scale;                                                               \
     const uint32_t shy = __float_as_uint(py) >> scale;                                                               \
     const uint32_t shz = __float_as_uint(pz) >> scale;                                                               \
-    px = __uint_as_float(shx << scale);                                                                              \
-    py = __uint_as_float(shy << scale);                                                                              \
-    pz = __uint_as_float(shz << scale);                                                                              \
-    idx = (shx & 1u) | ((shy & 1u) << 1) | ((shz & 1u) << 2);                                                        \
+    if (BAL) { /* x << scale as a multiplication by 2^scale; the child index assembled by IMADs */                  \
+      const uint32_t pow2 = sc.one << scale;                                                                         \
+      px = __uint_as_float(imad(shx, pow2, 0u));                                                                     \
+      py = __uint_as_float(imad(shy, pow2, 0u));                                                                     \
+      pz = __uint_as_float(imad(shz, pow2, 0u));                                                                     \
+      idx = imad(shz & 1u, sc.four, imad(shy & 1u, sc.two, shx & 1u));                                               \
+    } else {                                                                                                         \
+      px = __uint_as_float(shx << scale);                                                                            \
+      py = __uint_as_float(shy << scale);                                                                            \
+      pz = __uint_as_float(shz << scale);                                                                            \
+      idx = (shx & 1u) | ((shy & 1u) << 1) | ((shz & 1u) << 2);                                                      \
+    }                                                                                                                \
     h = 0.0f;                                                                                                        \
   }
 
@@ -474,10 +548,10 @@ struct Trav {
 };
 
 // intersectOctree run to completion on the caller's stack.
-template <bool FAST, bool STATS, bool BOX, bool TOP, class Stk>
+template <bool FAST, bool STATS, bool BOX, bool TOP, bool BAL = false, class Stk>
 __device__ __forceinline__ bool cast_ray_on(Stk stk, const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
                                             int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs, bool attrs) {
-  Trav<FAST, STATS, BOX, TOP> T;
+  Trav<FAST, STATS, BOX, TOP, BAL> T;
   T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
   if (T.outside_box() || T.nan_ray(rs)) return T.finish(sc, TRAV_MISS, res, loops, attrs);  // no iteration can change anything
   return T.finish(sc, T.run(sc, stk, rs), res, loops, attrs);
@@ -733,7 +807,7 @@ SVO_DI void pixel_store(const SceneView &sc, const FrameParams &f, const Planes 
 
 // main (svotrace.comp:649-729) for pixel (x, y), run to completion.  STACK: 0 default, 1 WideStack, 2 SmemStack (`smem_stack` =
 // the thread's column of the CTA's shared-memory stack).
-template <bool FAST, bool AUX, bool STATS = false, bool BOX = false, bool TOP = false, int STACK = 0>
+template <bool FAST, bool AUX, bool STATS = false, bool BOX = false, bool TOP = false, int STACK = 0, bool BAL = false>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                                             int x, int y, RayStats *rs = nullptr, uint2 *smem_stack = nullptr) {
   Pixel P;
@@ -747,11 +821,11 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
         uint4 wide[kMaxScale + 1];
         WideStack ws;
         ws.p = wide;
-        hit = cast_ray_on<FAST, STATS, BOX, TOP>(ws, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+        hit = cast_ray_on<FAST, STATS, BOX, TOP, BAL>(ws, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
       } else if (STACK == 2) {
         SmemStack ss;
         ss.p = smem_stack;
-        hit = cast_ray_on<FAST, STATS, BOX, TOP>(ss, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+        hit = cast_ray_on<FAST, STATS, BOX, TOP, BAL>(ss, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
       } else {
         hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
       }

@@ -25,6 +25,11 @@ inline svo::SceneView emu_view_of(const emu_scene *s, const svo::FrameParams *f)
   uint32_t w0 = 0;
   memcpy(&w0, s->raw.data(), std::min<size_t>(4, s->raw.size()));
   v.first_word_zero = w0 == 0u;
+  v.zero = 0u;
+  v.one = 1u;
+  v.two = 2u;
+  v.four = 4u;
+  v.exp_unit = 1u << 23;
   v.top = nullptr;
   v.ntop = 0;
   return v;

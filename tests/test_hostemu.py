@@ -149,7 +149,7 @@ def test_device_source_random_worlds_random_cameras(svo, oracle, seed):
             _assert_planes_equal(sc.render(f, W, H, box=True, aux=False), want, "box seed %d trial %d %s" % (seed, trial, kw),
                                  planes=("rgba8", "depth"))
         # the __global__ kernels with warp-level protocols, on the SIMT emulator: lane refill (7, 8), octant binning (6)
-        for kernel in (7, 8, 6, 9, 10):
+        for kernel in (7, 8, 6, 9, 10, 13):
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=True), want, "kernel %d seed %d trial %d %s" % (kernel, seed, trial, kw))
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=False, box=True), want,
                                  "kernel %d box seed %d trial %d %s" % (kernel, seed, trial, kw), planes=("rgba8", "depth"))
@@ -180,6 +180,7 @@ def test_device_source_iteration_cap_boundary(oracle):
             _assert_planes_equal(sc.render(f, W, H, path=E.PATH_RUN), wantp, "cap run %s mode %d" % (x0, mode))
             _assert_planes_equal(sc.render(f, W, H, path=E.PATH_STEP), wantp, "cap step %s mode %d" % (x0, mode))
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=7, aux=True), wantp, "cap refill kernel %s mode %d" % (x0, mode))
+            _assert_planes_equal(sc.launch_render(f, W, H, kernel=13, aux=True), wantp, "cap balanced kernel %s mode %d" % (x0, mode))
             seen |= set(np.unique(wantp["iter"]).tolist())
     assert {1497, 1500, 1501} <= seen
     sc.close()
@@ -223,7 +224,7 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
 
 
 KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
-              11: "regs72"}
+              11: "regs72", 13: "balanced"}
 
 
 @pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))

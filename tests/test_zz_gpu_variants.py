@@ -20,7 +20,16 @@ def _assert_equal(got, want, what, planes=PLANES):
         assert same.all(), "%s: plane %s differs in %d of %d elements" % (what, k, int((~same).sum()), same.size)
 
 
-@pytest.mark.parametrize("kernel", [7, 8, 9, 10, 11, 12], ids=["refill4", "refill2", "smemstack", "widestack", "regs72", "regs80"])
+import os
+
+VARIANTS = {7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack", 11: "regs72", 12: "regs80"}
+if os.environ.get("SVO_TEST_UNMEASURED") == "1":
+    # variant 13 (loop integer work on the FMA pipe, inline PTX) was written after the round's GPU budget was spent: bit-exact on
+    # the SIMT emulator, which runs the C++ side of its helpers, not the PTX.  First thing to run on a B200.
+    VARIANTS[13] = "balanced"
+
+
+@pytest.mark.parametrize("kernel", list(VARIANTS), ids=list(VARIANTS.values()))
 def test_kernel_variants_bit_exact(svo, oracle, terrain512, terrain128, kernel):
     with svo.SvoContext(640, 360) as c:
         c.set_option(svo._lib.OPT_KERNEL, kernel)
