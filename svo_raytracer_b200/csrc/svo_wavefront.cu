@@ -23,6 +23,14 @@
 #include "svo_kernels.h"
 #include "svo_trace.cuh"
 
+#ifndef SVO_LAUNCH  // see svo_kernels.cu
+#ifdef SVO_HOST_EMU
+#define SVO_LAUNCH(grid, block, stream, ...) simt::launcher(grid, block, __VA_ARGS__)
+#else
+#define SVO_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<grid, block, 0, stream>>>
+#endif
+#endif
+
 namespace svo {
 
 constexpr int kRefill = 8;  // a warp re-arms its idle lanes once this many have finished
@@ -238,11 +246,11 @@ cudaError_t launch_render_wavefront(const LaunchCfg &cfg, const SceneView &sc, c
     const int qi = (s + 1) & 1, qo = s & 1;  // stage s reads queue qi (written by stage s-1) and writes queue qo
     if (stages > 0) {
       if (s == 0) {
-        if (cfg.fast) k_wf_trav<true, true><<<trav_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, nullptr, nullptr, nullptr, ws.hitA, ws.hitB, work + 0);
-        else k_wf_trav<false, true><<<trav_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, nullptr, nullptr, nullptr, ws.hitA, ws.hitB, work + 0);
+        if (cfg.fast) SVO_LAUNCH(trav_grid, 128, stream, k_wf_trav<true, true>)(sc, f, pl, W, H, y0, y1, nullptr, nullptr, nullptr, ws.hitA, ws.hitB, work + 0);
+        else SVO_LAUNCH(trav_grid, 128, stream, k_wf_trav<false, true>)(sc, f, pl, W, H, y0, y1, nullptr, nullptr, nullptr, ws.hitA, ws.hitB, work + 0);
       } else {
-        if (cfg.fast) k_wf_trav<true, false><<<trav_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, ws.rayA[qi], ws.rayB[qi], count + s, ws.hitA, ws.hitB, work + s);
-        else k_wf_trav<false, false><<<trav_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, ws.rayA[qi], ws.rayB[qi], count + s, ws.hitA, ws.hitB, work + s);
+        if (cfg.fast) SVO_LAUNCH(trav_grid, 128, stream, k_wf_trav<true, false>)(sc, f, pl, W, H, y0, y1, ws.rayA[qi], ws.rayB[qi], count + s, ws.hitA, ws.hitB, work + s);
+        else SVO_LAUNCH(trav_grid, 128, stream, k_wf_trav<false, false>)(sc, f, pl, W, H, y0, y1, ws.rayA[qi], ws.rayB[qi], count + s, ws.hitA, ws.hitB, work + s);
       }
     }
     WfQueues q;
@@ -253,11 +261,11 @@ cudaError_t launch_render_wavefront(const LaunchCfg &cfg, const SceneView &sc, c
     q.n_in = count + s;
     q.n_out = count + s + 1;
     if (s == 0) {
-      if (cfg.aux) k_wf_shade<true, true><<<shade_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, q);
-      else k_wf_shade<false, true><<<shade_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, q);
+      if (cfg.aux) SVO_LAUNCH(shade_grid, 128, stream, k_wf_shade<true, true>)(sc, f, pl, W, H, y0, y1, q);
+      else SVO_LAUNCH(shade_grid, 128, stream, k_wf_shade<false, true>)(sc, f, pl, W, H, y0, y1, q);
     } else {
-      if (cfg.aux) k_wf_shade<true, false><<<shade_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, q);
-      else k_wf_shade<false, false><<<shade_grid, 128, 0, stream>>>(sc, f, pl, W, H, y0, y1, q);
+      if (cfg.aux) SVO_LAUNCH(shade_grid, 128, stream, k_wf_shade<true, false>)(sc, f, pl, W, H, y0, y1, q);
+      else SVO_LAUNCH(shade_grid, 128, stream, k_wf_shade<false, false>)(sc, f, pl, W, H, y0, y1, q);
     }
   }
   return cudaGetLastError();

@@ -11,9 +11,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.normpath(os.path.join(_HERE, "..", "..", "svo_raytracer_b200", "csrc"))
 _LIB_PATH = os.path.join(_HERE, "libsvo_hostemu.so")
-_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
+_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
 _SRCS = _CPP + [os.path.join(_HERE, f) for f in ("cuda_host_shim.h", "simt_emu.h", "emu_scene.h")] + \
-    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_transcode.h")]
+    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_wavefront.cu", "svo_transcode.h")]
 CUDA_INCLUDE = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 

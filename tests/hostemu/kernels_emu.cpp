@@ -18,6 +18,8 @@
 
 using namespace svo;
 
+int emu_launch_wavefront(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1);
+
 extern "C" {
 
 // svo_render_rows through the product's launch_render on the emulator.  kernel = SVO_OPT_KERNEL, ctas = CTAs of the
@@ -46,7 +48,8 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   cfg.band_offset = band_offset;
   cfg.band_ctas = band_rows / 8;
   cfg.tile_counter = &tile_counter;
-  simt::g_os_threads = kernel == 1 ? 1 : nthreads;  // the persistent kernel's queue is consumed by whichever block runs
+  simt::g_os_threads = (kernel == 1 || kernel == 2) ? 1 : nthreads;  // persistent kernels: the queue is consumed by whichever block runs
+  if (kernel == 2) return emu_launch_wavefront(cfg, sc, *f, pl, W, H, y0, y1);  // wavefront_emu.cpp
   return (int)launch_render(cfg, sc, *f, pl, W, H, y0, y1, nullptr);
 }
 

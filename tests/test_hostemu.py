@@ -223,7 +223,7 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
     assert scene128.simt(f, W, H, costs, box=False, tile_w=8)["if_if"] == r["if_if"]
 
 
-KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
+KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 2: "wavefront", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
               11: "regs72", 13: "balanced"}
 
 
@@ -234,7 +234,7 @@ def test_global_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kern
     shared-memory counting sort and block-wide votes of the binned kernel, the shared-memory descriptor prefix --
     every plane bit-exact against the oracle, image sizes that do not divide into CTA tiles, uneven row bands."""
     W, H = 200, 120
-    for cam, mode in (("B", 0), ("C", 2), ("A", 0)) if kernel != 1 else (("B", 0),):
+    for cam, mode in (("B", 0), ("C", 2), ("A", 0)) if kernel not in (1, 2) else (("B", 0), ("C", 2)):
         pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
         f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=mode, max_depth=7, casts=3 if cam == "A" else 2)
         want, _ = oracle.render(terrain128, f, W, H, nthreads=8)
