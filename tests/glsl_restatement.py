@@ -120,9 +120,34 @@ class Buffer:
         return self.extract_non_surface_leaf(pointer), pointer
 
 
-def intersect_octree(buf: Buffer, origin, direction, max_depth: int, cone_trace: bool):
+def new_cast_result():
+    """castResult (:186-197).  Uninitialised upstream; zero by the contract of DESIGN.md (U2)."""
+    z = F(0.0)
+    return {"value": 0, "pointer": 0, "iter": 0, "t": z, "scale": z, "debugColor": (z, z, z), "normal": (z, z, z), "voxelPos": (z, z, z), "depth": 0}
+
+
+def intersect_octree(buf: Buffer, origin, direction, max_depth: int, cone_trace: bool, res: dict | None = None):
     """:211-432.  Returns a dict: hit, iter (loop iterations run, 1501 = capped) and, when the code after the loop ran, the
-    castResult fields it writes."""
+    castResult fields it writes.  `res`: the caller's castResult, updated the way the `out` parameter is (fields the
+    shader does not write keep their old values)."""
+    out = _intersect_octree(buf, origin, direction, max_depth, cone_trace)
+    if res is not None:
+        res["pointer"] = out.get("last_pointer", res["pointer"])  # extractChild writes res.pointer on every call (:294, :381)
+        if out["capped"]:
+            res["debugColor"] = (F(0.3), F(0.3), F(0.6))  # :213 survives
+        elif "t" not in out:
+            g = F(0.01) * F(out["iter"])  # :376
+            res["debugColor"] = (g, g, g)
+        else:
+            for k in ("t", "value", "normal", "scale", "depth", "voxelPos"):
+                res[k] = out[k]
+            res["iter"] = out["iter"]
+            g = F(0.005) * F(out["iter"])  # :428
+            res["debugColor"] = (g, g, g)
+    return out
+
+
+def _intersect_octree(buf: Buffer, origin, direction, max_depth: int, cone_trace: bool):
     ox, oy, oz = (F(v) for v in origin)
     dx, dy, dz = (F(v) for v in direction)
     with np.errstate(all="ignore"):
@@ -175,7 +200,7 @@ def intersect_octree(buf: Buffer, origin, direction, max_depth: int, cone_trace:
         while scale < MAX_SCALE:
             it += 1
             if it > MAX_RAYCAST_ITERATIONS:
-                return {"hit": False, "iter": it, "capped": True, "stale_pops": stale_pops}
+                return {"hit": False, "iter": it, "capped": True, "stale_pops": stale_pops, "last_pointer": pointer}
             if child_descriptor == 0:
                 child_descriptor = parent.cp
             if t_min > F(0.05) and cone_trace:
@@ -257,7 +282,7 @@ def intersect_octree(buf: Buffer, origin, direction, max_depth: int, cone_trace:
                 h = F(0.0)
                 child_descriptor = 0
         if scale >= MAX_SCALE:
-            return {"hit": False, "iter": it, "capped": False, "stale_pops": stale_pops}
+            return {"hit": False, "iter": it, "capped": False, "stale_pops": stale_pops, "last_pointer": pointer}
         nx, ny, nz = F(0.0), F(0.0), F(0.0)
         target, pointer = buf.extract_child(parent.descriptor, child_descriptor, child_shift, parent.leafMask)
         if target.leafMask != 0:
@@ -277,6 +302,163 @@ def intersect_octree(buf: Buffer, origin, direction, max_depth: int, cone_trace:
         vpx = vpx + nx * scale_exp2 * F(2.0) * F(1.74)
         vpy = vpy + ny * scale_exp2 * F(2.0) * F(1.74)
         vpz = vpz + nz * scale_exp2 * F(2.0) * F(1.74)
-        return {"hit": bool(scale < MAX_SCALE and t_min <= t_max), "iter": it, "capped": False, "stale_pops": stale_pops, "pointer": pointer, "t": t_min,
+        return {"hit": bool(scale < MAX_SCALE and t_min <= t_max), "iter": it, "capped": False, "stale_pops": stale_pops, "pointer": pointer,
+                "last_pointer": pointer, "t": t_min,
                 "value": target.value, "normal": (nx, ny, nz), "scale": scale_exp2, "depth": MAX_SCALE - scale,
                 "voxelPos": (vpx, vpy, vpz)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trace() :435-646 and main() :649-729.  sin / cos / acos / exp are the contract's fixed kernels (DESIGN.md section 2;
+# tested against libm on their own): the caller passes them in, everything else is restated here.
+# ---------------------------------------------------------------------------------------------------------------
+PI = F(3.14159265359)
+SQRT3 = F(1.73205080757)
+MAX_DEPTH = 13
+
+
+def _v(a, b, c):
+    return (F(a), F(b), F(c))
+
+
+def _dot(a, b):
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+
+def _normalize(v):
+    length = np.sqrt(_dot(v, v))
+    return (v[0] / length, v[1] / length, v[2] / length)
+
+
+def _cross(a, b):
+    return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
+
+
+def _mix(x, y, a):
+    return x * (F(1.0) - a) + y * a
+
+
+def _rand(m, x, y):  # :26-29
+    s = m["sin"](x * F(12.9898) + y * F(78.233))
+    t = s * F(43758.5453)
+    return t - np.floor(t)
+
+
+def trace(buf, m, beam_dist, origin, direction, seed0, seed1, seed2, render_mode, max_depth=MAX_DEPTH, casts=2):
+    """Returns (colour, depth or None if never written, primary: dict of what the validation planes record)."""
+    with np.errstate(all="ignore"):
+        res = new_cast_result()
+        res["t"] = F(2.0)
+        origin = tuple(origin[k] + direction[k] * beam_dist for k in range(3))
+        d = direction
+        depth = None
+        accum = _v(0, 0, 0)
+        mask = _v(1, 1, 1)
+        primary = None
+
+        def cast(o, dd, cone):
+            nonlocal primary
+            out = intersect_octree(buf, o, dd, max_depth, cone, res)
+            if primary is None:
+                primary = {"hit": out["hit"], "iter": out["iter"], "pointer": out.get("pointer"), "t": out.get("t")}
+            return out["hit"]
+
+        if render_mode == 0:
+            for i in range(casts):
+                intersect = cast(origin, d, i != 0)
+                if not intersect and i == 0:
+                    sky = _v(0.6725, 0.8784, 1.0)
+                    k = _v(0.4, 0.4, 0.25)
+                    accum = tuple(accum[c] + (sky[c] - d[1] * k[c]) for c in range(3))
+                    break
+                normal = res["normal"]
+                hitpoint = res["voxelPos"]
+                r = _rand(m, seed0 + _rand(m, seed0, seed2 * F(0.1)), seed1 + _rand(m, seed1, seed2 * F(0.02)))
+                rand1 = F(2.0) * PI * r
+                w = normal
+                axis = _v(0, 1, 0) if abs(w[0]) > F(0.1) else _v(1, 0, 0)
+                u = _normalize(_cross(axis, w))
+                v = _cross(w, u)
+                c1, s1, omr = m["cos"](rand1), m["sin"](rand1), F(1.0) - r
+                newdir = _normalize(tuple((u[c] * c1 + v[c] * s1) + w[c] * omr for c in range(3)))
+                origin = hitpoint
+                d = newdir
+                matcolor = tuple(hitpoint[c] - F(1.0) for c in range(3))
+                if res["value"] == 1:
+                    matcolor = _v(0.84, 0.86, 0.78)
+                if res["value"] == 2:
+                    matcolor = _v(0.57, 0.5, 0.31)
+                if res["value"] == 3:
+                    matcolor = _v(0.37, 0.43, 0.27)
+                if intersect:
+                    depth = res["t"]
+                    accum = tuple(accum[c] + mask[c] * F(0.0) for c in range(3))
+                    dn = _dot(newdir, normal)
+                    mask = tuple(mask[c] * matcolor[c] * dn for c in range(3))
+                else:
+                    sun = _normalize(_v(1, 1, 1))
+                    diff = m["acos"](_dot(d, sun))
+                    if diff < F(0.4):
+                        accum = tuple(accum[c] + mask[c] * F(7.0) for c in range(3))
+                    accum = tuple(accum[c] + mask[c] * F(1.0) for c in range(3))
+                    depth = F(0.0)
+                    break
+            return accum, depth, primary
+        if render_mode == 1:
+            if cast(origin, d, False):
+                depth = res["t"]
+            else:
+                depth = F(0.0)
+            return res["debugColor"], depth, primary
+        if render_mode == 2:
+            if cast(origin, d, False):
+                depth = res["t"]
+                matcolor = _v(0, 0, 0)
+                if res["value"] == 1:
+                    matcolor = _v(0.84, 0.86, 0.78)
+                if res["value"] == 2:
+                    matcolor = _v(0.57, 0.5, 0.31)
+                if res["value"] == 3:
+                    matcolor = _v(0.37, 0.43, 0.27)
+                sun = _normalize(_v(0.5, 0.5, 0.5))
+                if res["depth"] >= 10:
+                    ph = _dot(res["normal"], sun) * F(0.1)
+                else:
+                    ph = _dot(_v(0, 1, 0), sun) * F(0.1)
+                matcolor = tuple(matcolor[c] + ph for c in range(3))
+                true_dist = res["t"] + beam_dist
+                lg = m["exp"](F(-0.5) * true_dist * F(2.0))
+                lb = m["exp"](F(-0.5) * true_dist * F(4.0))
+                lr = m["exp"](F(-0.5) * true_dist * F(1.0))
+                matcolor = (lr * matcolor[0] + (F(1.0) - lr) * F(1.0), lg * matcolor[1] + (F(1.0) - lg) * F(1.0),
+                            lb * matcolor[2] + (F(1.0) - lb) * F(1.0))
+                if cast(res["voxelPos"], sun, False) and res["t"] > res["scale"] * SQRT3:
+                    matcolor = tuple(matcolor[c] - F(0.2) for c in range(3))
+                elif res["iter"] > 260:
+                    pen = F(0.05) * F(res["iter"]) / F(100.0)
+                    matcolor = tuple(matcolor[c] - pen for c in range(3))
+                return matcolor, depth, primary
+            sky = _v(0.6725, 0.8784, 1.0)
+            k = _v(0.4, 0.4, 0.25)
+            return tuple(sky[c] - d[1] * k[c] for c in range(3)), F(0.0), primary
+        if render_mode == 3:
+            if cast(origin, d, False):
+                return tuple(res["normal"][c] * F(0.5) + F(0.5) for c in range(3)), res["t"], primary
+            return _v(0, 0, 0), F(0.0), primary
+        return res["voxelPos"], depth, primary  # mode 4
+
+
+def render_pixel(buf, m, cam_pos, l1, l2, r1, r2, frame_number, render_mode, width, height, x, y, max_depth=MAX_DEPTH, casts=2):
+    """main() for one pixel (no beam pass).  Returns (colour after the debug overlay, depth, primary)."""
+    with np.errstate(all="ignore"):
+        px = (F(x) + F(0.5)) / F(width)
+        py = (F(y) + F(0.5)) / F(height)
+        d = tuple(_mix(_mix(F(l1[k]), F(l2[k]), py), _mix(F(r1[k]), F(r2[k]), py), px) for k in range(3))
+        nd = _normalize(d)
+        color, depth, primary = trace(buf, m, F(0.0), tuple(F(v) for v in cam_pos), nd, F(x), F(y), F(frame_number), render_mode, max_depth, casts)
+        if depth is None:
+            depth = F(-1.0)  # :672
+        if x < 10 and y < 10:
+            first_word = int(buf.words[0]) if buf.words.size else 0
+            color = _v(1, 0, 0) if first_word == 0 else _v(1, 1, 1)
+        return color, depth, primary

@@ -104,3 +104,46 @@ def test_hand_assembled_streams_and_iteration_cap(oracle):
     assert (want["iter"][pick] == 1501).any() and (want["iter"][pick] == 1500).any()
     _, capped = _compare(oracle, tube, [(rays["o"][i], rays["d"][i]) for i in pick], 13, False)
     assert capped >= 1
+
+
+def _math(oracle):
+    L = oracle.lib()
+    return {k: (lambda f: (lambda x: np.float32(f(float(x)))))(getattr(L, "svo_oracle_" + k)) for k in ("sin", "cos", "acos", "exp")}
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_trace_and_main_every_render_mode(svo, oracle, mode):
+    """trace() and main() restated a second time (the contract's sin / cos / acos / exp kernels are shared, everything else --
+    bounce loop, stale castResult fields, material table, fog, shadow ray, penumbra, debug overlay -- is written anew):
+    colour, depth, primary hit id, iteration count and t of every pixel of a small frame, bit for bit."""
+    rng = np.random.default_rng(17)
+    n = 32
+    z, y, x = np.mgrid[0:n, 0:n, 0:n]
+    vox = np.zeros((n, n, n), np.uint8)
+    h = (9 + 4 * np.sin(x / 5.0) + 3 * np.cos(z / 4.0)).astype(int)
+    vox[y <= h] = 1
+    vox[(y <= h) & (y >= h - 1)] = 3
+    vox[(x - 20) ** 2 + (y - 20) ** 2 + (z - 12) ** 2 <= 30] = 2
+    pts = rng.integers(0, n, size=(40, 3))
+    vox[pts[:, 2], pts[:, 1], pts[:, 0]] = 4  # a value outside the material table
+    nodes, _ = oracle.build_dense(vox)
+    buf, m = G.Buffer(nodes), _math(oracle)
+    W, H = 40, 24
+    for cam in ("B", "C"):
+        pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+        kw = dict(frame_number=5, render_mode=mode, max_depth=5, casts=2 if cam == "B" else 3)
+        want, _ = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, **kw), W, H, nthreads=4)
+        for yy in range(H):
+            for xx in range(W):
+                color, depth, primary = G.render_pixel(buf, m, pos, l1, l2, r1, r2, 5, mode, W, H, xx, yy, max_depth=5, casts=kw["casts"])
+                what = (cam, mode, xx, yy)
+                for c in range(3):
+                    a, b = np.float32(color[c]), want["radiance"][yy, xx, c]
+                    assert _u32(a) == _u32(b) or (np.isnan(a) and np.isnan(b)), what + ("colour", c, a, b)
+                a, b = np.float32(depth), want["depth"][yy, xx]
+                assert _u32(a) == _u32(b) or (np.isnan(a) and np.isnan(b)), what + ("depth", a, b)
+                if primary is not None:  # mode 4 casts nothing
+                    assert min(primary["iter"], 1501) == want["iter"][yy, xx], what
+                    assert (primary["pointer"] if primary["hit"] else 0xFFFFFFFF) == want["hit_id"][yy, xx], what
+                    if primary["hit"]:
+                        assert _u32(primary["t"]) == _u32(want["primary_t"][yy, xx]), what
