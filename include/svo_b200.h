@@ -95,8 +95,10 @@ enum svo_option {
                                * non-empty leaves (computed at upload).  Outputs are unchanged; only the iteration count of
                                * MISSING casts differs, so it is ignored in render mode 1 and with SVO_OPT_AUX_PLANES.  default 1 */
   SVO_OPT_BAND_ROWS = 7,      /* image rows per band of svo_render_interleaved (multiple of 8); default 8 */
-  SVO_OPT_GPU_TRANSCODE = 8   /* 0/1: build the traversal descriptors from the uploaded stream on the device (default 1) or on
+  SVO_OPT_GPU_TRANSCODE = 8,  /* 0/1: build the traversal descriptors from the uploaded stream on the device (default 1) or on
                                * the host; same result bit for bit */
+  SVO_OPT_STREAM_KERNEL = 9   /* svo_cast / svo_cast_device: 0 (default) one grid-stride thread per ray; 1 persistent threads with
+                               * warp-level ray fetch -- lanes whose ray has finished are re-armed from the stream (not yet measured) */
 };
 
 /* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and

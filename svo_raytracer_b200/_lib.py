@@ -21,6 +21,7 @@ PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIM
 PLANE_BACK = 0x100
 # enum svo_option
 OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS, OPT_BAND_ROWS, OPT_GPU_TRANSCODE = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_STREAM_KERNEL = 9
 
 
 class SvoError(RuntimeError):

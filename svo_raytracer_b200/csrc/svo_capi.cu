@@ -55,7 +55,7 @@ struct svo_ctx {
   uint64_t sort_cap = 0;
   size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 10, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 10, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1, opt_stream_kernel = 0;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
@@ -170,6 +170,7 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.aux = c->opt_aux != 0;
   l.box = false;
   l.kernel = c->opt_kernel;
+  l.stream_kernel = c->opt_stream_kernel;
   l.sm_count = c->sm_count;
   l.band_stride = 0;
   l.band_offset = 0;
@@ -441,6 +442,10 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
     case SVO_OPT_GPU_TRANSCODE: c->opt_gpu_transcode = value != 0; return SVO_OK;
+    case SVO_OPT_STREAM_KERNEL:
+      if (value != 0 && value != 1) return fail(c, SVO_ERR_INVALID, "unknown ray-stream kernel");
+      c->opt_stream_kernel = (int)value;
+      return SVO_OK;
     case SVO_OPT_BAND_ROWS:
       if (value < 8 || value > 4096 || value % 8) return fail(c, SVO_ERR_INVALID, "band rows must be a multiple of 8");
       c->opt_band_rows = (int)value;
@@ -459,6 +464,7 @@ int svo_get_option(const svo_ctx *c, int option, int64_t *value) {
     case SVO_OPT_CONTENT_BOUNDS: *value = c->opt_bounds; return SVO_OK;
     case SVO_OPT_BAND_ROWS: *value = c->opt_band_rows; return SVO_OK;
     case SVO_OPT_GPU_TRANSCODE: *value = c->opt_gpu_transcode; return SVO_OK;
+    case SVO_OPT_STREAM_KERNEL: *value = c->opt_stream_kernel; return SVO_OK;
     default: return fail(const_cast<svo_ctx *>(c), SVO_ERR_INVALID, "unknown option");
   }
 }

@@ -480,6 +480,89 @@ __global__ void __launch_bounds__(128) k_cast_stream(SceneView sc, const RayRec 
 }
 
 // ---------------------------------------------------------------------------
+// Ray streams, persistent threads with warp-level ray fetch (Aila & Laine's while-while organisation; SVO_OPT_STREAM_KERNEL 1).
+// Free-standing rays carry no shading state, so a lane that has finished can be re-armed for the price of
+// Trav::setup: warps take chunks of the (binned) stream from a global counter, leave the traversal loop when
+// kRefillIdle lanes are free, write those lanes' hit records and hand them the next rays.  Trip counts of incoherent
+// rays range from 1 to 1500 within a warp; the grid-stride kernel above waits for the slowest ray of every 32.
+// ---------------------------------------------------------------------------
+constexpr unsigned kStreamChunk = 256;  // rays a warp takes from the stream per atomic
+
+template <bool FAST>
+__global__ void __launch_bounds__(128, 8) k_cast_stream_persistent(SceneView sc, const RayRec *__restrict__ rays, const uint32_t *__restrict__ order,
+                                                                  uint64_t n, HitRec *__restrict__ out, int maxDepth,
+                                                                  unsigned int *__restrict__ next_chunk) {
+  const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+  uint4 wide[kMaxScale + 1];
+  WideStack stk;
+  stk.p = wide;
+  Trav<FAST> T;
+  uint64_t mine = 0, pool_next = 0, pool_end = 0;
+  int busy = 0;
+  bool dry = false;  // the stream has no chunks left
+  for (;;) {
+    unsigned idle = __ballot_sync(0xffffffffu, !busy);
+    while (idle != 0u) {
+      if (pool_next == pool_end) {
+        if (dry) break;
+        unsigned c = 0;
+        if (lane == 0) c = atomicAdd(next_chunk, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        pool_next = (uint64_t)c * kStreamChunk;
+        if (pool_next >= n) { dry = true; pool_next = pool_end = 0; break; }
+        pool_end = pool_next + kStreamChunk < n ? pool_next + kStreamChunk : n;
+      }
+      const uint64_t avail = pool_end - pool_next;
+      const unsigned rank = __popc(idle & lt_mask);
+      if (!busy && rank < avail) {
+        const uint64_t i = pool_next + rank;
+        mine = order ? (uint64_t)order[i] : i;
+        const RayRec ray = rays[mine];
+        T.setup(sc, mk3(ray.ox, ray.oy, ray.oz), mk3(ray.dx, ray.dy, ray.dz), maxDepth, false, 11, nullptr);
+        if (T.nan_ray(nullptr)) {  // ends before the loop: the record is final
+          CastRes res;
+          cast_res_clear(res);
+          uint32_t loops = 0;
+          T.finish(sc, TRAV_MISS, res, loops);
+          HitRec h;
+          h.id = kNoHit; h.t = 0.0f; h.value = 0u; h.iter = loops;
+          out[mine] = h;
+        } else {
+          busy = 1;
+        }
+      }
+      const unsigned take = (unsigned)__popc(idle);
+      pool_next += avail < take ? avail : take;
+      idle = __ballot_sync(0xffffffffu, !busy);
+    }
+    const int busy0 = __popc(__ballot_sync(0xffffffffu, busy));
+    if (busy0 == 0) break;  // stream dry, every ray finished
+    const int limit = dry && pool_next == pool_end ? 0 : max(busy0 - kRefillIdle, 0);
+    for (;;) {
+      if (busy) {
+        int status = TRAV_CONTINUE;
+#pragma unroll 1
+        for (int k = 0; k < kRefillBatch && status == TRAV_CONTINUE; k++) status = T.step(sc, stk, nullptr);
+        if (status != TRAV_CONTINUE) {
+          busy = 0;
+          CastRes res;
+          cast_res_clear(res);
+          uint32_t loops = 0;
+          const bool hit = T.finish(sc, status, res, loops);
+          HitRec h;
+          h.id = hit ? res.pointer : kNoHit;
+          h.t = hit ? res.t : 0.0f;
+          h.value = hit ? res.value : 0u;
+          h.iter = loops;
+          out[mine] = h;
+        }
+      }
+      if (__popc(__ballot_sync(0xffffffffu, busy)) <= limit) break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Beam pre-pass (reference src/shaders/svobeam.comp:617-636): one
 // UN-normalised ray through pixel (4gx, 4gy); stores res.t (0 on miss, where
 // upstream leaves it undefined).
@@ -646,6 +729,16 @@ cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int 
 cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d_rays, const uint32_t *d_order, uint64_t n,
                         void *d_out, int maxDepth, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
+  if (cfg.stream_kernel == 1) {  // persistent threads with warp-level ray fetch
+    cudaError_t e = cudaMemsetAsync(cfg.tile_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const uint64_t warps = (n + 31) / 32;
+    const uint64_t ctas = (warps + 3) / 4, cap_ctas = (uint64_t)cfg.sm_count * 8u;
+    const unsigned pgrid = (unsigned)(ctas < cap_ctas ? ctas : cap_ctas);
+    if (cfg.fast) SVO_LAUNCH(pgrid, 128, stream, k_cast_stream_persistent<true>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth, cfg.tile_counter);
+    else SVO_LAUNCH(pgrid, 128, stream, k_cast_stream_persistent<false>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth, cfg.tile_counter);
+    return cudaGetLastError();
+  }
   const int block = 128;
   uint64_t want = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)cfg.sm_count * 16u * 8u;

@@ -39,6 +39,7 @@ struct LaunchCfg {
   bool aux;      // also write hit_id / iter / primary_t / radiance
   bool box;      // end casts that are outside the content box (SceneView::box_*)
   int kernel;    // variant selector (SVO_OPT_KERNEL)
+  int stream_kernel;  // ray streams: 0 grid-stride kernel, 1 persistent threads with warp-level ray fetch (SVO_OPT_STREAM_KERNEL)
   int sm_count;
   int band_stride, band_offset;  // tile kernel: interleaved bands (stride 0 = all bands)
   int band_ctas;                 // CTA rows (8 image rows each) per band

@@ -44,6 +44,8 @@ def lib():
         L.emu_launch_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int]
+        L.emu_launch_cast.restype = C.c_int
+        L.emu_launch_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emu_cast.restype = C.c_int
         L.emu_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
         L.emu_beam.restype = C.c_int
@@ -127,6 +129,17 @@ class Scene:
         rc = lib().emu_launch_render(self._h, C.byref(frame), width, height, y0, y1, kernel, int(box), int(aux), _ptr(beam),
                                      _ptr(out["rgba8"]), _ptr(out["depth"]), _ptr(out["hit_id"]), _ptr(out["iter"]),
                                      _ptr(out["primary_t"]), _ptr(out["radiance"]), band_stride, band_offset, band_rows, ctas, nthreads)
+        assert rc == 0, rc
+        return out
+
+    def launch_cast(self, rays, max_depth=13, kernel=0, order=None, ctas=2, nthreads=8):
+        """The product's launch_cast() (ray-stream kernels) on the SIMT emulator."""
+        from oracle import oracle as O
+        rays = np.ascontiguousarray(rays, dtype=O.RAY_DTYPE)
+        out = np.zeros(rays.shape[0], dtype=O.HIT_DTYPE)
+        if order is not None:
+            order = np.ascontiguousarray(order, dtype=np.uint32)
+        rc = lib().emu_launch_cast(self._h, _ptr(rays), _ptr(order), rays.shape[0], _ptr(out), max_depth, kernel, ctas, nthreads)
         assert rc == 0, rc
         return out
 

@@ -42,6 +42,7 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   cfg.aux = aux != 0;
   cfg.box = box != 0 && !aux && f->renderMode != 1;  // box_allowed() of svo_capi.cu
   cfg.kernel = kernel;
+  cfg.stream_kernel = 0;
   cfg.sm_count = ctas;
   cfg.ctas_per_sm = 1;
   cfg.band_stride = band_stride;
@@ -51,6 +52,27 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   simt::g_os_threads = (kernel == 1 || kernel == 2) ? 1 : nthreads;  // persistent kernels: the queue is consumed by whichever block runs
   if (kernel == 2) return emu_launch_wavefront(cfg, sc, *f, pl, W, H, y0, y1);  // wavefront_emu.cpp
   return (int)launch_render(cfg, sc, *f, pl, W, H, y0, y1, nullptr);
+}
+
+// svo_cast through the product's launch_cast on the emulator.  kernel 0 = grid-stride kernel, 1 = persistent threads with
+// warp-level ray fetch; order = optional permutation (the binned order of SVO_OPT_RAY_SORT).
+int emu_launch_cast(const emu_scene *s, const void *rays, const uint32_t *order, uint64_t n, void *out, int maxDepth, int kernel, int ctas,
+                    int nthreads) {
+  const SceneView sc = emu_view_of(s, nullptr);
+  unsigned int counter = 0;
+  LaunchCfg cfg;
+  cfg.fast = false;
+  cfg.aux = false;
+  cfg.box = false;
+  cfg.kernel = 0;
+  cfg.stream_kernel = kernel;
+  cfg.sm_count = ctas;
+  cfg.ctas_per_sm = 1;
+  cfg.band_stride = cfg.band_offset = 0;
+  cfg.band_ctas = 1;
+  cfg.tile_counter = &counter;
+  simt::g_os_threads = kernel == 1 ? 1 : nthreads;
+  return (int)launch_cast(cfg, sc, rays, order, n, out, maxDepth, nullptr);
 }
 
 }  // extern "C"

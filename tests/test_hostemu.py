@@ -168,6 +168,10 @@ def test_device_source_iteration_cap_boundary(oracle):
     got = sc.cast(rays, 13)
     for k in ("id", "iter", "value"):
         assert np.array_equal(got[k], want[k]), k
+    got = sc.launch_cast(rays[:6000], 13, kernel=1)  # persistent stream kernel: Trav::step + cap_fixup at every exit
+    for k in ("id", "iter", "value"):
+        assert np.array_equal(got[k], want[k][:6000]), k
+    assert (want["iter"][:6000] == 1500).any() and (want["iter"][:6000] == 1501).any()
     W, H = 96, 64
     h = 2.0 ** -10
     cam = ((1.9, 1 + h / 2, 1 + h / 2), (-1, -1e-4, -1e-4), (-1, 1e-4, -1e-4), (-1, -1e-4, 1e-4), (-1, 1e-4, 1e-4))
@@ -254,3 +258,25 @@ def test_global_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kern
             for part in range(parts):
                 got = scene128.launch_render(f, W, H, kernel=kernel, aux=True, band_stride=parts, band_offset=part, band_rows=rows, into=got)
             _assert_planes_equal(got, want, "kernel %d interleaved %d x %d rows" % (kernel, parts, rows))
+
+
+@pytest.mark.parametrize("kernel", [0, 1], ids=["gridstride", "persistent"])
+def test_ray_stream_kernels_on_simt_emulator(oracle, terrain128, scene128, kernel):
+    """k_cast_stream and k_cast_stream_persistent (warp-level ray fetch from a global counter, lane refill) through the
+    product's launch_cast: every hit record in the caller's slot, with and without a binned order, stream lengths that are
+    not multiples of the warp / chunk size, zero / axis-parallel / NaN rays that end before the loop."""
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 700, 5000):
+        rays = np.zeros(n, dtype=oracle.RAY_DTYPE)
+        rays["o"] = rng.uniform(0.9, 2.1, (n, 3)).astype(np.float32)
+        d = rng.normal(size=(n, 3))
+        rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        rays["d"][::37, 0] = 0.0
+        rays["d"][5::101] = 0.0
+        rays["d"][7::113] = np.nan
+        want, _ = oracle.cast_rays(terrain128, rays, max_depth=7, nthreads=4)
+        for order in (None, rng.permutation(n)):
+            got = scene128.launch_cast(rays, max_depth=7, kernel=kernel, order=order)
+            for k in ("id", "value", "iter"):
+                assert np.array_equal(got[k], want[k]), (kernel, n, k, order is not None)
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (kernel, n)

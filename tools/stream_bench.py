@@ -27,8 +27,9 @@ rays = torch.cat([o, d], 1).contiguous()
 hits = torch.empty((n, 4), dtype=torch.int32, device="cuda")
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 ref = None
-for sort in (0, 1, 0, 1):
+for sort, stream_kernel in ((0, 0), (1, 0), (0, 1), (1, 1), (1, 0), (1, 1)):  # stream_kernel 1 = persistent threads, warp-level ray fetch
     ctx.set_option(L.OPT_RAY_SORT, sort)
+    ctx.set_option(L.OPT_STREAM_KERNEL, stream_kernel)
     ctx.cast_device(rays.data_ptr(), n, hits.data_ptr(), depth)
     torch.cuda.synchronize()
     ctx.timer_begin()
@@ -39,5 +40,5 @@ for sort in (0, 1, 0, 1):
         ref = hits.clone()
     same = bool(torch.equal(ref, hits))
     hit_frac = float((hits[:, 0] != -1).float().mean())
-    print("size %d rays %d sort %d: %.2f ms  %.0f Mrays/s  hit %.2f  mean iter %.1f  identical %s" % (
-        size, n, sort, ms, n / ms / 1e3, hit_frac, float(hits[:, 3].float().mean()), same), flush=True)
+    print("size %d rays %d sort %d stream kernel %d: %.2f ms  %.0f Mrays/s  hit %.2f  mean iter %.1f  identical %s" % (
+        size, n, sort, stream_kernel, ms, n / ms / 1e3, hit_frac, float(hits[:, 3].float().mean()), same), flush=True)
