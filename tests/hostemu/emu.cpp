@@ -536,3 +536,73 @@ extern "C" int emu_pixel_ops(const emu_scene *s, const FrameParams *fp, int W, i
   snprintf(buf, (size_t)cap, "%s", out.c_str());
   return (int)out.size();
 }
+
+// The divergence model for a ray stream (svo_cast): rays in the given order, 32 consecutive rays per warp.
+// out[0] = issue slots of the grid-stride kernel (one ray per lane per pass, the warp waits for its slowest ray),
+// out[1] = of the persistent kernel (k_cast_stream_persistent: chunks of 256 rays per warp, lanes re-armed when >= 8 are
+// free), out[2] = 32 busy lanes, out[3] = casts, out[4] = iterations, out[5] = slowest lane per warp pass.
+extern "C" int emu_simt_stream(const emu_scene *s, const EmuRay *rays, const uint32_t *order, uint64_t n, int maxDepth, const double *costs,
+                               double *out, int nthreads) {
+  const SceneView sc = view_of(s, nullptr);
+  Costs c{costs[0], costs[1], costs[2], costs[3], costs[4], costs[5], costs[6], costs[7], costs[8], costs[9]};
+  const uint64_t chunk = 256;
+  const uint64_t nchunks = (n + chunk - 1) / chunk;
+  std::vector<Tally> tallies((size_t)std::max(1, nthreads));
+  std::vector<double> refill((size_t)std::max(1, nthreads), 0.0);
+  std::atomic<uint64_t> next(0);
+  auto work = [&](int tid) {
+    Tally &t = tallies[(size_t)tid];
+    for (;;) {
+      const uint64_t ci = next.fetch_add(1);
+      if (ci >= nchunks) break;
+      const uint64_t a = ci * chunk, b = std::min(n, a + chunk);
+      std::vector<LaneCast> lc((size_t)(b - a));
+      for (uint64_t i = a; i < b; i++) {
+        const EmuRay &r = rays[order ? order[i] : i];
+        LaneCast &l = lc[(size_t)(i - a)];
+        uint2 stk[kMaxScale + 1];
+        Trav<false> T;
+        T.setup(sc, mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]), maxDepth, false, 11, nullptr);
+        if (T.nan_ray(nullptr)) { l.early = true; continue; }
+        for (;;) {
+          const int s0 = T.scale;
+          const int status = T.step(sc, stk, nullptr);
+          if (status != TRAV_CONTINUE) { l.ops.push_back(status == TRAV_HIT ? OP_EXIT_HIT : OP_EXIT_MISS); break; }
+          l.ops.push_back(T.scale < s0 ? OP_PUSH : (T.scale > s0 ? OP_POP : OP_ADV));
+        }
+      }
+      std::vector<const LaneCast *> all;
+      for (const LaneCast &l : lc) {
+        all.push_back(&l);
+        double own = 0;
+        for (uint8_t op : l.ops) own += own_cost(c, op);
+        t.thread_ops += own + c.outside;
+        t.iters += l.ops.size();
+        t.casts++;
+      }
+      for (size_t i = 0; i < all.size(); i += 32) {
+        std::vector<const LaneCast *> w(all.begin() + (long)i, all.begin() + (long)std::min(all.size(), i + 32));
+        t.slots[0] += org_if_if(c, w, t) + c.outside;
+        double longest = 0;
+        for (const LaneCast *l : w) { double own = 0; for (uint8_t op : l->ops) own += own_cost(c, op); longest = std::max(longest, own); }
+        t.longest_lane += longest + c.outside;
+      }
+      // the persistent kernel: one warp works through the chunk; the hit records are written by the finishing lanes
+      refill[(size_t)tid] += org_refill(c, all, 1, 8) + c.outside * (double)((all.size() + 31) / 32) * 0.25;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; i++) th.emplace_back(work, i);
+  work(0);
+  for (auto &x : th) x.join();
+  for (int i = 0; i < 6; i++) out[i] = 0;
+  for (size_t i = 0; i < tallies.size(); i++) {
+    out[0] += tallies[i].slots[0];
+    out[1] += refill[i];
+    out[2] += tallies[i].thread_ops / 32.0;
+    out[3] += (double)tallies[i].casts;
+    out[4] += (double)tallies[i].iters;
+    out[5] += tallies[i].longest_lane;
+  }
+  return 0;
+}

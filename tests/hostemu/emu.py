@@ -20,7 +20,7 @@ CUDA_INCLUDE = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 def build(force: bool = False) -> str:
     stale = force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in _SRCS)
     if stale:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unknown-pragmas", "-Wno-maybe-uninitialized",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unknown-pragmas", "-Wno-maybe-uninitialized", "-Wno-uninitialized",
                                "-I" + CUDA_INCLUDE, "-o", _LIB_PATH] + _CPP + ["-lpthread"])
     return _LIB_PATH
 
@@ -54,6 +54,8 @@ def lib():
         L.emu_simt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emu_pixel_ops.restype = C.c_int
         L.emu_pixel_ops.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.emu_simt_stream.restype = C.c_int
+        L.emu_simt_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_math.restype = C.c_float
         L.emu_math.argtypes = [C.c_int, C.c_float, C.c_float]
         _lib = L
@@ -170,6 +172,19 @@ class Scene:
             for o, name in enumerate(("half_warps_idle8", "half_warps_idle16", "quarter_warps_idle8", "quarter_warps_idle16")):
                 r["refill%d_%s" % (G, name)] = float(out[35 + g * 4 + o])
         return r
+
+    def simt_stream(self, rays, costs, order=None, max_depth=13, nthreads=8):
+        """The divergence model for a ray stream: issue slots of the grid-stride and of the persistent (lane refill) kernel."""
+        from oracle import oracle as O
+        rays = np.ascontiguousarray(rays, dtype=O.RAY_DTYPE)
+        costs = np.ascontiguousarray(costs, dtype=np.float64)
+        assert costs.size == 10
+        if order is not None:
+            order = np.ascontiguousarray(order, dtype=np.uint32)
+        out = np.zeros(8, np.float64)
+        lib().emu_simt_stream(self._h, _ptr(rays), _ptr(order), rays.shape[0], max_depth, _ptr(costs), _ptr(out), nthreads)
+        return {"grid_stride": float(out[0]), "persistent": float(out[1]), "ideal": float(out[2]), "casts": int(out[3]), "iters": int(out[4]),
+                "longest_lane": float(out[5])}
 
     def pixel_ops(self, frame, width, height, x, y, box=True):
         """Path string of pixel (x, y): op letter (P/A/Q/H/M, X = ended before the loop) + scale letter per iteration."""

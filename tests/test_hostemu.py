@@ -280,3 +280,17 @@ def test_ray_stream_kernels_on_simt_emulator(oracle, terrain128, scene128, kerne
             for k in ("id", "value", "iter"):
                 assert np.array_equal(got[k], want[k]), (kernel, n, k, order is not None)
             assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (kernel, n)
+
+
+def test_simt_model_ray_stream(oracle, terrain128, scene128):
+    """The stream front end of the divergence model: counters equal the oracle's, bounds order as they must."""
+    rng = np.random.default_rng(8)
+    n = 3000
+    rays = np.zeros(n, dtype=oracle.RAY_DTYPE)
+    rays["o"] = rng.uniform(1.05, 1.95, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    _, st = oracle.cast_rays(terrain128, rays, max_depth=7, nthreads=4)
+    r = scene128.simt_stream(rays, [14, 40, 18, 31, 2, 8, 10, 300, 230, 6.5], max_depth=7)
+    assert r["casts"] == n and r["iters"] == st.iters
+    assert r["ideal"] <= r["longest_lane"] <= r["grid_stride"]
