@@ -87,7 +87,7 @@ enum svo_option {
                                * shared-memory upper levels, 5 64-thread CTAs, 6 tile + per-CTA octant binning, 7 / 8 tile +
                                * warp-local lane refill for bounce rays (4 / 2 pixels per thread), 9 parent stack in shared
                                * memory, 11 / 12 72 / 80 registers per thread, 13 variant 10 with the loop's integer work moved to
-                               * the FMA pipe (not yet measured).  All bit-exact; the others are measured ablations */
+                               * the FMA pipe, 14 variant 10 in the band-interleaved launch too (13, 14 not yet measured).  All bit-exact; the others are measured ablations */
   SVO_OPT_L2_PERSIST = 4,     /* 0/1: L2 access-policy window (persisting) over the upper octree levels, applied at the next
                                * upload; default 0 (measured: no effect, the path is not memory bound) */
   SVO_OPT_RAY_SORT = 5,       /* 0/1: trace ray streams of >= 65536 rays in (direction octant, origin Morton code) order; default 1 */
@@ -98,7 +98,8 @@ enum svo_option {
   SVO_OPT_GPU_TRANSCODE = 8,  /* 0/1: build the traversal descriptors from the uploaded stream on the device (default 1) or on
                                * the host; same result bit for bit */
   SVO_OPT_STREAM_KERNEL = 9   /* svo_cast / svo_cast_device: 0 (default) one grid-stride thread per ray; 1 persistent threads with
-                               * warp-level ray fetch -- lanes whose ray has finished are re-armed from the stream (not yet measured) */
+                               * warp-level ray fetch -- lanes whose ray has finished are re-armed from the stream; 2 the grid-stride kernel with
+                               * 16-byte stack entries (1, 2 not yet measured) */
 };
 
 /* -- lifetime: replaces Main.preRun's image/shader setup (Main.java:62-109) and

@@ -435,7 +435,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 13)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 14)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       c->opt_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
@@ -443,7 +443,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
     case SVO_OPT_GPU_TRANSCODE: c->opt_gpu_transcode = value != 0; return SVO_OK;
     case SVO_OPT_STREAM_KERNEL:
-      if (value != 0 && value != 1) return fail(c, SVO_ERR_INVALID, "unknown ray-stream kernel");
+      if (value < 0 || value > 2) return fail(c, SVO_ERR_INVALID, "unknown ray-stream kernel");
       c->opt_stream_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_BAND_ROWS:

@@ -22,7 +22,7 @@ namespace svo {
 // ---------------------------------------------------------------------------
 // (CTAs are launched top to bottom: a scrambled row order was measured 5-15 % slower -- CTAs of neighbouring rows
 // running together share their octree working set in L1/L2, which outweighs the better tail balance.)
-template <bool FAST, bool AUX, bool BOX>
+template <bool FAST, bool AUX, bool BOX, int STACK = 0>  // STACK 1: 16-byte stack entries (kernel variant 14: variant 10 with band interleaving)
 __global__ void __launch_bounds__(128, 8) k_render_tile(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
                                                      int band_stride, int band_offset, int band_ctas) {
   // A band is band_ctas consecutive CTA rows (8 image rows each).  This launch renders bands number
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128, 8) k_render_tile(SceneView sc, FrameParam
   const int band = (int)blockIdx.y / band_ctas, in_band = (int)blockIdx.y % band_ctas;
   const int y = y0 + ((band * band_stride + band_offset) * band_ctas + in_band) * 8 + (warp / warps_x) * 4 + (lane >> 3);
   if (x >= W || y >= y1) return;
-  shade_pixel<FAST, AUX, false, BOX>(sc, f, pl, W, H, x, y);
+  shade_pixel<FAST, AUX, false, BOX, false, STACK>(sc, f, pl, W, H, x, y);
 }
 
 // ---------------------------------------------------------------------------
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) k_gather_probe(const uint2 *__restrict__ 
 struct RayRec { float ox, oy, oz, dx, dy, dz; };
 struct HitRec { uint32_t id; float t; uint32_t value, iter; };
 
-template <bool FAST>
+template <bool FAST, bool WIDE = false>  // WIDE: 16-byte stack entries (SVO_OPT_STREAM_KERNEL 2)
 __global__ void __launch_bounds__(128) k_cast_stream(SceneView sc, const RayRec *__restrict__ rays, const uint32_t *__restrict__ order,
                                                      uint64_t n, HitRec *__restrict__ out, int maxDepth) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -469,7 +469,15 @@ __global__ void __launch_bounds__(128) k_cast_stream(SceneView sc, const RayRec 
     res.t = 0.0f; res.scale = 0.0f; res.dbg = 0.0f; res.dbg_init = 0;
     res.normal = mk3(0.f, 0.f, 0.f); res.voxelPos = mk3(0.f, 0.f, 0.f);
     uint32_t loops = 0;
-    const bool hit = cast_ray<FAST>(sc, mk3(ray.ox, ray.oy, ray.oz), mk3(ray.dx, ray.dy, ray.dz), maxDepth, false, 11, res, loops);
+    bool hit;
+    if (WIDE) {
+      uint4 wide[kMaxScale + 1];
+      WideStack ws;
+      ws.p = wide;
+      hit = cast_ray_on<FAST, false, false, false>(ws, sc, mk3(ray.ox, ray.oy, ray.oz), mk3(ray.dx, ray.dy, ray.dz), maxDepth, false, 11, res, loops, nullptr, true);
+    } else {
+      hit = cast_ray<FAST>(sc, mk3(ray.ox, ray.oy, ray.oz), mk3(ray.dx, ray.dy, ray.dz), maxDepth, false, 11, res, loops);
+    }
     HitRec h;
     h.id = hit ? res.pointer : kNoHit;
     h.t = hit ? res.t : 0.0f;
@@ -690,7 +698,12 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
   const dim3 grid(small_cta ? (W + 7) / 8 : (W + 15) / 16, bands > offset ? ((bands - offset + stride - 1) / stride) * band_ctas : 0);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
 #define SVO_LAUNCH_TILE(F, A, B) SVO_LAUNCH(grid, block, stream, k_render_tile<F, A, B>)(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas)
-  if (cfg.fast) {
+#define SVO_LAUNCH_TILE_WIDE(A, B) SVO_LAUNCH(grid, block, stream, k_render_tile<false, A, B, 1>)(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas)
+  if (cfg.kernel == 14 && !cfg.fast) {  // variant 10's stack entries in the band-interleaved launch (multi-GPU tile partition); not yet measured
+    if (cfg.aux) SVO_LAUNCH_TILE_WIDE(true, false);
+    else if (cfg.box) SVO_LAUNCH_TILE_WIDE(false, true);
+    else SVO_LAUNCH_TILE_WIDE(false, false);
+  } else if (cfg.fast) {
     if (cfg.aux) SVO_LAUNCH_TILE(true, true, false);
     else if (cfg.box) SVO_LAUNCH_TILE(true, false, true);
     else SVO_LAUNCH_TILE(true, false, false);
@@ -700,6 +713,7 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
     else SVO_LAUNCH_TILE(false, false, false);
   }
 #undef SVO_LAUNCH_TILE
+#undef SVO_LAUNCH_TILE_WIDE
   return cudaGetLastError();
 }
 
@@ -743,7 +757,8 @@ cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d
   uint64_t want = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)cfg.sm_count * 16u * 8u;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (cfg.fast) SVO_LAUNCH(grid, block, stream, k_cast_stream<true>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
+  if (cfg.stream_kernel == 2 && !cfg.fast) SVO_LAUNCH(grid, block, stream, k_cast_stream<false, true>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
+  else if (cfg.fast) SVO_LAUNCH(grid, block, stream, k_cast_stream<true>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
   else SVO_LAUNCH(grid, block, stream, k_cast_stream<false>)(sc, (const RayRec *)d_rays, d_order, n, (HitRec *)d_out, maxDepth);
   return cudaGetLastError();
 }

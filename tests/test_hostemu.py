@@ -228,7 +228,7 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
 
 
 KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 2: "wavefront", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
-              11: "regs72", 13: "balanced"}
+              11: "regs72", 13: "balanced", 14: "wide_bands"}
 
 
 @pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))
@@ -249,7 +249,7 @@ def test_global_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kern
             _assert_planes_equal(got, want, "kernel %d cam %s aux" % (kernel, cam))
         got = scene128.launch_render(f, W, H, kernel=kernel, aux=False, box=True)
         _assert_planes_equal(got, want, "kernel %d cam %s production" % (kernel, cam), planes=("rgba8", "depth"))
-    if kernel in (0, 5):  # interleaved bands of the multi-GPU tile partition, one launch per part
+    if kernel in (0, 5, 14):  # interleaved bands of the multi-GPU tile partition, one launch per part
         pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
         f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=7)
         want, _ = oracle.render(terrain128, f, W, H, nthreads=8)
@@ -260,7 +260,7 @@ def test_global_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kern
             _assert_planes_equal(got, want, "kernel %d interleaved %d x %d rows" % (kernel, parts, rows))
 
 
-@pytest.mark.parametrize("kernel", [0, 1], ids=["gridstride", "persistent"])
+@pytest.mark.parametrize("kernel", [0, 1, 2], ids=["gridstride", "persistent", "gridstride_wide"])
 def test_ray_stream_kernels_on_simt_emulator(oracle, terrain128, scene128, kernel):
     """k_cast_stream and k_cast_stream_persistent (warp-level ray fetch from a global counter, lane refill) through the
     product's launch_cast: every hit record in the caller's slot, with and without a binned order, stream lengths that are

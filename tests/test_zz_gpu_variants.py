@@ -27,6 +27,7 @@ if os.environ.get("SVO_TEST_UNMEASURED") == "1":
     # variant 13 (loop integer work on the FMA pipe, inline PTX) was written after the round's GPU budget was spent: bit-exact on
     # the SIMT emulator, which runs the C++ side of its helpers, not the PTX.  First thing to run on a B200.
     VARIANTS[13] = "balanced"
+    VARIANTS[14] = "wide_bands"
 
 
 @pytest.mark.parametrize("kernel", list(VARIANTS), ids=list(VARIANTS.values()))
@@ -75,10 +76,10 @@ def test_persistent_stream_kernel_bit_exact(svo, oracle, terrain512):
     want, _ = oracle.cast_rays(terrain512, rays, max_depth=9, nthreads=8)
     with svo.SvoContext(64, 64) as c:
         c.upload(terrain512)
-        c.set_option(svo._lib.OPT_STREAM_KERNEL, 1)
-        for sort in (0, 1):
+        for stream_kernel, sort in ((1, 0), (1, 1), (2, 1)):
+            c.set_option(svo._lib.OPT_STREAM_KERNEL, stream_kernel)
             c.set_option(svo._lib.OPT_RAY_SORT, sort)
             got = c.cast(rays, 9)
             for k in ("id", "value", "iter"):
-                assert np.array_equal(got[k], want[k]), (k, sort)
-            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), sort
+                assert np.array_equal(got[k], want[k]), (k, stream_kernel, sort)
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (stream_kernel, sort)

@@ -27,7 +27,7 @@ rays = torch.cat([o, d], 1).contiguous()
 hits = torch.empty((n, 4), dtype=torch.int32, device="cuda")
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 ref = None
-for sort, stream_kernel in ((0, 0), (1, 0), (0, 1), (1, 1), (1, 0), (1, 1)):  # stream_kernel 1 = persistent threads, warp-level ray fetch
+for sort, stream_kernel in ((0, 0), (1, 0), (0, 1), (1, 1), (1, 2), (1, 0), (1, 1), (1, 2)):  # stream_kernel 1 = persistent threads with warp-level ray fetch, 2 = grid-stride with 16-byte stack entries
     ctx.set_option(L.OPT_RAY_SORT, sort)
     ctx.set_option(L.OPT_STREAM_KERNEL, stream_kernel)
     ctx.cast_device(rays.data_ptr(), n, hits.data_ptr(), depth)
