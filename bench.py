@@ -173,6 +173,22 @@ def cpu_arm(nodes, size, steps, warmup, budget_s, cores):
     return rays / secs / 1e6, "rows [%d,%d) of each %dx%d frame, %d steps, cameras A/B/C cycled" % (y0, y0 + rows, W, H, steps), secs / steps * 1e3
 
 
+def other_baselines():
+    """The two baselines BASELINE.json's north star names next to the C port of castRay: probed, reported, never faked."""
+    import ctypes.util
+    import shutil
+    egl = ctypes.util.find_library("EGL")
+    java = shutil.which("java")
+    return {
+        "reference_glsl_via_egl": {"available": False, "libEGL": egl,
+                                   "why": "the reference's shader sources are not on this box (they may not be copied into the repo) and no "
+                                          "GL 4.3 harness can run them here" + ("" if egl else "; no libEGL either")},
+        "java_castRay": {"available": False, "java": java,
+                         "why": ("a JVM exists but " if java else "no JVM on this box; ") + "the reference has no CPU castRay: its traversal exists only as "
+                                "GLSL, so the scalar multi-threaded C restatement (cpu_baseline) stands in"},
+    }
+
+
 def main():
     a = parse()
     global W, H, CASTS, MODE, CAM_CYCLE
@@ -466,6 +482,7 @@ def main():
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+        out["other_baselines"] = other_baselines()
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
