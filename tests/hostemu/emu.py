@@ -56,6 +56,8 @@ def lib():
         L.emu_pixel_ops.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.emu_simt_stream.restype = C.c_int
         L.emu_simt_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_selftest.restype = C.c_int
+        L.emu_selftest.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.emu_math.restype = C.c_float
         L.emu_math.argtypes = [C.c_int, C.c_float, C.c_float]
         _lib = L
@@ -196,6 +198,13 @@ class Scene:
         out = np.zeros((height // 4, width // 4), np.float32)
         lib().emu_beam(self._h, C.byref(frame), _ptr(out), width, height)
         return out
+
+
+def selftest(blocks=3, os_threads=2):
+    """Runs the emulator's self-test kernel; returns out[block, thread, 8]."""
+    out = np.zeros((blocks, 128, 8), np.uint32)
+    lib().emu_selftest(_ptr(out), blocks, os_threads)
+    return out
 
 
 def math(fn: int, x: float, y: float = 0.0) -> float:

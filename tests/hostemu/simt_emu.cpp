@@ -99,3 +99,41 @@ void run_grid(Dim3 grid, Dim3 block, const std::function<void()> &kernel, int os
 }
 
 }  // namespace simt
+
+// ---- self-test of the emulator's collective semantics (called from tests/test_hostemu.py) -------------------------
+#include "cuda_host_shim.h"
+#define threadIdx (simt::g_threadIdx)
+#define blockIdx (simt::g_blockIdx)
+#define blockDim (simt::g_blockDim)
+namespace {
+void k_selftest(unsigned *out) {
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  unsigned *o = out + (size_t)blockIdx.x * 8u * blockDim.x + (size_t)tid * 8u;
+  // every third thread leaves at once: collectives must complete among the rest (sm_70+ semantics)
+  if (tid % 3u == 2u) { o[0] = 0xDEADu; return; }
+  o[0] = __ballot_sync(0xffffffffu, (lane & 1u) != 0u);        // exited lanes vote 0
+  o[1] = __shfl_sync(0xffffffffu, tid * 7u + 1u, __ffs(__ballot_sync(0xffffffffu, 1)) - 1);  // from the lowest live lane
+  o[2] = __reduce_add_sync(0xffffffffu, lane);
+  o[3] = (unsigned)__syncthreads_or(tid == 64u);                // one live thread of warp 2 says yes
+  __shared__ unsigned s_sum[4];
+  if (tid == 0u) s_sum[0] = s_sum[1] = s_sum[2] = s_sum[3] = 0u;
+  __syncthreads();
+  atomicAdd(&s_sum[warp], 1u);
+  __syncthreads();
+  o[4] = s_sum[warp];
+  // a loop whose trip count differs per lane, with a vote in every trip (the kernels' refill pattern)
+  unsigned trips = 0, left = lane % 5u;
+  for (;;) {
+    const bool busy = left > 0u;
+    if (busy) left--;
+    trips++;
+    if (__ballot_sync(0xffffffffu, left > 0u) == 0u) break;
+  }
+  o[5] = trips;
+}
+}  // namespace
+
+extern "C" int emu_selftest(unsigned *out, int blocks, int os_threads) {
+  simt::run_grid(simt::Dim3((unsigned)blocks), simt::Dim3(128), [&] { k_selftest(out); }, os_threads);
+  return 0;
+}

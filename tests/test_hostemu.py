@@ -294,3 +294,23 @@ def test_simt_model_ray_stream(oracle, terrain128, scene128):
     r = scene128.simt_stream(rays, [14, 40, 18, 31, 2, 8, 10, 300, 230, 6.5], max_depth=7)
     assert r["casts"] == n and r["iters"] == st.iters
     assert r["ideal"] <= r["longest_lane"] <= r["grid_stride"]
+
+
+def test_simt_emulator_collective_semantics():
+    """The emulator itself: collectives complete among the threads that have not exited, exited lanes vote 0, shuffles /
+    reductions / block-wide votes / shared memory / atomics behave like sm_70+ for full-mask calls."""
+    out = E.selftest(blocks=3, os_threads=2)
+    for b in range(3):
+        for t in range(128):
+            o = out[b, t]
+            lane, warp = t & 31, t >> 5
+            if t % 3 == 2:
+                assert o[0] == 0xDEAD and not o[1:].any()
+                continue
+            alive = [l for l in range(32) if (warp * 32 + l) % 3 != 2]
+            assert o[0] == sum(1 << l for l in alive if l & 1)
+            assert o[1] == (warp * 32 + alive[0]) * 7 + 1
+            assert o[2] == sum(alive)
+            assert o[3] == 1
+            assert o[4] == len(alive)          # shared-memory counter: one atomicAdd per live thread of the warp
+            assert o[5] == max(l % 5 for l in alive)  # loop with a vote per trip: everyone stays until the slowest lane is done
