@@ -63,6 +63,8 @@ struct svo_ctx {
   std::vector<IpcMap> ipc_maps;  // peer blocks opened by svo_ipc_import
   WaveWorkspace ws{};  // wavefront variant, allocated on first use
   void *ws_block = nullptr;
+  void *split_block = nullptr;  // variant 15: record queue
+  SplitQueue split = {};
   int ctas_per_sm = 8;
   uint64_t launches = 0;
   std::string err;
@@ -145,6 +147,17 @@ int ensure_wavefront(svo_ctx *c) {
   return SVO_OK;
 }
 
+int ensure_split(svo_ctx *c) {
+  if (c->split_block) return SVO_OK;
+  const uint64_t cap = (uint64_t)c->W * (uint64_t)c->H;
+  SVO_CUDA(c, cudaMalloc(&c->split_block, 5 * cap * sizeof(uint4) + 256));
+  uint4 *p = (uint4 *)c->split_block;
+  for (int k = 0; k < 5; k++) c->split.q[k] = p + (size_t)k * cap;
+  c->split.counters = (unsigned int *)(p + 5 * cap);
+  c->split.capacity = cap;
+  return SVO_OK;
+}
+
 SceneView scene_view(const svo_ctx *c, const svo_frame *frame = nullptr) {
   SceneView v;
   // content box of the frame (svo_transcode.h)
@@ -177,6 +190,7 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.band_ctas = c->opt_band_rows / 8;
   l.ctas_per_sm = c->ctas_per_sm;
   l.tile_counter = c->d_tile_counter;
+  l.split = c->split;
   return l;
 }
 Planes planes_of(const svo_ctx *c) {
@@ -420,6 +434,7 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_tile_counter) cudaFree(c->d_tile_counter);
   if (c->d_fence) cudaFree(c->d_fence);
   if (c->ws_block) cudaFree(c->ws_block);
+  if (c->split_block) cudaFree(c->split_block);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -435,7 +450,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 14)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 15)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       c->opt_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
@@ -548,10 +563,11 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
     c->launches += (uint64_t)wavefront_launches(fp);
     return SVO_OK;
   }
+  if (c->opt_kernel == 15 && (rc = ensure_split(c)) != SVO_OK) return rc;
   LaunchCfg cfg = launch_cfg(c);
   cfg.box = box_allowed(c, frame);
   SVO_CUDA(c, launch_render(cfg, scene_view(c, frame), fp, planes_of(c), c->W, c->H, y0, y1, c->stream));
-  c->launches++;
+  c->launches += (uint64_t)render_launches(cfg, fp);
   return SVO_OK;
 }
 int svo_render(svo_ctx *c, const svo_frame *frame) { return svo_render_rows(c, frame, 0, c ? c->H : 0); }
@@ -567,7 +583,7 @@ int svo_render_interleaved(svo_ctx *c, const svo_frame *frame, int part, int par
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
   LaunchCfg cfg = launch_cfg(c);
-  cfg.kernel = 0;  // the band-interleaved partition is a feature of the tile kernel
+  cfg.kernel = c->opt_kernel == 14 ? 14 : 0;  // the band-interleaved partition is a feature of the tile kernel (14: with wide stack entries)
   cfg.band_stride = parts;
   cfg.band_offset = part;
   cfg.box = box_allowed(c, frame);

@@ -370,6 +370,155 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_refill(SceneView sc, Fra
 }
 
 // ---------------------------------------------------------------------------
+// Kernel variant 15: the last cast of a mode-0 pixel (the diffuse bounce of the metric's configuration) in a kernel of its
+// own, with lane refill.  Lesson of variants 7 / 8: refilling pays only if the state that waits for a ray is small and
+// not in local memory.  k_split_primary is variant 10 up to the point where a pixel wants its last cast; it then appends
+// a 80-byte record -- the ray, and the nine floats + two flags the code after the cast still reads (stale normal,
+// accumulated colour, mask, mirror flag, pixel) -- to a global queue (warp-aggregated atomic) instead of tracing.
+// k_split_bounce is persistent: a warp takes 128 records, traces them with lanes re-armed when kRefillIdle are free,
+// parks each end state (six words: the iteration count is not observable in mode 0) in its record, and when the chunk
+// is done finishes its 128 pixels at full width through the same pixel_finish_cast / pixel_store as every other
+// kernel, on a Pixel rebuilt from the record (fields the last cast's shading never reads are zero).
+// ---------------------------------------------------------------------------
+constexpr unsigned kSplitChunk = 128;
+
+template <bool BOX>
+__global__ void __launch_bounds__(128, 8) k_split_primary(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1, SplitQueue q) {
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 16 + (int)(warp & 1u) * 8 + (int)(lane & 7u);
+  const int y = y0 + blockIdx.y * 8 + (int)(warp >> 1) * 4 + (int)(lane >> 3);
+  const bool valid = x < W && y < y1;
+  Pixel P;
+  bool more = valid && pixel_begin(f, pl, W, H, x, y, P);
+  bool defer = false;
+  uint4 wide[kMaxScale + 1];
+  WideStack ws;
+  ws.p = wide;
+  while (more) {
+    if (P.cast_i >= 1 && P.cast_i + 1 >= f.casts) { defer = true; break; }  // the last cast of a path: k_split_bounce traces it
+    uint32_t loops = 0;
+    const bool attrs = cast_needs_attrs(f, P);
+    const bool hit = cast_ray_on<false, false, BOX, false>(ws, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, nullptr, attrs);
+    if (!attrs && hit && f.renderMode == 0) {
+      pixel_after_last_hit(P);
+      more = false;
+    } else {
+      more = pixel_after_cast(f, P, hit, loops);
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, defer);
+  if (m != 0u) {
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(q.counters + 0, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (defer) {
+      const size_t s_ = (size_t)base + (size_t)__popc(m & ((1u << lane) - 1u));
+      const bool mirror = f.mirrorValue != 0 && P.res.value == (uint32_t)f.mirrorValue;
+      const uint32_t pix = (uint32_t)((size_t)y * (size_t)W + (size_t)x) | (mirror ? 0x80000000u : 0u);
+      q.q[0][s_] = make_uint4(__float_as_uint(P.origin.x), __float_as_uint(P.origin.y), __float_as_uint(P.origin.z), pix);
+      q.q[1][s_] = make_uint4(__float_as_uint(P.dir.x), __float_as_uint(P.dir.y), __float_as_uint(P.dir.z), __float_as_uint(P.res.normal.x));
+      q.q[2][s_] = make_uint4(__float_as_uint(P.res.normal.y), __float_as_uint(P.res.normal.z), __float_as_uint(P.acc.x), __float_as_uint(P.acc.y));
+      q.q[3][s_] = make_uint4(__float_as_uint(P.acc.z), __float_as_uint(P.mask.x), __float_as_uint(P.mask.y), __float_as_uint(P.mask.z));
+    }
+  }
+  if (valid && !defer) pixel_store<false>(sc, f, pl, W, P);
+}
+
+template <bool BOX>
+__global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FrameParams f, Planes pl, int W, SplitQueue q) {
+  const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+  const uint64_t n = (uint64_t)q.counters[0];  // written by k_split_primary, earlier in the stream
+  uint4 wide[kMaxScale + 1];
+  WideStack stk;
+  stk.p = wide;
+  for (;;) {
+    unsigned c = 0;
+    if (lane == 0) c = atomicAdd(q.counters + 1, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    const uint64_t a = (uint64_t)c * kSplitChunk;
+    if (a >= n) break;
+    const uint64_t b = a + kSplitChunk < n ? a + kSplitChunk : n;
+    // ---- trace the chunk's rays, re-arming lanes as rays finish ----
+    uint64_t head = a, mine = 0;
+    int busy = 0;
+    Trav<false, false, BOX> T;
+    for (;;) {
+      unsigned idle = __ballot_sync(0xffffffffu, !busy);
+      while (idle != 0u && head < b) {
+        const unsigned rank = __popc(idle & lt_mask);
+        if (!busy && head + rank < b) {
+          mine = head + rank;
+          const uint4 r0 = q.q[0][mine], r1 = q.q[1][mine];
+          T.setup(sc, mk3(__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z)),
+                  mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z)), f.maxDepth, true, f.coneDepth, nullptr);
+          if (T.outside_box() || T.nan_ray(nullptr)) {
+            const HitState r = T.export_hit(TRAV_MISS);
+            q.q[0][mine] = make_uint4(r.pidx, r.meta, r.ipx, r0.w);
+            q.q[4][mine] = make_uint4(r.ipy, r.ipz, __float_as_uint(r.t_min), 0u);
+          } else {
+            busy = 1;
+          }
+        }
+        const uint64_t left = b - head;
+        const unsigned take = (unsigned)__popc(idle);
+        head += left < take ? left : take;
+        idle = __ballot_sync(0xffffffffu, !busy);
+      }
+      const int busy0 = __popc(__ballot_sync(0xffffffffu, busy));
+      if (busy0 == 0) break;
+      const int limit = head < b ? max(busy0 - kRefillIdle, 0) : 0;
+      for (;;) {
+        if (busy) {
+          int status = TRAV_CONTINUE;
+#pragma unroll 1
+          for (int k = 0; k < kRefillBatch && status == TRAV_CONTINUE; k++) status = T.step(sc, stk, nullptr);
+          if (status != TRAV_CONTINUE) {
+            busy = 0;
+            const HitState r = T.export_hit(status);
+            const uint32_t pix = q.q[0][mine].w;
+            q.q[0][mine] = make_uint4(r.pidx, r.meta, r.ipx, pix);
+            q.q[4][mine] = make_uint4(r.ipy, r.ipz, __float_as_uint(r.t_min), 0u);
+          }
+        }
+        if (__popc(__ballot_sync(0xffffffffu, busy)) <= limit) break;
+      }
+    }
+    __syncwarp();
+    // ---- finish the chunk's pixels at full width ----
+#pragma unroll 1
+    for (uint64_t i = a + lane; i < b; i += 32) {
+      const uint4 r0 = q.q[0][i], r1 = q.q[1][i], r2 = q.q[2][i], r3 = q.q[3][i], r4 = q.q[4][i];
+      const uint32_t pix = r0.w & 0x7FFFFFFFu;
+      Pixel P;
+      P.x = (int)(pix % (uint32_t)W);
+      P.y = (int)(pix / (uint32_t)W);
+      P.origin = mk3(0.0f, 0.0f, 0.0f);  // dead after the last cast
+      P.dir = mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z));
+      P.cone = true;
+      P.cast_i = f.casts - 1;
+      P.acc = mk3(__uint_as_float(r2.z), __uint_as_float(r2.w), __uint_as_float(r3.x));
+      P.mask = mk3(__uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w));
+      cast_res_clear(P.res);
+      P.res.normal = mk3(__uint_as_float(r1.w), __uint_as_float(r2.x), __uint_as_float(r2.y));
+      P.res.value = (r0.w & 0x80000000u) ? (uint32_t)f.mirrorValue : ~(uint32_t)f.mirrorValue;  // only `== mirrorValue` is read
+      P.color = mk3(0.0f, 0.0f, 0.0f);
+      P.depth = 0.0f;
+      P.beamDist = 0.0f;
+      P.hit_id = kNoHit;
+      P.iter = 0;
+      P.primary_t = 0.0f;
+      HitState hs;
+      hs.pidx = r0.x; hs.meta = r0.y; hs.ipx = r0.z; hs.ipy = r4.x; hs.ipz = r4.y; hs.t_min = __uint_as_float(r4.z);
+      hs.iter = 0;  // not observable in render mode 0 without the validation planes
+      pixel_finish_cast(sc, f, P, hs);
+      pixel_store<false>(sc, f, pl, W, P);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Kernel variant 4 (experiment): variant 0 with the upper octree levels staged in shared memory.  Every CTA
 // copies the first kTopDescs descriptors (breadth-first array: levels 0..3 and part of 4) before tracing.
 // ---------------------------------------------------------------------------
@@ -614,8 +763,28 @@ __global__ void k_math_probe(int fn, const float *__restrict__ x, const float *_
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
-cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
+static bool split_applies(const LaunchCfg &cfg, const FrameParams &f) {
+  return cfg.kernel == 15 && !cfg.fast && !cfg.aux && cfg.band_stride == 0 && f.renderMode == 0 && f.casts >= 2 && cfg.split.q[0] != nullptr;
+}
+int render_launches(const LaunchCfg &cfg, const FrameParams &f) { return split_applies(cfg, f) ? 2 : 1; }
+
+cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                           int y0, int y1, cudaStream_t stream) {
+  LaunchCfg cfg = cfg_in;
+  if (split_applies(cfg, f)) {
+    if (y1 <= y0) return cudaSuccess;
+    if ((uint64_t)W * (uint64_t)(y1 - y0) > cfg.split.capacity) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(cfg.split.counters, 0, 2 * sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
+    if (cfg.box) SVO_LAUNCH(grid, 128, stream, k_split_primary<true>)(sc, f, pl, W, H, y0, y1, cfg.split);
+    else SVO_LAUNCH(grid, 128, stream, k_split_primary<false>)(sc, f, pl, W, H, y0, y1, cfg.split);
+    const int pgrid = cfg.sm_count * 8;
+    if (cfg.box) SVO_LAUNCH(pgrid, 128, stream, k_split_bounce<true>)(sc, f, pl, W, cfg.split);
+    else SVO_LAUNCH(pgrid, 128, stream, k_split_bounce<false>)(sc, f, pl, W, cfg.split);
+    return cudaGetLastError();
+  }
+  if (cfg.kernel == 15) cfg.kernel = 10;  // frames the split does not cover: the default kernel
   if (cfg.kernel == 1) {
     if (y1 <= y0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(cfg.tile_counter, 0, sizeof(unsigned int), stream);

@@ -34,6 +34,14 @@ struct Planes {
   float4 *radiance;
 };
 
+// Device workspace of kernel variant 15 (primary kernel + persistent bounce kernel): one record per deferred cast in five
+// uint4 planes of `capacity` entries (image pixels), and two counters (records queued, next chunk to hand out).
+struct SplitQueue {
+  uint4 *q[5];
+  unsigned int *counters;
+  uint64_t capacity;
+};
+
 struct LaunchCfg {
   bool fast;     // Ops<true>: fma-contracted t arithmetic
   bool aux;      // also write hit_id / iter / primary_t / radiance
@@ -45,6 +53,7 @@ struct LaunchCfg {
   int band_ctas;                 // CTA rows (8 image rows each) per band
   int ctas_per_sm;             // persistent grid = sm_count * ctas_per_sm
   unsigned int *tile_counter;  // device word: the persistent kernel's tile queue head
+  SplitQueue split;            // variant 15 only (q[0] == nullptr: not allocated)
 };
 
 constexpr int kWaveMaxStages = 64;  // casts per pixel the wavefront path supports (svo_frame.casts <= 64)
@@ -64,6 +73,8 @@ cudaError_t launch_render_wavefront(const LaunchCfg &cfg, const SceneView &sc, c
 int wavefront_launches(const FrameParams &f);
 cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                           int y0, int y1, cudaStream_t stream);
+// kernels launch_render() enqueues for this frame (variant 15: two)
+int render_launches(const LaunchCfg &cfg, const FrameParams &f);
 cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1,
                                 unsigned long long *d_counters, cudaStream_t stream);
 struct FenceList { unsigned int *p[16]; int n; };

@@ -134,6 +134,7 @@ class Scene:
                                      _ptr(out["rgba8"]), _ptr(out["depth"]), _ptr(out["hit_id"]), _ptr(out["iter"]),
                                      _ptr(out["primary_t"]), _ptr(out["radiance"]), band_stride, band_offset, band_rows, ctas, nthreads)
         assert rc == 0, rc
+        self.last_launches = int(lib().emu_last_render_launches())
         return out
 
     def launch_cast(self, rays, max_depth=13, kernel=0, order=None, ctas=2, nthreads=8):

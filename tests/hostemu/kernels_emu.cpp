@@ -20,7 +20,11 @@ using namespace svo;
 
 int emu_launch_wavefront(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1);
 
+static int g_last_launches = 0;
+
 extern "C" {
+
+int emu_last_render_launches() { return g_last_launches; }  // kernels the last emu_launch_render enqueued (variant 15: 2)
 
 // svo_render_rows through the product's launch_render on the emulator.  kernel = SVO_OPT_KERNEL, ctas = CTAs of the
 // persistent variant (sm_count * ctas_per_sm on the device).
@@ -49,6 +53,17 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   cfg.band_offset = band_offset;
   cfg.band_ctas = band_rows / 8;
   cfg.tile_counter = &tile_counter;
+  std::vector<uint4> split_planes;
+  unsigned int split_counters[2] = {0u, 0u};
+  cfg.split = SplitQueue();
+  if (kernel == 15) {  // ensure_split() of svo_capi.cu
+    const uint64_t cap = (uint64_t)W * (uint64_t)H;
+    split_planes.resize((size_t)(5 * cap));
+    for (int k = 0; k < 5; k++) cfg.split.q[k] = split_planes.data() + (size_t)k * cap;
+    cfg.split.counters = split_counters;
+    cfg.split.capacity = cap;
+  }
+  g_last_launches = render_launches(cfg, *f);
   simt::g_os_threads = (kernel == 1 || kernel == 2) ? 1 : nthreads;  // persistent kernels: the queue is consumed by whichever block runs
   if (kernel == 2) return emu_launch_wavefront(cfg, sc, *f, pl, W, H, y0, y1);  // wavefront_emu.cpp
   return (int)launch_render(cfg, sc, *f, pl, W, H, y0, y1, nullptr);
@@ -71,6 +86,7 @@ int emu_launch_cast(const emu_scene *s, const void *rays, const uint32_t *order,
   cfg.band_stride = cfg.band_offset = 0;
   cfg.band_ctas = 1;
   cfg.tile_counter = &counter;
+  cfg.split = SplitQueue();
   simt::g_os_threads = kernel == 1 ? 1 : nthreads;
   return (int)launch_cast(cfg, sc, rays, order, n, out, maxDepth, nullptr);
 }

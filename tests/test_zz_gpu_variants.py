@@ -28,6 +28,7 @@ if os.environ.get("SVO_TEST_UNMEASURED") == "1":
     # the SIMT emulator, which runs the C++ side of its helpers, not the PTX.  First thing to run on a B200.
     VARIANTS[13] = "balanced"
     VARIANTS[14] = "wide_bands"
+    VARIANTS[15] = "split"  # aux planes on: falls back to the default kernel; its own path is the production instance below
 
 
 @pytest.mark.parametrize("kernel", list(VARIANTS), ids=list(VARIANTS.values()))
@@ -83,3 +84,31 @@ def test_persistent_stream_kernel_bit_exact(svo, oracle, terrain512):
             for k in ("id", "value", "iter"):
                 assert np.array_equal(got[k], want[k]), (k, stream_kernel, sort)
             assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (stream_kernel, sort)
+
+
+@pytest.mark.skipif(os.environ.get("SVO_TEST_UNMEASURED") != "1", reason="split kernels: written after the round's GPU budget was spent")
+def test_split_kernels_bit_exact(svo, oracle, terrain512, terrain128):
+    """Kernel variant 15 (k_split_primary + k_split_bounce) on the device: colour and depth against the oracle."""
+    with svo.SvoContext(640, 360) as c:
+        c.set_option(svo._lib.OPT_KERNEL, 15)
+        c.upload(terrain512)
+        for cam in ("A", "B", "C"):
+            for casts, mirror in ((2, 0), (3, 0), (4, 1)):
+                pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+                kw = dict(frame_number=3, render_mode=0, casts=casts, mirror_value=mirror)
+                want, _ = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, **kw), 640, 360, nthreads=8, planes=("rgba8", "depth"))
+                n0 = c.launch_count()
+                c.render(svo.camera_frame(cam, **kw))
+                assert c.launch_count() - n0 == 2
+                _assert_equal({"rgba8": c.read_color_rgba8(), "depth": c.read_depth()}, want, "split cam %s casts %d" % (cam, casts), planes=("rgba8", "depth"))
+    W, H = 200, 120
+    with svo.SvoContext(W, H) as c:
+        c.set_option(svo._lib.OPT_KERNEL, 15)
+        c.upload(terrain128)
+        pos, l1, l2, r1, r2 = svo.CAMERAS["C"]
+        kw = dict(frame_number=1, render_mode=0, max_depth=7)
+        want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, **kw), W, H, nthreads=8, planes=("rgba8", "depth"))
+        f = svo.camera_frame("C", **kw)
+        for y0, y1 in ((0, 37), (37, 38), (38, H)):
+            c.render(f, y0, y1)
+        _assert_equal({"rgba8": c.read_color_rgba8(), "depth": c.read_depth()}, want, "split bands", planes=("rgba8", "depth"))
