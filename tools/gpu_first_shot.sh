@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call that answers the open questions of DESIGN.md section 7 (about 4 minutes on one B200):
-#   /usr/local/graft/bin/gpurun --timeout 420 -- 'bash tools/gpu_first_shot.sh'
+# One gpurun call that answers the open questions of DESIGN.md section 7 (about 5 minutes on one B200):
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_first_shot.sh'
 # 1. device parity of the kernel variants, including the not-yet-measured variant 13 (inline PTX)
 # 2. per-camera kernel times: default (10) against 13, 0 and the FFMA build
 # 3. if 13 is bit-exact: ncu --set full of the three bench frames under 10 and 13 (pipe utilisation, stall reasons)
