@@ -88,7 +88,8 @@ enum svo_option {
                                * warp-local lane refill for bounce rays (4 / 2 pixels per thread), 9 parent stack in shared
                                * memory, 11 / 12 72 / 80 registers per thread, 13 variant 10 with the loop's integer work moved to
                                * the FMA pipe, 14 variant 10 in the band-interleaved launch too, 15 the last cast of
-                               * mode-0 pixels in a persistent kernel of its own with lane refill (13, 14, 15 not yet measured).  All bit-exact; the others are measured ablations */
+                               * mode-0 pixels in a persistent kernel of its own with lane refill, 16 the same with the cast's set-up
+                               * done by the primary kernel (13 ... 16 not yet measured).  All bit-exact; the others are measured ablations */
   SVO_OPT_L2_PERSIST = 4,     /* 0/1: L2 access-policy window (persisting) over the upper octree levels, applied at the next
                                * upload; default 0 (measured: no effect, the path is not memory bound) */
   SVO_OPT_RAY_SORT = 5,       /* 0/1: trace ray streams of >= 65536 rays in (direction octant, origin Morton code) order; default 1 */

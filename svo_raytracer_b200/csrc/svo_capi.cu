@@ -150,10 +150,10 @@ int ensure_wavefront(svo_ctx *c) {
 int ensure_split(svo_ctx *c) {
   if (c->split_block) return SVO_OK;
   const uint64_t cap = (uint64_t)c->W * (uint64_t)c->H;
-  SVO_CUDA(c, cudaMalloc(&c->split_block, 5 * cap * sizeof(uint4) + 256));
+  SVO_CUDA(c, cudaMalloc(&c->split_block, 6 * cap * sizeof(uint4) + 256));
   uint4 *p = (uint4 *)c->split_block;
-  for (int k = 0; k < 5; k++) c->split.q[k] = p + (size_t)k * cap;
-  c->split.counters = (unsigned int *)(p + 5 * cap);
+  for (int k = 0; k < 6; k++) c->split.q[k] = p + (size_t)k * cap;
+  c->split.counters = (unsigned int *)(p + 6 * cap);
   c->split.capacity = cap;
   return SVO_OK;
 }
@@ -450,7 +450,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 15)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 16)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       c->opt_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
@@ -563,7 +563,7 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
     c->launches += (uint64_t)wavefront_launches(fp);
     return SVO_OK;
   }
-  if (c->opt_kernel == 15 && (rc = ensure_split(c)) != SVO_OK) return rc;
+  if ((c->opt_kernel == 15 || c->opt_kernel == 16) && (rc = ensure_split(c)) != SVO_OK) return rc;
   LaunchCfg cfg = launch_cfg(c);
   cfg.box = box_allowed(c, frame);
   SVO_CUDA(c, launch_render(cfg, scene_view(c, frame), fp, planes_of(c), c->W, c->H, y0, y1, c->stream));

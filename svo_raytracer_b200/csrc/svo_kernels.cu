@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_refill(SceneView sc, Fra
 // ---------------------------------------------------------------------------
 constexpr unsigned kSplitChunk = 128;
 
-template <bool BOX>
+// PRE (variant 16): the primary kernel also runs Trav::setup for the deferred cast -- at full width -- and queues its result
+// (ten words) instead of origin and direction, so that a refill in k_split_bounce is a dozen loads instead of ~230
+// instructions; casts that end before the loop (outside the content box, NaN) are finished here and never queued.
+template <bool BOX, bool PRE>
 __global__ void __launch_bounds__(128, 8) k_split_primary(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1, SplitQueue q) {
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 16 + (int)(warp & 1u) * 8 + (int)(lane & 7u);
@@ -406,6 +409,17 @@ __global__ void __launch_bounds__(128, 8) k_split_primary(SceneView sc, FramePar
       more = pixel_after_cast(f, P, hit, loops);
     }
   }
+  uint32_t w[10];
+  if (PRE && defer) {
+    Trav<false, false, BOX> T;
+    T.setup(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, nullptr);
+    if (T.outside_box() || T.nan_ray(nullptr)) {  // ends before the loop: finish the pixel here
+      pixel_finish_cast(sc, f, P, T.export_hit(TRAV_MISS));
+      defer = false;
+    } else {
+      T.save_setup(w);
+    }
+  }
   const unsigned m = __ballot_sync(0xffffffffu, defer);
   if (m != 0u) {
     unsigned base = 0;
@@ -416,16 +430,25 @@ __global__ void __launch_bounds__(128, 8) k_split_primary(SceneView sc, FramePar
       const size_t s_ = (size_t)base + (size_t)__popc(m & ((1u << lane) - 1u));
       const bool mirror = f.mirrorValue != 0 && P.res.value == (uint32_t)f.mirrorValue;
       const uint32_t pix = (uint32_t)((size_t)y * (size_t)W + (size_t)x) | (mirror ? 0x80000000u : 0u);
-      q.q[0][s_] = make_uint4(__float_as_uint(P.origin.x), __float_as_uint(P.origin.y), __float_as_uint(P.origin.z), pix);
-      q.q[1][s_] = make_uint4(__float_as_uint(P.dir.x), __float_as_uint(P.dir.y), __float_as_uint(P.dir.z), __float_as_uint(P.res.normal.x));
-      q.q[2][s_] = make_uint4(__float_as_uint(P.res.normal.y), __float_as_uint(P.res.normal.z), __float_as_uint(P.acc.x), __float_as_uint(P.acc.y));
-      q.q[3][s_] = make_uint4(__float_as_uint(P.acc.z), __float_as_uint(P.mask.x), __float_as_uint(P.mask.y), __float_as_uint(P.mask.z));
+      if (PRE) {
+        q.q[0][s_] = make_uint4(w[0], w[1], w[2], pix);
+        q.q[1][s_] = make_uint4(w[3], w[4], w[5], w[9]);
+        q.q[2][s_] = make_uint4(w[6], w[7], w[8], __float_as_uint(P.res.normal.x));
+        q.q[3][s_] = make_uint4(__float_as_uint(P.dir.x), __float_as_uint(P.dir.y), __float_as_uint(P.dir.z), __float_as_uint(P.res.normal.y));
+        q.q[4][s_] = make_uint4(__float_as_uint(P.res.normal.z), __float_as_uint(P.acc.x), __float_as_uint(P.acc.y), __float_as_uint(P.acc.z));
+        q.q[5][s_] = make_uint4(__float_as_uint(P.mask.x), __float_as_uint(P.mask.y), __float_as_uint(P.mask.z), 0u);
+      } else {
+        q.q[0][s_] = make_uint4(__float_as_uint(P.origin.x), __float_as_uint(P.origin.y), __float_as_uint(P.origin.z), pix);
+        q.q[1][s_] = make_uint4(__float_as_uint(P.dir.x), __float_as_uint(P.dir.y), __float_as_uint(P.dir.z), __float_as_uint(P.res.normal.x));
+        q.q[2][s_] = make_uint4(__float_as_uint(P.res.normal.y), __float_as_uint(P.res.normal.z), __float_as_uint(P.acc.x), __float_as_uint(P.acc.y));
+        q.q[3][s_] = make_uint4(__float_as_uint(P.acc.z), __float_as_uint(P.mask.x), __float_as_uint(P.mask.y), __float_as_uint(P.mask.z));
+      }
     }
   }
   if (valid && !defer) pixel_store<false>(sc, f, pl, W, P);
 }
 
-template <bool BOX>
+template <bool BOX, bool PRE>
 __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FrameParams f, Planes pl, int W, SplitQueue q) {
   const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
   const uint64_t n = (uint64_t)q.counters[0];  // written by k_split_primary, earlier in the stream
@@ -450,14 +473,21 @@ __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FramePara
         if (!busy && head + rank < b) {
           mine = head + rank;
           const uint4 r0 = q.q[0][mine], r1 = q.q[1][mine];
-          T.setup(sc, mk3(__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z)),
-                  mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z)), f.maxDepth, true, f.coneDepth, nullptr);
-          if (T.outside_box() || T.nan_ray(nullptr)) {
-            const HitState r = T.export_hit(TRAV_MISS);
-            q.q[0][mine] = make_uint4(r.pidx, r.meta, r.ipx, r0.w);
-            q.q[4][mine] = make_uint4(r.ipy, r.ipz, __float_as_uint(r.t_min), 0u);
+          if (PRE) {
+            const uint4 r2 = q.q[2][mine];
+            const uint32_t w[10] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r1.w};
+            T.restore_setup(sc, w, f.maxDepth, true, f.coneDepth);
+            busy = 1;  // casts that end before the loop were finished by k_split_primary
           } else {
-            busy = 1;
+            T.setup(sc, mk3(__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z)),
+                    mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z)), f.maxDepth, true, f.coneDepth, nullptr);
+            if (T.outside_box() || T.nan_ray(nullptr)) {
+              const HitState r = T.export_hit(TRAV_MISS);
+              q.q[0][mine] = make_uint4(r.pidx, r.meta, r.ipx, r0.w);
+              q.q[4][mine] = make_uint4(r.ipy, r.ipz, __float_as_uint(r.t_min), 0u);
+            } else {
+              busy = 1;
+            }
           }
         }
         const uint64_t left = b - head;
@@ -478,7 +508,7 @@ __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FramePara
             const HitState r = T.export_hit(status);
             const uint32_t pix = q.q[0][mine].w;
             q.q[0][mine] = make_uint4(r.pidx, r.meta, r.ipx, pix);
-            q.q[4][mine] = make_uint4(r.ipy, r.ipz, __float_as_uint(r.t_min), 0u);
+            q.q[PRE ? 1 : 4][mine] = make_uint4(r.ipy, r.ipz, __float_as_uint(r.t_min), 0u);
           }
         }
         if (__popc(__ballot_sync(0xffffffffu, busy)) <= limit) break;
@@ -494,13 +524,25 @@ __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FramePara
       P.x = (int)(pix % (uint32_t)W);
       P.y = (int)(pix / (uint32_t)W);
       P.origin = mk3(0.0f, 0.0f, 0.0f);  // dead after the last cast
-      P.dir = mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z));
       P.cone = true;
       P.cast_i = f.casts - 1;
-      P.acc = mk3(__uint_as_float(r2.z), __uint_as_float(r2.w), __uint_as_float(r3.x));
-      P.mask = mk3(__uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w));
       cast_res_clear(P.res);
-      P.res.normal = mk3(__uint_as_float(r1.w), __uint_as_float(r2.x), __uint_as_float(r2.y));
+      HitState hs;
+      hs.pidx = r0.x; hs.meta = r0.y; hs.ipx = r0.z;
+      if (PRE) {
+        const uint4 r5 = q.q[5][i];
+        P.dir = mk3(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z));
+        P.res.normal = mk3(__uint_as_float(r2.w), __uint_as_float(r3.w), __uint_as_float(r4.x));
+        P.acc = mk3(__uint_as_float(r4.y), __uint_as_float(r4.z), __uint_as_float(r4.w));
+        P.mask = mk3(__uint_as_float(r5.x), __uint_as_float(r5.y), __uint_as_float(r5.z));
+        hs.ipy = r1.x; hs.ipz = r1.y; hs.t_min = __uint_as_float(r1.z);
+      } else {
+        P.dir = mk3(__uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z));
+        P.res.normal = mk3(__uint_as_float(r1.w), __uint_as_float(r2.x), __uint_as_float(r2.y));
+        P.acc = mk3(__uint_as_float(r2.z), __uint_as_float(r2.w), __uint_as_float(r3.x));
+        P.mask = mk3(__uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w));
+        hs.ipy = r4.x; hs.ipz = r4.y; hs.t_min = __uint_as_float(r4.z);
+      }
       P.res.value = (r0.w & 0x80000000u) ? (uint32_t)f.mirrorValue : ~(uint32_t)f.mirrorValue;  // only `== mirrorValue` is read
       P.color = mk3(0.0f, 0.0f, 0.0f);
       P.depth = 0.0f;
@@ -508,8 +550,6 @@ __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FramePara
       P.hit_id = kNoHit;
       P.iter = 0;
       P.primary_t = 0.0f;
-      HitState hs;
-      hs.pidx = r0.x; hs.meta = r0.y; hs.ipx = r0.z; hs.ipy = r4.x; hs.ipz = r4.y; hs.t_min = __uint_as_float(r4.z);
       hs.iter = 0;  // not observable in render mode 0 without the validation planes
       pixel_finish_cast(sc, f, P, hs);
       pixel_store<false>(sc, f, pl, W, P);
@@ -764,7 +804,7 @@ __global__ void k_math_probe(int fn, const float *__restrict__ x, const float *_
 // host-side launchers
 // ---------------------------------------------------------------------------
 static bool split_applies(const LaunchCfg &cfg, const FrameParams &f) {
-  return cfg.kernel == 15 && !cfg.fast && !cfg.aux && cfg.band_stride == 0 && f.renderMode == 0 && f.casts >= 2 && cfg.split.q[0] != nullptr;
+  return (cfg.kernel == 15 || cfg.kernel == 16) && !cfg.fast && !cfg.aux && cfg.band_stride == 0 && f.renderMode == 0 && f.casts >= 2 && cfg.split.q[0] != nullptr;
 }
 int render_launches(const LaunchCfg &cfg, const FrameParams &f) { return split_applies(cfg, f) ? 2 : 1; }
 
@@ -777,14 +817,18 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
     cudaError_t e = cudaMemsetAsync(cfg.split.counters, 0, 2 * sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
-    if (cfg.box) SVO_LAUNCH(grid, 128, stream, k_split_primary<true>)(sc, f, pl, W, H, y0, y1, cfg.split);
-    else SVO_LAUNCH(grid, 128, stream, k_split_primary<false>)(sc, f, pl, W, H, y0, y1, cfg.split);
     const int pgrid = cfg.sm_count * 8;
-    if (cfg.box) SVO_LAUNCH(pgrid, 128, stream, k_split_bounce<true>)(sc, f, pl, W, cfg.split);
-    else SVO_LAUNCH(pgrid, 128, stream, k_split_bounce<false>)(sc, f, pl, W, cfg.split);
+#define SVO_LAUNCH_SPLIT(B, P)                                                                              \
+  do {                                                                                                      \
+    SVO_LAUNCH(grid, 128, stream, k_split_primary<B, P>)(sc, f, pl, W, H, y0, y1, cfg.split);                \
+    SVO_LAUNCH(pgrid, 128, stream, k_split_bounce<B, P>)(sc, f, pl, W, cfg.split);                           \
+  } while (0)
+    if (cfg.kernel == 16) { if (cfg.box) SVO_LAUNCH_SPLIT(true, true); else SVO_LAUNCH_SPLIT(false, true); }
+    else { if (cfg.box) SVO_LAUNCH_SPLIT(true, false); else SVO_LAUNCH_SPLIT(false, false); }
+#undef SVO_LAUNCH_SPLIT
     return cudaGetLastError();
   }
-  if (cfg.kernel == 15) cfg.kernel = 10;  // frames the split does not cover: the default kernel
+  if (cfg.kernel == 15 || cfg.kernel == 16) cfg.kernel = 10;  // frames the split does not cover: the default kernel
   if (cfg.kernel == 1) {
     if (y1 <= y0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(cfg.tile_counter, 0, sizeof(unsigned int), stream);

@@ -35,9 +35,9 @@ struct Planes {
 };
 
 // Device workspace of kernel variant 15 (primary kernel + persistent bounce kernel): one record per deferred cast in five
-// uint4 planes of `capacity` entries (image pixels), and two counters (records queued, next chunk to hand out).
+// (variant 16: six) uint4 planes of `capacity` entries (image pixels), and two counters (records queued, next chunk to hand out).
 struct SplitQueue {
-  uint4 *q[5];
+  uint4 *q[6];
   unsigned int *counters;
   uint64_t capacity;
 };

@@ -360,6 +360,34 @@ struct Trav {
       else if (!(tb_in <= tb_out)) tb_out = -1.0f;                         // never inside the box: ends at the first POP/ADVANCE test
     }
   }
+  // The state setup() leaves behind, in ten words, and back: lets one thread set a cast up and another one trace it
+  // (kernel variant 16).  Everything else setup() writes is a constant or follows from these and the frame.
+  __device__ __forceinline__ void save_setup(uint32_t w[10]) const {
+    w[0] = __float_as_uint(cx); w[1] = __float_as_uint(cy); w[2] = __float_as_uint(cz);
+    w[3] = __float_as_uint(bx); w[4] = __float_as_uint(by); w[5] = __float_as_uint(bz);
+    w[6] = __float_as_uint(t_min); w[7] = __float_as_uint(t_max); w[8] = BOX ? __float_as_uint(tb_out) : 0u;
+    w[9] = oct | (idx << 3);
+  }
+  __device__ __forceinline__ void restore_setup(const SceneView &sc, const uint32_t w[10], int maxDepth, bool coneTrace, int coneDepth) {
+    cx = __uint_as_float(w[0]); cy = __uint_as_float(w[1]); cz = __uint_as_float(w[2]);
+    bx = __uint_as_float(w[3]); by = __uint_as_float(w[4]); bz = __uint_as_float(w[5]);
+    t_min = __uint_as_float(w[6]); t_max = __uint_as_float(w[7]);
+    if (BOX) tb_out = __uint_as_float(w[8]);
+    oct = w[9] & 7u;
+    idx = (w[9] >> 3) & 7u;
+    h = t_max;
+    px = (idx & 1u) ? 1.5f : 1.0f;
+    py = (idx & 2u) ? 1.5f : 1.0f;
+    pz = (idx & 4u) ? 1.5f : 1.0f;
+    scale = kMaxScale - 1;
+    scale_exp2 = 0.5f;
+    pidx = 0;
+    pd = fetch(sc, 0u);
+    iter = 0.0f;
+    stop_scale = kMaxScale - maxDepth;
+    cone_stop = coneTrace ? kMaxScale - coneDepth : stop_scale;
+    if (t_min > 0.05f) stop_scale = cone_stop;
+  }
   // true if the cast can end now: nothing can be hit any more
   __device__ __forceinline__ bool outside_box() const { return BOX && t_min > tb_out; }
   // All three corner times NaN (NaN direction from a zero or 555 normal, NaN origin, or a zero direction): that does

@@ -56,10 +56,10 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   std::vector<uint4> split_planes;
   unsigned int split_counters[2] = {0u, 0u};
   cfg.split = SplitQueue();
-  if (kernel == 15) {  // ensure_split() of svo_capi.cu
+  if (kernel == 15 || kernel == 16) {  // ensure_split() of svo_capi.cu
     const uint64_t cap = (uint64_t)W * (uint64_t)H;
-    split_planes.resize((size_t)(5 * cap));
-    for (int k = 0; k < 5; k++) cfg.split.q[k] = split_planes.data() + (size_t)k * cap;
+    split_planes.resize((size_t)(6 * cap));
+    for (int k = 0; k < 6; k++) cfg.split.q[k] = split_planes.data() + (size_t)k * cap;
     cfg.split.counters = split_counters;
     cfg.split.capacity = cap;
   }

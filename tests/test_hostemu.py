@@ -149,7 +149,7 @@ def test_device_source_random_worlds_random_cameras(svo, oracle, seed):
             _assert_planes_equal(sc.render(f, W, H, box=True, aux=False), want, "box seed %d trial %d %s" % (seed, trial, kw),
                                  planes=("rgba8", "depth"))
         # the __global__ kernels with warp-level protocols, on the SIMT emulator: lane refill (7, 8), octant binning (6)
-        for kernel in (7, 8, 6, 9, 10, 13, 15):
+        for kernel in (7, 8, 6, 9, 10, 13, 15, 16):
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=True), want, "kernel %d seed %d trial %d %s" % (kernel, seed, trial, kw))
             _assert_planes_equal(sc.launch_render(f, W, H, kernel=kernel, aux=False, box=True), want,
                                  "kernel %d box seed %d trial %d %s" % (kernel, seed, trial, kw), planes=("rgba8", "depth"))
@@ -228,7 +228,7 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
 
 
 KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 2: "wavefront", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
-              11: "regs72", 13: "balanced", 14: "wide_bands", 15: "split"}
+              11: "regs72", 13: "balanced", 14: "wide_bands", 15: "split", 16: "split_presetup"}
 
 
 @pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))
@@ -316,7 +316,8 @@ def test_simt_emulator_collective_semantics():
             assert o[5] == max(l % 5 for l in alive)  # loop with a vote per trip: everyone stays until the slowest lane is done
 
 
-def test_split_kernels_on_simt_emulator(svo, oracle, terrain128, scene128):
+@pytest.mark.parametrize("kernel", [15, 16], ids=["split", "split_presetup"])
+def test_split_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kernel):
     """Kernel variant 15: k_split_primary queues the last cast of every mode-0 path, k_split_bounce traces the queue with lane
     refill and finishes the pixels from 80-byte records.  Colour and depth bit-exact for one and several bounces, the mirror
     rule, row bands, image sizes that do not divide into tiles; frames it does not cover fall back to the default kernel."""
@@ -326,18 +327,18 @@ def test_split_kernels_on_simt_emulator(svo, oracle, terrain128, scene128):
         f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=9, render_mode=0, max_depth=7, casts=casts, mirror_value=mirror)
         want, _ = oracle.render(terrain128, f, W, H, nthreads=8, planes=("rgba8", "depth"))
         for box in (True, False):
-            got = scene128.launch_render(f, W, H, kernel=15, aux=False, box=box)
+            got = scene128.launch_render(f, W, H, kernel=kernel, aux=False, box=box)
             assert scene128.last_launches == 2
             _assert_planes_equal(got, want, "split cam %s casts %d mirror %d box %s" % (cam, casts, mirror, box), planes=("rgba8", "depth"))
         got = None
         for y0, y1 in ((0, 37), (37, 38), (38, H)):
-            got = scene128.launch_render(f, W, H, y0, y1, kernel=15, aux=False, box=True, into=got)
+            got = scene128.launch_render(f, W, H, y0, y1, kernel=kernel, aux=False, box=True, into=got)
         _assert_planes_equal(got, want, "split bands cam %s" % cam, planes=("rgba8", "depth"))
     pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
     for kw in (dict(render_mode=2), dict(render_mode=0, casts=1)):  # not covered: one launch, the default kernel
         f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=9, max_depth=7, **kw)
         want, _ = oracle.render(terrain128, f, W, H, nthreads=8, planes=("rgba8", "depth"))
-        got = scene128.launch_render(f, W, H, kernel=15, aux=False, box=True)
+        got = scene128.launch_render(f, W, H, kernel=kernel, aux=False, box=True)
         assert scene128.last_launches == 1
         _assert_planes_equal(got, want, "split fallback %s" % kw, planes=("rgba8", "depth"))
     # progressive accumulation reads the previous frame's colour at the pixel: through the rebuilt Pixel too
@@ -346,6 +347,6 @@ def test_split_kernels_on_simt_emulator(svo, oracle, terrain128, scene128):
     for frame in (1, 2, 3):
         f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=frame, render_mode=0, max_depth=7, flags=1)
         want, _ = oracle.render(terrain128, f, 160, 90, nthreads=4, planes=("rgba8", "depth"), prev_rgba8=prev)
-        got = scene128.launch_render(f, 160, 90, kernel=15, aux=False, box=True, prev_rgba8=prev)
+        got = scene128.launch_render(f, 160, 90, kernel=kernel, aux=False, box=True, prev_rgba8=prev)
         assert np.array_equal(got["rgba8"], want["rgba8"]), frame
         prev = want["rgba8"]

@@ -29,6 +29,7 @@ if os.environ.get("SVO_TEST_UNMEASURED") == "1":
     VARIANTS[13] = "balanced"
     VARIANTS[14] = "wide_bands"
     VARIANTS[15] = "split"  # aux planes on: falls back to the default kernel; its own path is the production instance below
+    VARIANTS[16] = "split_presetup"
 
 
 @pytest.mark.parametrize("kernel", list(VARIANTS), ids=list(VARIANTS.values()))
@@ -87,10 +88,11 @@ def test_persistent_stream_kernel_bit_exact(svo, oracle, terrain512):
 
 
 @pytest.mark.skipif(os.environ.get("SVO_TEST_UNMEASURED") != "1", reason="split kernels: written after the round's GPU budget was spent")
-def test_split_kernels_bit_exact(svo, oracle, terrain512, terrain128):
-    """Kernel variant 15 (k_split_primary + k_split_bounce) on the device: colour and depth against the oracle."""
+@pytest.mark.parametrize("kernel", [15, 16], ids=["split", "split_presetup"])
+def test_split_kernels_bit_exact(svo, oracle, terrain512, terrain128, kernel):
+    """Kernel variants 15 / 16 (k_split_primary + k_split_bounce) on the device: colour and depth against the oracle."""
     with svo.SvoContext(640, 360) as c:
-        c.set_option(svo._lib.OPT_KERNEL, 15)
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
         c.upload(terrain512)
         for cam in ("A", "B", "C"):
             for casts, mirror in ((2, 0), (3, 0), (4, 1)):
@@ -103,7 +105,7 @@ def test_split_kernels_bit_exact(svo, oracle, terrain512, terrain128):
                 _assert_equal({"rgba8": c.read_color_rgba8(), "depth": c.read_depth()}, want, "split cam %s casts %d" % (cam, casts), planes=("rgba8", "depth"))
     W, H = 200, 120
     with svo.SvoContext(W, H) as c:
-        c.set_option(svo._lib.OPT_KERNEL, 15)
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
         c.upload(terrain128)
         pos, l1, l2, r1, r2 = svo.CAMERAS["C"]
         kw = dict(frame_number=1, render_mode=0, max_depth=7)

@@ -9,7 +9,7 @@
 mkdir -p gpurun_out
 SVO_TEST_UNMEASURED=1 timeout -k 5 120 python -m pytest tests/test_zz_gpu_variants.py -q -m gpu > gpurun_out/variants_test.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/variants_test.log
-timeout -k 5 120 python tools/kbench.py 8192 10,13,15,14,0,10,13,15,0f > gpurun_out/kbench_13.log 2>&1
+timeout -k 5 120 python tools/kbench.py 8192 10,13,15,16,14,0,10,13,15,16,0f > gpurun_out/kbench_13.log 2>&1
 if grep -q "rc=0" gpurun_out/variants_test.log; then
   timeout -k 5 150 ncu --set full --clock-control none -k regex:k_render_tile -c 6 -f -o gpurun_out/tile_10_13 python tools/ncu_ab.py 8192 ABC 10,13 > gpurun_out/ncu_10_13.log 2>&1
 fi
