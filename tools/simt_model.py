@@ -30,8 +30,9 @@ def main():
     ap.add_argument("--casts", type=int, default=2)
     ap.add_argument("--box", type=int, default=1)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
-    # SASS of k_render_tile<0,0,1>: loop head 14, PUSH 40, ADVANCE 18, POP 34, BSYNC+BRA 2, exits ~8; code outside the loop per warp cast ~700
-    ap.add_argument("--costs", default="14,40,18,34,2,8,10,700")
+    # SASS of the default kernel (variant 10, 16-byte stack entries): loop head 14, PUSH 40, ADVANCE 18, POP 31 (34 with the 8-byte
+    # entries of variant 0), BSYNC+BRA 2, exits ~8; code outside the loop per warp cast ~700
+    ap.add_argument("--costs", default="14,40,18,31,2,8,10,700")
     ap.add_argument("--shapes", type=int, default=0, help="1: also evaluate other warp tile shapes (4x8, 16x2, 32x1)")
     ap.add_argument("--out", default="", help="write the tables as markdown to this file")
     a = ap.parse_args()
