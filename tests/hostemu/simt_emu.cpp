@@ -1,4 +1,5 @@
 // simt_emu.cpp -- TEST INFRASTRUCTURE: scheduler of the coroutine SIMT emulator (see simt_emu.h).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -46,13 +47,26 @@ static void run_block(Block &b, int nthreads, const std::function<void()> &kerne
     makecontext(&b.ctx[(size_t)t], trampoline, 0);
   }
   g_block = &b;
-  // round-robin; a full round in which nobody exits and no collective completes means the block is stuck
+  // One round resumes every live thread once, each running up to its next collective: in thread order, or -- with
+  // SVO_EMU_SHUFFLE=<seed> in the environment -- in a fresh random order every round, which makes a kernel that reads what
+  // another lane wrote without a barrier in between fail instead of passing by luck of the order.
+  // A full round in which nobody exits and no collective completes means the block is stuck.
+  static const char *shuffle_env = getenv("SVO_EMU_SHUFFLE");
+  uint64_t rng = shuffle_env ? (uint64_t)strtoull(shuffle_env, nullptr, 10) * 0x9E3779B97F4A7C15ull + g_blockIdx.x * 1315423911ull + g_blockIdx.y + 1 : 0;
+  std::vector<int> order((size_t)nthreads);
+  for (int t = 0; t < nthreads; t++) order[(size_t)t] = t;
   unsigned long stuck_rounds = 0;
   while (b.alive > 0) {
+    if (shuffle_env)
+      for (int t = nthreads - 1; t > 0; t--) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        std::swap(order[(size_t)t], order[(size_t)((rng >> 33) % (uint64_t)(t + 1))]);
+      }
     const int alive0 = b.alive;
     unsigned gens0 = b.cta_bar.gen;
     for (int w = 0; w * 32 < nthreads; w++) gens0 += b.warp_bar[w].gen;
-    for (int t = 0; t < nthreads; t++) {
+    for (int k = 0; k < nthreads; k++) {
+      const int t = order[(size_t)k];
       if (b.done[(size_t)t]) continue;
       b.cur = t;
       g_threadIdx.x = (unsigned)t;
