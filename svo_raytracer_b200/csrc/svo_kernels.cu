@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FramePara
       }
       const int busy0 = __popc(__ballot_sync(0xffffffffu, busy));
       if (busy0 == 0) break;
-      const int limit = head < b ? max(busy0 - kRefillIdle, 0) : 0;
+      // with the set-up already done a refill is a dozen loads: the divergence model then prefers re-arming at 4 free lanes
+      const int limit = head < b ? max(busy0 - (PRE ? kRefillIdle / 2 : kRefillIdle), 0) : 0;
       for (;;) {
         if (busy) {
           int status = TRAV_CONTINUE;
