@@ -3,7 +3,8 @@
  * /root/reference/src/shaders/svotrace.comp (hot path) and
  * /root/reference/src/shaders/svobeam.comp:617-636 (beam pre-pass main).
  *
- * PARITY UNPINNED (see svo_oracle.h).  Arithmetic contract: oracle_math.h.
+ * Pinned bit for bit to the reference's own shaders compiled for the CPU (oracle/_ref, see svo_oracle.h and
+ * tests/test_oracle_ref.py).  Arithmetic contract: oracle_math.h.
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (oracle/Makefile).
  *
  * Interpretation choices where GLSL leaves behaviour undefined (each is

@@ -3,11 +3,19 @@
  * reference hot path, /root/reference/src/shaders/svotrace.comp, and of the
  * octree builder in /root/reference/src/engine/Octree.java.
  *
- * PARITY UNPINNED: the reference ships no golden vector, known-answer test or
- * level file for this path and neither its Java
- * host nor its GLSL can execute in this image (no JVM, no GL).  The oracle's
- * authority is line-by-line correspondence (each function cites the lines it
- * follows) plus the hand-derived known-answer tests in tests/test_oracle_kat.py.
+ * PINNED TO THE REFERENCE'S OWN CODE: the reference ships no golden vector,
+ * known-answer test or level file for this path,
+ * but its shader text compiles for the CPU: oracle/build_ref.py builds
+ * oracle/_ref/libsvo_ref.so from /root/reference/src/shaders/svotrace.comp and
+ * svobeam.comp (g++ through oracle/glsl_shim.h), and tests/test_oracle_ref.py
+ * demands that every function below equals it bit for bit (all planes of all
+ * render modes on BASELINE configs[0], single casts with every castResult
+ * field, ray streams, the iteration cap, degenerate directions, the beam
+ * pass).  tests/golden/svo_golden.npz is generated from that library.
+ * NOT pinned: the builder (Octree.java needs a JVM; svo_builder.c is a
+ * restatement checked by hand-derived known answers), and the two extensions
+ * the shipped shader has only as comments (mirror material :500-504,
+ * progressive mean :712-719).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product never does.
