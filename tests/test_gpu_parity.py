@@ -584,15 +584,16 @@ def test_random_worlds_random_cameras(svo, oracle, seed):
 
 import os as _os
 
-FULL_SIZES = [2048] + ([8192] if _os.environ.get("SVO_TEST_8192") == "1" else [])  # 8192^3 (the bench world): opt-in, ~1 min
+FULL_SIZES = [2048, 8192]  # BASELINE configs[1] and the bench world
 
 
 @pytest.mark.parametrize("size", FULL_SIZES)
 def test_full_size_properties(svo, oracle, size):
-    """BASELINE configs[1] (2048^3) -- and with SVO_TEST_8192=1 the bench world (8192^3) -- at 1920x1080 through size-independent properties: hit ids are offsets
-    of non-empty records of the stream, all kernel variants and the band partition produce the same frame, the
-    content-bounds shortcut changes nothing, rendering is deterministic, and a random sample of pixels agrees with
-    the oracle bit for bit."""
+    """BASELINE configs[1] (2048^3) and the bench world (8192^3) at 1920x1080: the FULL mode-0 frame (primary + diffuse
+    bounce, colour and depth of all 2 073 600 pixels) against the oracle bit for bit, plus size-independent properties: hit
+    ids are offsets of non-empty records of the stream, all kernel variants and the band partition produce the same
+    frame, the content-bounds shortcut changes nothing, rendering is deterministic, and a random sample of primary rays
+    agrees with the oracle in id, iteration count and t."""
     W, H, depth = 1920, 1080, min(13, int(np.log2(size)))
     hm, mm = svo.terrain_inputs(size)
     nodes = svo.build_terrain(hm, mm, size, 1024)  # the product's generator (byte-equal to the oracle's, test_builder.py)
@@ -631,7 +632,11 @@ def test_full_size_properties(svo, oracle, size):
             ref_rgba, ref_depth = c.read_color_rgba8(), c.read_depth()
             c.render(f0)
             assert np.array_equal(c.read_color_rgba8(), ref_rgba)  # deterministic
-            for kernel in (2, 6, 1):
+            full, _ = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=depth), W, H,
+                                    nthreads=_os.cpu_count() or 8, planes=("rgba8", "depth"))
+            assert np.array_equal(ref_rgba, full["rgba8"]), "full frame colour differs from the oracle (%d^3, cam %s)" % (size, cam)
+            assert np.array_equal(ref_depth.view(np.uint32), full["depth"].view(np.uint32)), "full frame depth differs (%d^3, cam %s)" % (size, cam)
+            for kernel in (10, 2, 6, 1):
                 c.set_option(svo._lib.OPT_KERNEL, kernel)
                 c.render(f0)
                 assert np.array_equal(c.read_color_rgba8(), ref_rgba), (cam, kernel)

@@ -22,14 +22,11 @@ def _assert_equal(got, want, what, planes=PLANES):
 
 import os
 
-VARIANTS = {7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack", 11: "regs72", 12: "regs80"}
-if os.environ.get("SVO_TEST_UNMEASURED") == "1":
-    # variant 13 (loop integer work on the FMA pipe, inline PTX) was written after the round's GPU budget was spent: bit-exact on
-    # the SIMT emulator, which runs the C++ side of its helpers, not the PTX.  First thing to run on a B200.
-    VARIANTS[13] = "balanced"
-    VARIANTS[14] = "wide_bands"
-    VARIANTS[15] = "split"  # aux planes on: falls back to the default kernel; its own path is the production instance below
-    VARIANTS[16] = "split_presetup"
+VARIANTS = {7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack", 11: "regs72", 12: "regs80",
+            13: "balanced",  # loop integer work on the FMA pipe (inline PTX)
+            14: "wide_bands",
+            15: "split",  # aux planes on: falls back to the default kernel; its own path is the production instance below
+            16: "split_presetup"}
 
 
 @pytest.mark.parametrize("kernel", list(VARIANTS), ids=list(VARIANTS.values()))
@@ -63,7 +60,6 @@ def test_kernel_variants_bit_exact(svo, oracle, terrain512, terrain128, kernel):
             _assert_equal(_planes(c), want, "kernel %d terrain128 cam %s casts %d" % (kernel, cam, casts))
 
 
-@pytest.mark.skipif(os.environ.get("SVO_TEST_UNMEASURED") != "1", reason="persistent ray-stream kernel: written after the round's GPU budget was spent")
 def test_persistent_stream_kernel_bit_exact(svo, oracle, terrain512):
     """SVO_OPT_STREAM_KERNEL 1 (persistent threads, warp-level ray fetch) against the oracle and the grid-stride kernel."""
     rng = np.random.default_rng(42)
@@ -87,7 +83,6 @@ def test_persistent_stream_kernel_bit_exact(svo, oracle, terrain512):
             assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), (stream_kernel, sort)
 
 
-@pytest.mark.skipif(os.environ.get("SVO_TEST_UNMEASURED") != "1", reason="split kernels: written after the round's GPU budget was spent")
 @pytest.mark.parametrize("kernel", [15, 16], ids=["split", "split_presetup"])
 def test_split_kernels_bit_exact(svo, oracle, terrain512, terrain128, kernel):
     """Kernel variants 15 / 16 (k_split_primary + k_split_bounce) on the device: colour and depth against the oracle."""

@@ -7,7 +7,9 @@
 # 4. the ray-stream kernels (grid-stride against persistent threads with warp-level ray fetch) on 16 Mi incoherent rays
 # 5. the bench line and its ncu launch list with the library default
 mkdir -p gpurun_out
-SVO_TEST_UNMEASURED=1 timeout -k 5 120 python -m pytest tests/test_zz_gpu_variants.py -q -m gpu > gpurun_out/variants_test.log 2>&1
+timeout -k 5 400 python -m pytest tests -q -m gpu -x > gpurun_out/r02_gpu_tests_first.log 2>&1
+echo "full pytest rc=$?" >> gpurun_out/r02_gpu_tests_first.log
+timeout -k 5 200 python -m pytest tests/test_zz_gpu_variants.py -q -m gpu > gpurun_out/variants_test.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/variants_test.log
 timeout -k 5 120 python tools/kbench.py 8192 10,13,15,16,14,0,10,13,15,16,0f > gpurun_out/kbench_13.log 2>&1
 if grep -q "rc=0" gpurun_out/variants_test.log; then
@@ -16,4 +18,4 @@ fi
 timeout -k 5 120 python tools/stream_bench.py 8192 16777216 > gpurun_out/stream_bench.log 2>&1  # grid-stride vs persistent ray-stream kernel
 timeout -k 5 180 python bench.py --steps 300 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 timeout -k 5 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-tail -n 4 gpurun_out/variants_test.log gpurun_out/kbench_13.log
+tail -n 6 gpurun_out/r02_gpu_tests_first.log gpurun_out/variants_test.log gpurun_out/kbench_13.log gpurun_out/stream_bench.log
