@@ -14,16 +14,26 @@ Rays = intersectOctree calls actually issued.
              back into pinned host memory each step (what Main.java does per frame)
   roofline   algorithmic bytes of the reference layout (7 B root + every child
              record the reference fetches + 8 B/pixel output) / kernel time,
-             against the measured HBM copy peak; plus the random-sector gather
-             roofline of SURVEY 8d
-  cpu_baseline  the CPU oracle (a port of the reference shader; the reference's
-             own Java/GLSL cannot run here) on the host cores, bounded sample
+             against the measured HBM copy peak; plus what actually bounds the
+             kernel: issue slots and active lanes (from the ncu capture
+             tools/profile_bench.sh makes of this same command) and the L1-miss
+             sector rate against the measured gather rates
+  cpu_baseline  the reference's own shader compiled for the CPU (oracle/_ref,
+             kind "reference") -- or the C restatement (kind "port") where that
+             library is absent -- on the host cores, bounded sample; its planes are
+             compared with the frames the GPU has just been timed on ("parity")
+  N > 1      ONE frame per step split into interleaved 8-row bands over the ranks
+             (replicated octree); peers store straight into rank 0's planes over
+             NVLink and the render kernel's last CTA bumps the frame-complete fence:
+             strong scaling, the north-star layout.  `--partition frames` keeps the
+             replica mode (rank r renders its own progressive sample; weak scaling).
 
-`--impl reference` times that CPU oracle as the reference arm.
+`--impl reference` times the CPU arm alone (rank 0; no CUDA library is mapped).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -38,6 +48,14 @@ sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
 CAM_CYCLE = ("A", "B", "C")
+CASTS, MODE = 2, 0
+NO_HIT = 0xFFFFFFFF
+
+# the three camera poses of SURVEY.md section 8d (== svo_raytracer_b200/cameras.py; repeated here so that the reference
+# arm does not import the product package)
+_FWD = ((-1.6, -0.9, -1.0), (-1.6, 0.9, -1.0), (1.6, -0.9, -1.0), (1.6, 0.9, -1.0))
+_DOWN = ((-0.8, -1.0, -0.45), (-0.8, -1.0, 0.45), (0.8, -1.0, -0.45), (0.8, -1.0, 0.45))
+CAMERAS = {"A": ((1.5, 1.5, 2.0),) + _FWD, "B": ((1.5, 1.3, 2.0),) + _FWD, "C": ((1.5, 1.6, 1.5),) + _DOWN}
 
 
 def parse():
@@ -48,40 +66,112 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=int(os.environ.get("SVO_BENCH_SIZE", "8192")), help="world edge in voxels")
     ap.add_argument("--fast-math", type=int, default=0, help="1: fma-contracted kernels (not bit-exact)")
-    ap.add_argument("--kernel", type=int, default=10, help="SVO_OPT_KERNEL (10 = the library default)")
+    ap.add_argument("--kernel", type=int, default=-1, help="SVO_OPT_KERNEL (-1 = the library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--camera", default="cycle", choices=["cycle", "A", "B", "C"], help="camera pose per step (default: A, B, C cycled)")
     ap.add_argument("--casts", type=int, default=2, help="mode-0 loop count (reference: 2 = primary + 1 diffuse bounce)")
     ap.add_argument("--mode", type=int, default=0, help="render mode (0 = the GI path of the metric; 2 = the engine's default)")
+    ap.add_argument("--mirror", type=int, default=0, help="svo_frame.mirrorValue (config 3: 4 with --world blobs)")
+    ap.add_argument("--world", default="terrain", choices=["terrain"], help="synthetic world")
+    ap.add_argument("--accumulate", type=int, default=0, help="1: progressive running mean (svo_frame.flags bit 0), frameNumber = step + 1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
-    ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
-                    help="N>1: frames = rank r renders progressive sample s*N+r of each view (weak scaling, no collective); "
-                         "tiles = ONE frame per step split in interleaved 8-row bands, peers store straight into rank 0's "
-                         "planes over NVLink (CUDA IPC) + one NCCL fence per frame (strong scaling)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
+                    help="N>1: tiles (default) = ONE frame per step split in interleaved bands, peers store straight into rank 0's "
+                         "planes over NVLink (CUDA IPC), frame-complete fence bumped by the render kernel (strong scaling); "
+                         "frames = rank r renders progressive sample s*N+r of each view (weak scaling, no exchange)")
+    ap.add_argument("--world-cache", default=os.environ.get("SVO_BENCH_WORLD_CACHE", "/dev/shm"),
+                    help="directory for the generated world (built once per box, shared by ranks and by the reference arm); '' disables")
+    ap.add_argument("--profile-json", default=os.path.join(ROOT, "profiles", "r02_bench_kernel.json"),
+                    help="ncu summary of this command's render kernel (tools/profile_bench.sh) for roofline.issue / lanes / traffic")
     return ap.parse_args()
 
 
-def world(size: int, nthreads: int = 0):
-    """Synthetic heightmap world, built by the product's own generator (host code; every rank builds its replica)."""
-    import svo_raytracer_b200 as svo
+# ---- world ------------------------------------------------------------------------------------------------------
+def _worldgen():
+    """Host-only world generation (svo_terrain_generate, svo_build_terrain) from its own small library, so that the
+    reference arm never maps the CUDA library."""
+    path = os.path.join(ROOT, "svo_raytracer_b200", "libsvo_worldgen.so")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "svo_raytracer_b200", "libsvo_b200.so")  # same functions (older build)
+    L = C.CDLL(path)
+    L.svo_terrain_generate.restype = C.c_int
+    L.svo_terrain_generate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.svo_build_terrain.restype = C.c_int
+    L.svo_build_terrain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+    return L
+
+
+def build_world(size: int, nthreads: int = 0) -> np.ndarray:
+    L = _worldgen()
+    hm = np.empty((size, size), np.uint16)
+    mm = np.empty((size, size), np.uint8)
+    if L.svo_terrain_generate(size, 1, hm.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), nthreads) != 0:
+        raise RuntimeError("svo_terrain_generate failed")
+    need = C.c_uint64()
+    chunk = min(size, 1024)
+    if L.svo_build_terrain(hm.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), size, chunk, None, 0, C.byref(need), nthreads) != 0:
+        raise RuntimeError("svo_build_terrain(size) failed")
+    out = np.empty(int(need.value), np.uint8)
+    if L.svo_build_terrain(hm.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), size, chunk, out.ctypes.data_as(C.c_void_p), out.size,
+                           C.byref(need), nthreads) != 0:
+        raise RuntimeError("svo_build_terrain failed")
+    return out
+
+
+def world(size: int, cache_dir: str, rank: int = 0, barrier=None, nthreads: int = 0):
+    """The synthetic heightmap world (node stream in the engine's layout).  Built ONCE per box by whoever gets there first
+    and kept in `cache_dir` (default /dev/shm): at N ranks rank 0 builds while the others wait, and later runs on the same
+    box -- the other N of a scaling sweep, the reference arm -- map the file.  Returns (nodes, seconds, how)."""
     t0 = time.time()
-    hm, mm = svo.terrain_inputs(size, nthreads=nthreads)
-    nodes = svo.build_terrain(hm, mm, size, min(size, 1024), nthreads=nthreads)
-    return nodes, time.time() - t0
+    path = os.path.join(cache_dir, "svo_bench_world_terrain_%d_seed1.u8" % size) if cache_dir else None
+    if path and os.path.exists(path):
+        if barrier:
+            barrier()
+        return np.memmap(path, dtype=np.uint8, mode="r"), time.time() - t0, "cached"
+    nodes = None
+    if rank == 0:
+        nodes = build_world(size, nthreads)
+        if path:
+            try:
+                tmp = path + ".tmp.%d" % os.getpid()
+                nodes.tofile(tmp)
+                os.replace(tmp, path)
+            except OSError:
+                path = None
+    if barrier:
+        barrier()
+    if nodes is None:
+        nodes = np.memmap(path, dtype=np.uint8, mode="r") if path and os.path.exists(path) else build_world(size, nthreads)
+    return nodes, time.time() - t0, "built"
 
 
-CASTS, MODE = 2, 0
+def depth_for(size: int) -> int:
+    return min(13, max(1, int(np.log2(size))))  # MAX_DEPTH = log2 N (13 for the reference's 8192^3, svotrace.comp:40)
 
 
-def frame_for(step: int, size: int):
-    import svo_raytracer_b200 as svo
-    depth = min(13, max(1, int(np.log2(size))))  # MAX_DEPTH = log2 N (13 for the reference's 8192^3, svotrace.comp:40)
-    return svo.camera_frame(CAM_CYCLE[step % len(CAM_CYCLE)], frame_number=step + 1, render_mode=MODE,
-                            max_depth=depth, casts=CASTS, cone_depth=11)
+def frame_params(step: int, size: int, a) -> dict:
+    cam = CAM_CYCLE[step % len(CAM_CYCLE)]
+    pos, l1, l2, r1, r2 = CAMERAS[cam]
+    return dict(cam_pos=pos, l1=l1, l2=l2, r1=r1, r2=r2, frame_number=step + 1, render_mode=MODE, max_depth=depth_for(size), casts=CASTS,
+                cone_depth=11, mirror_value=a.mirror, flags=1 if a.accumulate else 0)
+
+
+def config_of(a, world_size: int, tree_bytes: int, partition: str) -> dict:
+    """The workload, in the same words for both arms (the driver compares the two dicts)."""
+    what = "primary + %d diffuse bounce%s" % (CASTS - 1, "s" if CASTS > 2 else "") if MODE == 0 else "render mode %d" % MODE
+    return {
+        "workload": "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode %d (%s), %s" % (
+            a.size, W, H, MODE, what, "cameras A/B/C cycled" if a.camera == "cycle" else "camera " + a.camera),
+        "size": a.size, "width": W, "height": H, "render_mode": MODE, "casts": CASTS, "mirror_value": a.mirror,
+        "accumulate": a.accumulate, "cameras": list(CAM_CYCLE) if a.camera == "cycle" else [a.camera], "tree_bytes": int(tree_bytes),
+        "partition": partition if world_size > 1 else "single GPU",
+        "l2_policy": ("inputs larger than L2 (octree %.2f GB, 3 camera poses cycled); no flush between steps" % (tree_bytes / 1e9))
+        if tree_bytes > 126e6 else "octree fits L2; camera poses cycled; no flush",
+    }
 
 
 class ClockSampler:
@@ -142,50 +232,77 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_arm(nodes, size, steps, warmup, budget_s, cores):
-    """The CPU oracle (port of svotrace.comp) on the host cores; bounded sample of the same workload."""
+# ---- CPU arm ----------------------------------------------------------------------------------------------------
+def cpu_arm(nodes, a, steps, warmup, budget_s, cores, keep_planes=False):
+    """The reference's own shader compiled for the CPU (oracle/_ref) -- or, where that library is absent, the C
+    restatement -- on the host cores; bounded sample of the same workload.  Returns (Mrays/s, kind, sample text,
+    ms per step, {step: (y0, y1, planes)})."""
     from oracle import oracle as O
     O.build()
-    # bounded sample: every `stride`-th row block of each frame, sized from a pilot run
-    def run(step, y0, y1):
-        f = frame_for(step, size)
-        of = O.make_frame(list(f.camPos), list(f.l1), list(f.l2), list(f.r1), list(f.r2), frame_number=f.frameNumber,
-                          render_mode=f.renderMode, max_depth=f.maxDepth, casts=f.casts, cone_depth=f.coneDepth)
+    R = None
+    if a.mirror == 0 and not a.accumulate:  # the shipped shader has neither (both are comments upstream)
+        try:
+            from oracle import ref as Rmod
+            if Rmod.available():
+                Rmod.lib()
+                R = Rmod
+        except Exception:
+            R = None
+    kind = "reference" if R is not None else "port"
+    ray_cache = {}
+
+    def rays_of(of, key, y0, y1):  # rays = casts issued; counted once per (camera, rows), untimed, by the restatement's counters
+        if key not in ray_cache:
+            _, st = O.render(nodes, of, W, H, y0=y0, y1=y1, nthreads=cores, planes=())
+            ray_cache[key] = st.casts
+        return ray_cache[key]
+
+    def run(step, y0, y1, keep=False):
+        fp = frame_params(step, a.size, a)
+        of = O.make_frame(fp["cam_pos"], fp["l1"], fp["l2"], fp["r1"], fp["r2"], frame_number=fp["frame_number"], render_mode=fp["render_mode"],
+                          max_depth=fp["max_depth"], casts=fp["casts"], cone_depth=fp["cone_depth"], mirror_value=fp["mirror_value"], flags=0)
+        n = rays_of(of, (step % len(CAM_CYCLE), y0, y1), y0, y1)
         t0 = time.perf_counter()
-        _, st = O.render(nodes, of, W, H, y0=y0, y1=y1, nthreads=cores, planes=("rgba8", "depth"))
-        return st.casts, time.perf_counter() - t0
-    rows = 40
-    pilot_rays, pilot_t = 0, 0.0
+        if R is not None:
+            planes = R.render(nodes, of, W, H, y0=y0, y1=y1, nthreads=cores, planes=("rgba8", "depth"))
+        else:
+            planes, _ = O.render(nodes, of, W, H, y0=y0, y1=y1, nthreads=cores, planes=("rgba8", "depth"))
+        return n, time.perf_counter() - t0, (planes if keep else None)
+
+    rows = min(40, H)
+    pilot_t = 0.0
     for s in range(3):
-        r, t = run(s, H // 2 - rows // 2, H // 2 + rows // 2)
-        pilot_rays += r
+        _, t, _ = run(s, H // 2 - rows // 2, H // 2 - rows // 2 + rows)
         pilot_t += t
     per_step_budget = budget_s / max(1, steps + warmup)
     rows = int(max(8, min(H, rows * per_step_budget / max(pilot_t / 3, 1e-6))))
     y0 = (H - rows) // 2
     for s in range(warmup):
         run(s, y0, y0 + rows)
-    rays, secs = 0, 0.0
+    rays, secs, kept = 0, 0.0, {}
     for s in range(steps):
-        r, t = run(warmup + s, y0, y0 + rows)
+        r, t, planes = run(warmup + s, y0, y0 + rows, keep_planes)
         rays += r
         secs += t
-    return rays / secs / 1e6, "rows [%d,%d) of each %dx%d frame, %d steps, cameras A/B/C cycled" % (y0, y0 + rows, W, H, steps), secs / steps * 1e3
+        if planes is not None:
+            kept[warmup + s] = (y0, y0 + rows, planes)
+    sample = "rows [%d,%d) of each %dx%d frame, %d steps, cameras %s" % (y0, y0 + rows, W, H, steps, "/".join(CAM_CYCLE[:3]))
+    return rays / secs / 1e6, kind, sample, secs / steps * 1e3, kept
 
 
 def other_baselines():
-    """The two baselines BASELINE.json's north star names next to the C port of castRay: probed, reported, never faked."""
+    """The two baselines BASELINE.json's north star names next to the CPU arm: probed, reported, never faked."""
     import ctypes.util
     import shutil
     egl = ctypes.util.find_library("EGL")
     java = shutil.which("java")
     return {
         "reference_glsl_via_egl": {"available": False, "libEGL": egl,
-                                   "why": "the reference's shader sources are not on this box (they may not be copied into the repo) and no "
-                                          "GL 4.3 harness can run them here" + ("" if egl else "; no libEGL either")},
+                                   "why": "no GL 4.3 compute context can be created on this box" + ("" if egl else " (no libEGL)") +
+                                          "; the reference's GLSL runs instead on the CPU, compiled by g++ (cpu_baseline kind 'reference')"},
         "java_castRay": {"available": False, "java": java,
                          "why": ("a JVM exists but " if java else "no JVM on this box; ") + "the reference has no CPU castRay: its traversal exists only as "
-                                "GLSL, so the scalar multi-threaded C restatement (cpu_baseline) stands in"},
+                                "GLSL, which is what cpu_baseline runs"},
     }
 
 
@@ -199,21 +316,23 @@ def main():
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    what = "primary + %d diffuse bounce%s" % (CASTS - 1, "s" if CASTS > 2 else "") if MODE == 0 else "render mode %d" % MODE
-    workload = "%d^3 synthetic heightmap terrain SVO, %dx%d, render mode %d (%s), %s" % (
-        a.size, W, H, MODE, what, "cameras A/B/C cycled" if a.camera == "cycle" else "camera " + a.camera)
+    partition = ("tiles" if a.partition == "auto" else a.partition) if max(world_size, a.gpus) > 1 else "single GPU"
+    metric = "Mrays/s (primary + diffuse bounce)"
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        nodes, _ = world(a.size)
-        v, sample, ms = cpu_arm(nodes, a.size, a.steps, a.warmup, 120.0, cores)
+        nodes, build_s, how = world(a.size, a.world_cache)
+        v, kind, sample, ms, _ = cpu_arm(nodes, a, a.steps, a.warmup, 120.0, cores)
         print(json.dumps({
-            "impl": "reference", "metric": "Mrays/s (primary + diffuse bounce)", "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "tree_bytes": int(nodes.size)},
-            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "impl": "reference", "metric": metric, "value": v, "unit": "Mrays/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if partition == "tiles" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(a, max(world_size, a.gpus), nodes.size, partition),
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample,
+                             "what": "svotrace.comp compiled for the CPU by g++ (oracle/build_ref.py)" if kind == "reference" else "C restatement of svotrace.comp (oracle/svo_oracle.c)"},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "world": {"how": how, "seconds": round(build_s, 2)}}))
         return 0
 
     import torch
@@ -228,23 +347,36 @@ def main():
     dev = local_rank if world_size > 1 else 0
     torch.cuda.set_device(dev)
 
-    nodes, build_s = world(a.size, max(1, cores // world_size))
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nodes, build_s, world_how = world(a.size, a.world_cache, rank, (lambda: dist.barrier()) if dist is not None else None,
+                                      max(1, cores // world_size))
     ctx = svo.SvoContext(W, H, device=dev)
     ctx.set_option(L.OPT_FAST_MATH, a.fast_math)
-    ctx.set_option(L.OPT_KERNEL, a.kernel)
+    if a.kernel >= 0:
+        ctx.set_option(L.OPT_KERNEL, a.kernel)
+    kernel_id = ctx.get_option(L.OPT_KERNEL)
     ctx.set_option(L.OPT_BAND_ROWS, a.band_rows)
     t0 = time.time()
-    ctx.upload(nodes)
+    ctx.upload(np.ascontiguousarray(nodes))
     upload_s = time.time() - t0
     info = ctx.scene_info()
 
-    tiles = world_size > 1 and a.partition == "tiles"
+    def frame_for(s):
+        fp = frame_params(s, a.size, a)
+        return svo.make_frame(fp["cam_pos"], fp["l1"], fp["l2"], fp["r1"], fp["r2"], frame_number=fp["frame_number"], render_mode=fp["render_mode"],
+                              max_depth=fp["max_depth"], casts=fp["casts"], cone_depth=fp["cone_depth"], mirror_value=fp["mirror_value"], flags=fp["flags"])
+
+    tiles = world_size > 1 and partition == "tiles"
     total = a.warmup + a.steps
+    PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
     if tiles:
         # ONE frame per step, image bands interleaved over the ranks, replicated octree.  Rank 0 owns the frame
         # buffer; every peer maps it (CUDA IPC over NVLink) and its kernel stores its bands straight into it.
-        frames = [frame_for(s, a.size) for s in range(total)]
-        PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
+        frames = [frame_for(s) for s in range(total + 3)]
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         drain = lambda: None
         if a.fence == "nccl":
@@ -264,8 +396,9 @@ def main():
                     dist.all_reduce(fence)  # the frame has been consumed: peers may overwrite the planes
         else:
             # No collective in the data path.  Rank 0 owns TWO colour/depth sets; frame k goes to set k&1, so two
-            # frames are in flight.  Fences are counters in GPU memory bumped by remote atomics over NVLink
-            # (svo_fence_*): slot 2+(k&1) of rank 0's counter = "bands of frame k stored" (complete at (k//2+1)*N),
+            # frames are in flight.  Fences are counters in GPU memory bumped by remote atomics over NVLink:
+            # slot 2+(k&1) of rank 0's counter = "bands of frame k stored" (complete at (k//2+1)*N) -- bumped by the
+            # LAST CTA of each rank's render kernel (svo_render_interleaved_signal: one launch per rank and frame) --
             # slot 0 of every peer's counter = "frames consumed by rank 0".
             handles = [ctx.ipc_export(p | s) for s in (0, L.PLANE_BACK) for p in PL] if rank == 0 else [None] * 4
             dist.broadcast_object_list(handles, src=0)
@@ -298,16 +431,14 @@ def main():
                 state["k"] = k + 1
                 if rank == 0:
                     bind(k)
-                    ctx.render_interleaved(frames[s], 0, world_size)
-                    ctx.fence_signal((), slot=2 + (k & 1))
+                    ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=2 + (k & 1))
                     if state["pending"] is not None:
                         finish(*state["pending"])
                     state["pending"] = (k, consume)
                 else:
                     ctx.fence_wait(max(k - 1, 0), slot=0)  # rank 0 has consumed frames 0..k-2: set k&1 is free
                     bind(k)
-                    ctx.render_interleaved(frames[s], rank, world_size)
-                    ctx.fence_signal(owner_fence, slot=2 + (k & 1))
+                    ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=2 + (k & 1))
 
             def drain():
                 if rank == 0 and state["pending"] is not None:
@@ -315,12 +446,13 @@ def main():
                     state["pending"] = None
     else:
         # Units: rank r renders its own progressive sample (frameNumber) of the same views -- independent units, no
-        # data-path collective (weak scaling); step s on rank r is sample s*N + r.
+        # data-path exchange (weak scaling); step s on rank r is sample s*N + r.
         def my_frame(s):
-            f = frame_for(s, a.size)
-            f.frameNumber = s * world_size + rank + 1
+            f = frame_for(s)
+            if not a.accumulate:
+                f.frameNumber = s * world_size + rank + 1
             return f
-        frames = [my_frame(s) for s in range(total)]
+        frames = [my_frame(s) for s in range(total + 3)]
 
         drain = lambda: None
 
@@ -329,19 +461,18 @@ def main():
             if consume is not None:
                 consume()
 
-    # rays per frame and algorithmic bytes (instrumented kernel, outside the timed region; casts do not depend on the
+    # rays per frame and algorithmic bytes (instrumented kernels, outside the timed region; casts do not depend on the
     # RNG sample: a bounce is cast iff the primary ray hit)
-    per_cam = {}
+    per_cam, per_cam_exec = {}, {}
     for ci, cam in enumerate(CAM_CYCLE):
-        per_cam[cam] = ctx.render_stats(frames[ci])
+        f = frame_for(ci)
+        f.flags = 0
+        per_cam[cam] = ctx.render_stats(f)
+        per_cam_exec[cam] = ctx.render_stats_executed(f)
     rays_per_step = [per_cam[CAM_CYCLE[s % 3]]["casts"] for s in range(total)]
     alg_bytes_per_step = [per_cam[CAM_CYCLE[s % 3]]["record_bytes"] + 8 * W * H for s in range(total)]
     iters_per_step = [per_cam[CAM_CYCLE[s % 3]]["iters"] for s in range(total)]
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    exec_iters_per_step = [per_cam_exec[CAM_CYCLE[s % 3]]["iters"] for s in range(total)]
 
     def reduce_max(v):
         if dist is None:
@@ -366,11 +497,12 @@ def main():
     dev_ms = ctx.timer_end()
     clocks.end()
     launches = ctx.launch_count() - launches0
+    ctx.sync()  # raises if a frame-complete fence ran into its watchdog: the frames would be incomplete
     barrier()
     clk = clocks.stop()
     max_ms = reduce_max(dev_ms)
     step_rays = float(sum(rays_per_step[a.warmup:]))
-    all_rays = step_rays if tiles else step_rays * world_size  # frames mode: every rank casts a full frame per step
+    all_rays = step_rays if (tiles or world_size == 1) else step_rays * world_size  # frames mode: every rank casts a full frame per step
     value = all_rays / (max_ms * 1e-3) / 1e6
 
     # ---- end to end through the C ABI with host buffers -------------------------
@@ -418,10 +550,97 @@ def main():
         e2e_s = timed(e2e_step_pipelined, ctx.read_wait)
     e2e_value = all_rays / e2e_s / 1e6
 
+    # ---- the frames just timed, kept for the parity check (outside the timed region) ------------------------------
+    got_frames = {}
+    if not a.accumulate:
+        for ci in range(len(set(CAM_CYCLE))):
+            s = a.warmup + ci  # a timed step of each camera
+            if s >= total:
+                break
+            render_step(s, readback if reads else None, True)
+            drain()
+            if reads:
+                ctx.sync()
+                got_frames[s] = (color_h.numpy().copy(), depth_h.numpy().copy())
+
+    # ---- tiles: where does the step time go? ----------------------------------------------------------------------
+    scaling_detail = None
+    if tiles:
+        barrier()
+        per_rank = []
+        for ci in range(3):  # this rank's share of each camera's frame, alone on its stream (no fences)
+            ctx.render_interleaved(frames[ci], rank, world_size)
+            ctx.sync()
+            ctx.timer_begin()
+            for _ in range(5):
+                ctx.render_interleaved(frames[ci], rank, world_size)
+            per_rank.append(ctx.timer_end() / 5)
+        t = torch.tensor(per_rank, device="cuda", dtype=torch.float64)
+        gathered = [torch.zeros_like(t) for _ in range(world_size)]
+        dist.all_gather(gathered, t)
+        shares = np.array([g.cpu().numpy() for g in gathered])  # [rank, camera]
+        barrier()
+        single = []
+        if rank == 0:  # the whole frame on one GPU with the same kernel: the strong-scaling reference point
+            for plane in PL:
+                ctx.bind_plane(plane, None)
+            for ci in range(3):
+                ctx.render_interleaved(frames[ci], 0, 1)
+                ctx.sync()
+                ctx.timer_begin()
+                for _ in range(5):
+                    ctx.render_interleaved(frames[ci], 0, 1)
+                single.append(ctx.timer_end() / 5)
+        barrier()
+        scaling_detail = {
+            "share_kernel_ms_by_camera": {c: {"min": float(shares[:, i].min()), "mean": float(shares[:, i].mean()), "max": float(shares[:, i].max())}
+                                          for i, c in enumerate(CAM_CYCLE)},
+            "share_kernel_ms_max_mean": float(shares.max(axis=0).mean()),
+            "single_gpu_frame_ms_by_camera": {c: float(single[i]) for i, c in enumerate(CAM_CYCLE)} if single else None,
+            "single_gpu_frame_ms_mean": float(np.mean(single)) if single else None,
+            "nvlink_bytes_per_frame": int(8 * W * H * (world_size - 1) // world_size),
+            "launches_per_step_rank0": launches / max(1, a.steps),
+            "note": "step time - max share kernel time = launch + fence latency and inter-GPU skew; max share x N - single-GPU frame = load "
+                    "imbalance between the interleaved bands plus the per-launch tail",
+        }
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
+
+    # ---- parity of the timed frames ------------------------------------------------------------------------------
+    parity = None
+    cpu = None
+    if world_size == 1 and not a.no_cpu_baseline:
+        v, kind, sample, _, kept = cpu_arm(nodes, a, 3, a.warmup, a.cpu_seconds, cores, keep_planes=True)
+        cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample,
+               "what": "svotrace.comp compiled for the CPU by g++ (oracle/build_ref.py)" if kind == "reference" else "C restatement of svotrace.comp (oracle/svo_oracle.c)"}
+        if got_frames:
+            px = bad_c = bad_d = 0
+            for s, (y0, y1, planes) in kept.items():
+                if s not in got_frames:
+                    continue
+                gc, gd = got_frames[s]
+                bad_c += int((gc[y0:y1] != planes["rgba8"][y0:y1]).any(axis=-1).sum())
+                bad_d += int((gd[y0:y1].view(np.uint32) != planes["depth"][y0:y1].view(np.uint32)).sum())
+                px += (y1 - y0) * W
+            parity = {"against": "cpu_baseline planes (kind %s) of the same frames" % kind, "frames": len(kept), "pixels": px,
+                      "rgba8_mismatch": bad_c, "depth_mismatch": bad_d}
+    elif tiles and got_frames:
+        # the frame assembled from N GPUs' bands against the same frame rendered by GPU 0 alone (itself checked against
+        # the CPU arm by the N = 1 run and by tests/test_gpu_parity.py::test_full_size_properties)
+        for plane in PL:
+            ctx.bind_plane(plane, None)
+        px = bad_c = bad_d = 0
+        for s, (gc, gd) in got_frames.items():
+            ctx.render(frames[s])
+            wc, wd = ctx.read_color_rgba8(), ctx.read_depth()
+            bad_c += int((gc != wc).any(axis=-1).sum())
+            bad_d += int((gd.view(np.uint32) != wd.view(np.uint32)).sum())
+            px += W * H
+        parity = {"against": "the same frames rendered by GPU 0 alone", "frames": len(got_frames), "pixels": px, "rgba8_mismatch": bad_c,
+                  "depth_mismatch": bad_d}
 
     # ---- roofline ----------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -429,57 +648,90 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    timed = range(a.warmup, total)
-    launch_ms = dev_ms / max(1, launches)
-    alg_bytes = float(np.mean([alg_bytes_per_step[s] for s in timed]))
+    timed_steps = range(a.warmup, total)
+    render_launches = a.steps  # one render kernel per step on this rank (fence kernels of the tile partition are not counted here)
+    launch_ms = dev_ms / max(1, render_launches)
+    alg_bytes = float(np.mean([alg_bytes_per_step[s] for s in timed_steps])) / (world_size if tiles else 1)
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    mean_F = sum(iters_per_step[s] for s in timed) / sum(rays_per_step[s] for s in timed)
+    n_rays = sum(rays_per_step[s] for s in timed_steps)
+    mean_F = sum(iters_per_step[s] for s in timed_steps) / n_rays
+    mean_F_exec = sum(exec_iters_per_step[s] for s in timed_steps) / n_rays
+    kernel_name = {1: "k_render_persistent", 10: "k_render_tile_stack<wide>", 13: "k_render_tile_balanced", 17: "k_render_tile_queue"}.get(kernel_id, "k_render_tile")
+    if tiles:
+        kernel_name = "k_render_tile_queue"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                "node_fetches_per_ray_reference": mean_F, "loop_iterations_per_ray_executed": mean_F_exec,
+                "note": "the kernel is instruction-issue bound, not memory bound: upload-time transcoding removed the per-iteration record "
+                        "fetch the algorithmic-byte count assumes (real DRAM traffic = `traffic`), and the content box skips the empty-space "
+                        "iterations between the reference's count and the executed one.  `issue` and `lanes` are the bounds that bind."}
+    # ncu capture of this same command's render kernel (tools/profile_bench.sh writes it; one row per camera frame)
+    prof = None
+    if os.path.exists(a.profile_json) and world_size == 1 and (a.size, W, H, CASTS, MODE) == (8192, 1920, 1080, 2, 0):
+        try:
+            rows = [r for r in json.load(open(a.profile_json)) if kernel_name.split("<")[0] in r.get("kernel", "")]
+            if rows:
+                prof = {k: float(np.mean([r[k] for r in rows if k in r])) for k in rows[0] if isinstance(rows[0][k], (int, float))}
+                prof["rows"] = len(rows)
+        except (ValueError, OSError, KeyError):
+            prof = None
+    if prof:
+        sm_clk = (clk.get("sm_mhz") or 1965.0) * 1e6
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_issue = sms * 4 * sm_clk
+        roofline["traffic"] = prof.get("dram_traffic_MB", 0.0) * 1e6
+        roofline["profile"] = os.path.relpath(a.profile_json, ROOT)
+        if "warp_instructions" in prof:
+            ach = prof["warp_instructions"] / (launch_ms * 1e-3)
+            roofline["issue"] = {"warp_instructions_per_launch": prof["warp_instructions"], "achieved": ach, "peak": peak_issue,
+                                 "unit": "warp instructions/s", "frac": ach / peak_issue,
+                                 "issue_slot_util_pct_ncu": prof.get("issue_slot_util_pct"),
+                                 "how": "smsp__inst_executed.sum per launch (ncu) / live launch time, against SMs x 4 schedulers x live SM clock"}
+        if "active_lanes_per_inst" in prof:
+            roofline["lanes"] = {"active_lanes_per_inst": prof["active_lanes_per_inst"], "frac": prof["active_lanes_per_inst"] / 32.0}
     gather = {}
-    try:
-        S = ctx.gather_probe(min(max(info["descriptors"] * 8, 1 << 20), 8 << 30))
-        rays_s = sum(rays_per_step[s] for s in timed) / (dev_ms * 1e-3)
-        gather = {"sectors_per_s": S, "working_set_bytes": info["descriptors"] * 8, "node_fetches_per_ray": mean_F,
-                  "achieved_sector_equiv_per_s": rays_s * mean_F, "frac": rays_s * mean_F / S}
+    try:  # SURVEY 8d's gather roofline: random 32-byte sectors, L2-resident and HBM-resident working sets
+        S_hbm = ctx.gather_probe(min(max(info["descriptors"] * 8, 1 << 20), 8 << 30))
+        S_l2 = ctx.gather_probe(48 << 20)
+        rays_s = n_rays / (dev_ms * 1e-3)
+        gather = {"sectors_per_s_hbm_resident": S_hbm, "sectors_per_s_l2_resident": S_l2, "working_set_bytes": info["descriptors"] * 8,
+                  "reference_fetches_per_s": rays_s * mean_F}
+        if prof and "l1_miss_sectors" in prof:
+            # sectors the kernel really requests from L2 per launch, split by where they were served, against the two rates
+            miss = prof["l1_miss_sectors"]
+            l2_hit = prof.get("l2_hit_pct", 60.0) / 100.0
+            t_bound = miss * l2_hit / S_l2 + miss * (1.0 - l2_hit) / S_hbm
+            gather.update({"l1_miss_sectors_per_launch": miss, "l2_hit_rate": l2_hit, "bound_ms": t_bound * 1e3,
+                           "frac": t_bound / (launch_ms * 1e-3),
+                           "how": "time the measured gather rates need for the kernel's L1-miss sectors (ncu) / live launch time"})
     except svo.SvoError as e:
         gather = {"error": str(e)}
-    # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (dram__bytes_read.sum +
-    # dram__bytes_write.sum, mean of the three camera frames), profiles/r01_tile_full.json
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", {0: "r01_tile_full.json", 10: "r01_tile_wide_full.json"}.get(a.kernel, "none"))
-    if os.path.exists(tpath) and a.size == 8192 and world_size == 1 and (W, H, CASTS, MODE) == (1920, 1080, 2, 0):
-        caps = json.load(open(tpath))
-        traffic = float(np.mean([c["dram_traffic_MB"] for c in caps])) * 1e6
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": {1: "k_render_persistent", 10: "k_render_tile_stack<wide>"}.get(a.kernel, "k_render_tile"), "algorithmic_bytes_per_launch": alg_bytes,
-                "launch_ms": launch_ms, "gather": gather,
-                "note": "the kernel is instruction-issue bound, not memory bound (ncu: issue slots 73 %, ALU pipe 74 %, DRAM 5 %): "
-                        "upload-time transcoding removed the per-iteration record fetch the algorithmic-byte count assumes"}
-
-    cpu = None
-    if not a.no_cpu_baseline and world_size == 1:
-        v, sample, _ = cpu_arm(nodes, a.size, 3, 0, a.cpu_seconds, cores)
-        cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample}
+    roofline["gather"] = gather
 
     out = {
-        "metric": "Mrays/s (primary + diffuse bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": a.steps,
+        "metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "partition": a.partition if world_size > 1 else "single GPU", "tree_bytes": int(nodes.size), "descriptors": info["descriptors"], "levels": info["levels"],
-                   "l2_policy": "inputs larger than L2 (octree %.2f GB, 3 camera poses cycled); no flush between steps" % (nodes.size / 1e9)
-                   if nodes.size > 126e6 else "octree fits L2; camera poses cycled; no flush",
-                   "fast_math": a.fast_math, "kernel": a.kernel, "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
-                   "world_build_s": round(build_s, 2), "upload_transcode_s": round(upload_s, 2),
-                   "units": ("one frame per step, interleaved 8-row bands per rank, peers store into rank 0's planes over NVLink, "
-                             "frame-complete fence = " + ("remote atomics over NVLink" if a.fence == "p2p" else "NCCL all-reduce")) if tiles else
-                            "rank r renders progressive sample s*N+r of each view; no data-path collective"},
+        "config": config_of(a, world_size, nodes.size, partition),
+        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "descriptors": info["descriptors"], "levels": info["levels"],
+                         "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
+                         "world": {"how": world_how, "seconds": round(build_s, 2)}, "upload_transcode_s": round(upload_s, 2),
+                         "units": ("one frame per step, interleaved %d-row bands per rank, peers store into rank 0's planes over NVLink, "
+                                   "frame-complete fence = %s" % (a.band_rows, "remote atomics over NVLink, bumped by the render kernel's last CTA" if a.fence == "p2p" else "NCCL all-reduce")) if tiles else
+                                  ("rank r renders progressive sample s*N+r of each view; no data-path exchange" if world_size > 1 else "one GPU renders every frame")},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
                 "ms_per_step": e2e_s / a.steps * 1e3,
                 "how": "svo_render + svo_read_planes_async + svo_swap_buffers per frame (read-back of frame s overlaps the render of "
-                       "frame s+1), svo_read_wait inside the timed region" if not tiles else "rank 0 reads the assembled frame back after every frame-complete fence",
+                       "frame s+1), svo_read_wait inside the timed region" if not tiles else
+                       "rank 0 reads the assembled frame back after every frame-complete fence (16.6 MB per frame over GPU 0's PCIe link bounds it)",
                 "blocking_value": all_rays / e2e_sync_s / 1e6},
         "roofline": roofline,
     }
+    if parity is not None:
+        out["parity"] = parity
+    if scaling_detail is not None:
+        out["scaling_detail"] = scaling_detail
     if cpu is not None:
         out["cpu_baseline"] = cpu
         out["other_baselines"] = other_baselines()

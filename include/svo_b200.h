@@ -34,7 +34,8 @@ enum svo_status {
   SVO_ERR_NO_DEVICE = 100,/* CUDA_ERROR_NO_DEVICE: no fallback exists */
   SVO_ERR_CUDA = 999,     /* any other CUDA failure; text in svo_last_error */
   SVO_ERR_FORMAT = 1000,  /* node stream is not a tree this path can walk */
-  SVO_ERR_NO_SCENE = 1001 /* render/cast before svo_upload */
+  SVO_ERR_NO_SCENE = 1001,/* render/cast before svo_upload */
+  SVO_ERR_FENCE = 1002    /* svo_sync: a svo_fence_wait gave up (~2 s watchdog): a peer GPU fell behind or died */
 };
 
 typedef struct svo_ctx svo_ctx;
@@ -89,7 +90,8 @@ enum svo_option {
                                * memory, 11 / 12 72 / 80 registers per thread, 13 variant 10 with the loop's integer work moved to
                                * the FMA pipe, 14 variant 10 in the band-interleaved launch too, 15 the last cast of
                                * mode-0 pixels in a persistent kernel of its own with lane refill, 16 the same with the cast's set-up
-                               * done by the primary kernel (13 ... 16 not yet measured).  All bit-exact; the others are measured ablations */
+                               * done by the primary kernel, 17 variant 10 as persistent warps that take whole 8x4 tiles from a queue (what
+                               * svo_render_interleaved runs unless 0 or 14 is selected).  All bit-exact; the others are measured ablations */
   SVO_OPT_L2_PERSIST = 4,     /* 0/1: L2 access-policy window (persisting) over the upper octree levels, applied at the next
                                * upload; default 0 (measured: no effect, the path is not memory bound) */
   SVO_OPT_RAY_SORT = 5,       /* 0/1: trace ray streams of >= 65536 rays in (direction octant, origin Morton code) order; default 1 */
@@ -138,6 +140,11 @@ int svo_render_rows(svo_ctx *ctx, const svo_frame *frame, int y0, int y1);
 /* Bands part, part+parts, part+2*parts, ... of the frame (SVO_OPT_BAND_ROWS image rows each, default 8) in ONE
  * launch: the interleaved image partition of the multi-GPU mode (rank = part, world size = parts). */
 int svo_render_interleaved(svo_ctx *ctx, const svo_frame *frame, int part, int parts);
+/* The same launch followed, in stream order, by svo_fence_signal(fence_ptrs, n, slot) (n = 0: this context's own
+ * fence; n = -1: no signal).  With the tile-queue kernel (SVO_OPT_KERNEL 17, what the interleaved launch runs by
+ * default) the signal is part of the render kernel -- its last CTA bumps the fences -- so a rank's whole share of a
+ * frame, stores into the owner's planes over NVLink and frame-complete fence included, is ONE kernel launch. */
+int svo_render_interleaved_signal(svo_ctx *ctx, const svo_frame *frame, int part, int parts, void *const *fence_ptrs, int n, int slot);
 /* replaces dispatchCompute(beamShader, W/8/4, H/8/4, 1) (Main.java:257-266) */
 int svo_beam(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
@@ -206,6 +213,10 @@ int svo_launch_count(const svo_ctx *ctx, uint64_t *count);
  * fetches, svotrace.comp:294), [2] = bytes of those records in the reference
  * layout plus 7 per cast for the root (SURVEY 8d "algorithmic bytes"). */
 int svo_render_stats(svo_ctx *ctx, const svo_frame *frame, uint64_t counters[3]);
+/* The same counters for what the PRODUCTION kernel executes on this frame (content box on, casts that end before the
+ * loop not spun to the cap): [1] is the number of loop iterations actually run -- bench.py reports it next to the
+ * reference's count.  Writes the colour and depth planes like svo_render. */
+int svo_render_stats_executed(svo_ctx *ctx, const svo_frame *frame, uint64_t counters[3]);
 /* Gather roofline: random 32-byte-sector read rate over a working
  * set of `working_set_bytes`, measured with CUDA events.  Returns sectors/s. */
 int svo_gather_probe(svo_ctx *ctx, uint64_t working_set_bytes, int loads_per_thread, double *sectors_per_s);

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SVO_B200_LIB") or os.path.join(_HERE, "libsvo_b200.so
 NO_HIT = 0xFFFFFFFF
 
 # enum svo_status
-OK, ERR_INVALID, ERR_OOM, ERR_NO_DEVICE, ERR_CUDA, ERR_FORMAT, ERR_NO_SCENE = 0, 1, 2, 100, 999, 1000, 1001
+OK, ERR_INVALID, ERR_OOM, ERR_NO_DEVICE, ERR_CUDA, ERR_FORMAT, ERR_NO_SCENE, ERR_FENCE = 0, 1, 2, 100, 999, 1000, 1001, 1002
 # enum svo_plane
 PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIMARY_T, PLANE_RADIANCE = range(7)
 PLANE_BACK = 0x100
@@ -56,6 +56,7 @@ SYMBOLS = {
     "svo_render": (_i, [_vp, C.POINTER(Frame)]),
     "svo_render_rows": (_i, [_vp, C.POINTER(Frame), _i, _i]),
     "svo_render_interleaved": (_i, [_vp, C.POINTER(Frame), _i, _i]),
+    "svo_render_interleaved_signal": (_i, [_vp, C.POINTER(Frame), _i, _i, C.POINTER(_vp), _i, _i]),
     "svo_beam": (_i, [_vp, C.POINTER(Frame)]),
     "svo_sync": (_i, [_vp]),
     "svo_read_plane": (_i, [_vp, _i, _vp, _u64]),
@@ -85,6 +86,7 @@ SYMBOLS = {
     "svo_timer_end": (_i, [_vp, C.POINTER(C.c_float)]),
     "svo_launch_count": (_i, [_vp, C.POINTER(_u64)]),
     "svo_render_stats": (_i, [_vp, C.POINTER(Frame), C.POINTER(_u64 * 3)]),
+    "svo_render_stats_executed": (_i, [_vp, C.POINTER(Frame), C.POINTER(_u64 * 3)]),
     "svo_gather_probe": (_i, [_vp, _u64, _i, C.POINTER(C.c_double)]),
     "svo_math_probe": (_i, [_vp, _i, _vp, _vp, _vp, _u64]),
     "svo_terrain_generate": (_i, [_i, _i, _vp, _vp, _i]),

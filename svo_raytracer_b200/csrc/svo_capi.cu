@@ -55,10 +55,11 @@ struct svo_ctx {
   uint64_t sort_cap = 0;
   size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 10, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1, opt_stream_kernel = 0;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 13, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1, opt_stream_kernel = 0;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
+  bool fence_waits_unchecked = false;  // a k_fence_wait ran since svo_sync last looked at the watchdog latch (d_fence[7])
   struct IpcMap { cudaIpcMemHandle_t handle; void *base; };
   std::vector<IpcMap> ipc_maps;  // peer blocks opened by svo_ipc_import
   WaveWorkspace ws{};  // wavefront variant, allocated on first use
@@ -185,11 +186,15 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.kernel = c->opt_kernel;
   l.stream_kernel = c->opt_stream_kernel;
   l.sm_count = c->sm_count;
+  l.scene_levels = (int)c->nlevels;
   l.band_stride = 0;
   l.band_offset = 0;
   l.band_ctas = c->opt_band_rows / 8;
   l.ctas_per_sm = c->ctas_per_sm;
   l.tile_counter = c->d_tile_counter;
+  l.tile_queue = c->d_tile_counter + 2;  // words 2, 3: zero between launches (the last CTA out resets them)
+  l.fences.n = 0;
+  for (int i = 0; i < 16; i++) l.fences.p[i] = nullptr;
   l.split = c->split;
   return l;
 }
@@ -395,6 +400,7 @@ int svo_create(svo_ctx **out, int device, int width, int height) {
     c->stream = c->own_stream;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
     if ((e = cudaMalloc((void **)&c->d_tile_counter, 64)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(counter)"); break; }
+    cudaMemsetAsync(c->d_tile_counter, 0, 64, c->stream);
     if ((e = cudaMalloc((void **)&c->d_fence, 256)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(fence)"); break; }
     cudaMemsetAsync(c->d_fence, 0, 256, c->stream);
     for (int p = SVO_PLANE_COLOR_RGBA8; p <= SVO_PLANE_BEAM; p++) {
@@ -450,7 +456,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 16)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 21)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       c->opt_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
@@ -558,6 +564,7 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
   if (c->opt_kernel == 2) {
+    if (c->W > 65535 || c->H > 65535) return fail(c, SVO_ERR_INVALID, "the wavefront kernel packs pixel coordinates in 16 bits: width and height must be <= 65535");
     if ((rc = ensure_wavefront(c)) != SVO_OK) return rc;
     SVO_CUDA(c, launch_render_wavefront(launch_cfg(c), scene_view(c), fp, planes_of(c), c->W, c->H, y0, y1, c->ws, c->stream));
     c->launches += (uint64_t)wavefront_launches(fp);
@@ -572,24 +579,44 @@ int svo_render_rows(svo_ctx *c, const svo_frame *frame, int y0, int y1) {
 }
 int svo_render(svo_ctx *c, const svo_frame *frame) { return svo_render_rows(c, frame, 0, c ? c->H : 0); }
 
-int svo_render_interleaved(svo_ctx *c, const svo_frame *frame, int part, int parts) {
+int svo_render_interleaved_signal(svo_ctx *c, const svo_frame *frame, int part, int parts, void *const *fence_ptrs, int n, int slot) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_render before svo_upload");
   int rc = check_frame(c, frame);
   if (rc) return rc;
   if (parts < 1 || part < 0 || part >= parts) return fail(c, SVO_ERR_INVALID, "part must be in [0, parts)");
+  if (n < -1 || n > 16 || (n > 0 && !fence_ptrs)) return fail(c, SVO_ERR_INVALID, "bad fence list (at most 16)");
+  if (n >= 0 && (slot < 0 || slot >= 8)) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   if (c->opt_aux && (rc = ensure_aux(c)) != SVO_OK) return rc;
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
   LaunchCfg cfg = launch_cfg(c);
-  cfg.kernel = c->opt_kernel == 14 ? 14 : 0;  // the band-interleaved partition is a feature of the tile kernel (14: with wide stack entries)
+  // the band-interleaved partition is a feature of the tile kernels: 17 (tile queue, the default) / 14 (wide stack
+  // entries, static CTAs) / 0 (8-byte stack entries; also the only one with SVO_OPT_FAST_MATH)
+  cfg.kernel = c->opt_fast ? 0 : (c->opt_kernel == 0 || c->opt_kernel == 14) ? c->opt_kernel : 17;
   cfg.band_stride = parts;
   cfg.band_offset = part;
   cfg.box = box_allowed(c, frame);
+  FenceList fl;
+  fl.n = 0;
+  for (int i = 0; i < 16; i++) fl.p[i] = nullptr;
+  if (n >= 0) {  // n == 0: this context's own fence (as svo_fence_signal)
+    fl.n = n > 0 ? n : 1;
+    if (n == 0) fl.p[0] = c->d_fence + 8 * slot;
+    for (int i = 0; i < n; i++) fl.p[i] = (unsigned int *)fence_ptrs[i] + 8 * slot;
+  }
+  if (cfg.kernel == 17) cfg.fences = fl;  // signalled by the render kernel's last CTA
   SVO_CUDA(c, launch_render(cfg, scene_view(c, frame), fp, planes_of(c), c->W, c->H, 0, c->H, c->stream));
   c->launches++;
+  if (cfg.kernel != 17 && fl.n > 0) {
+    SVO_CUDA(c, launch_fence_signal(fl, c->stream));
+    c->launches++;
+  }
   return SVO_OK;
+}
+int svo_render_interleaved(svo_ctx *c, const svo_frame *frame, int part, int parts) {
+  return svo_render_interleaved_signal(c, frame, part, parts, nullptr, -1, 0);
 }
 
 int svo_beam(svo_ctx *c, const svo_frame *frame) {
@@ -609,6 +636,14 @@ int svo_sync(svo_ctx *c) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->fence_waits_unchecked) {  // did a frame-complete wait give up (k_fence_wait's watchdog)?  Frames since then are incomplete.
+    unsigned int dead = 0;
+    SVO_CUDA(c, cudaMemcpy(&dead, c->d_fence + 7, sizeof dead, cudaMemcpyDeviceToHost));
+    c->fence_waits_unchecked = false;
+    if (dead == 0xDEADu)
+      return fail(c, SVO_ERR_FENCE, "a frame-complete fence timed out: a peer GPU fell behind or died; frames rendered since are incomplete "
+                                    "(svo_fence_reset clears the latch)");
+  }
   return SVO_OK;
 }
 
@@ -743,6 +778,7 @@ int svo_fence_wait(svo_ctx *c, int slot, uint32_t target) {
   if (slot < 0 || slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, launch_fence_wait(c->d_fence + 8 * slot, c->d_fence + 7, target, c->stream));
+  c->fence_waits_unchecked = true;
   c->launches++;
   return SVO_OK;
 }
@@ -914,7 +950,7 @@ int svo_scene_probe(svo_ctx *c, uint64_t out[8]) {
   return SVO_OK;
 }
 
-int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
+static int render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3], bool executed) {
   if (!c || !counters) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
   if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_render_stats before svo_upload");
   int rc = check_frame(c, frame);
@@ -927,7 +963,7 @@ int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
   SVO_CUDA(c, cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), c->stream));
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
-  SVO_CUDA(c, launch_render_stats(scene_view(c), fp, planes_of(c), c->W, c->H, 0, c->H, d, c->stream));
+  SVO_CUDA(c, launch_render_stats(scene_view(c, executed ? frame : nullptr), fp, planes_of(c), c->W, c->H, 0, c->H, d, c->stream, executed));
   c->launches++;
   unsigned long long h[3];
   SVO_CUDA(c, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -935,6 +971,9 @@ int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) {
   for (int i = 0; i < 3; i++) counters[i] = h[i];
   return SVO_OK;
 }
+
+int svo_render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) { return render_stats(c, frame, counters, false); }
+int svo_render_stats_executed(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]) { return render_stats(c, frame, counters, true); }
 
 int svo_gather_probe(svo_ctx *c, uint64_t working_set_bytes, int loads_per_thread, double *sectors_per_s) {
   if (!c || !sectors_per_s) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");

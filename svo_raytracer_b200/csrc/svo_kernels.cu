@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_binned(SceneView sc, Fra
 //      of the loop as IMADs on the FMA pipe (ncu: ALU pipe 75 % busy, math-pipe throttle stalls, FMA pipe 20 %).
 //      Static count of the loop: ALU-pipe instructions 64 -> 44, FMA-pipe 26 -> 43, 6 more constant loads.
 // ---------------------------------------------------------------------------
-template <bool AUX, bool BOX, int STACK, bool BAL = false>
+template <bool AUX, bool BOX, int STACK, int BAL = 0>
 __device__ __forceinline__ void tile_body(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1) {
   __shared__ uint2 s_stack[STACK == 2 ? kSmemStackLevels : 1][kSmemStackStride];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,9 +221,9 @@ __device__ __forceinline__ void tile_body(const SceneView &sc, const FrameParams
   if (x >= W || y >= y1) return;
   shade_pixel<false, AUX, false, BOX, false, STACK, BAL>(sc, f, pl, W, H, x, y, nullptr, &s_stack[0][threadIdx.x]);
 }
-template <bool AUX, bool BOX>
+template <bool AUX, bool BOX, int BAL = 15>  // BAL: which parts of the loop run as IMADs (mask, see Trav); 15 = variant 13
 __global__ void __launch_bounds__(128, 8) k_render_tile_balanced(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
-  tile_body<AUX, BOX, 1, true>(sc, f, pl, W, H, y0, y1);
+  tile_body<AUX, BOX, 1, BAL>(sc, f, pl, W, H, y0, y1);
 }
 template <bool AUX, bool BOX, int STACK>
 __global__ void __launch_bounds__(128, 8) k_render_tile_stack(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
@@ -232,6 +232,55 @@ __global__ void __launch_bounds__(128, 8) k_render_tile_stack(SceneView sc, Fram
 template <bool AUX, bool BOX, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_render_tile_regs(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
   tile_body<AUX, BOX, 0>(sc, f, pl, W, H, y0, y1);
+}
+
+// ---------------------------------------------------------------------------
+// Kernel variant 17: variant 10 as persistent warps that take whole 8x4-pixel tiles from a queue (one atomic per tile,
+// warp-level fetch).  Nothing about the per-pixel work changes -- no lane is re-armed inside a tile, which is what cost
+// variants 1 / 2 / 7 / 8 their coherence -- only WHO renders a tile does: a warp that finishes early takes the next tile at
+// once instead of idling until the three other warps of its CTA are done (ncu, variant 10: achieved occupancy 42-44 % of
+// the 50 % the registers allow), and a launch has no wave quantisation: 2 025 CTAs over 1 184 CTA slots = 1.7 waves is what
+// bounds one GPU's share of a 1080p frame in the 8-GPU tile partition.  Tiles are numbered so that four consecutive
+// indices form a 16x8 block and blocks run left to right, top to bottom: warps that fetch together work on neighbouring
+// pixels, like the CTAs of variant 10 (L1 / L2 locality).  band_stride / band_offset select the interleaved bands of one
+// GPU as in k_render_tile.  The queue head is reset by the last CTA to leave, so a frame is one launch and nothing else;
+// the same CTA then signals the frame-complete fences of the multi-GPU partition (FenceList; n = 0: none), which saves
+// the separate signal kernel and its launch latency.
+// ---------------------------------------------------------------------------
+template <bool AUX, bool BOX>
+__global__ void __launch_bounds__(128, 8) k_render_tile_queue(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
+                                                           int band_stride, int band_offset, int band_ctas, unsigned int nblocks_y,
+                                                           unsigned int *__restrict__ queue, FenceList fl) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned blocks_x = ((unsigned)W + 15u) >> 4;
+  const unsigned ntiles = blocks_x * nblocks_y * 4u;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(queue, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= ntiles) break;
+    const unsigned b = t >> 2, sub = t & 3u;
+    const unsigned bx = b % blocks_x, by = b / blocks_x;
+    const int band = (int)by / band_ctas, in_band = (int)by % band_ctas;
+    const int x = (int)(bx * 16u + (sub & 1u) * 8u + (lane & 7u));
+    const int y = y0 + ((band * band_stride + band_offset) * band_ctas + in_band) * 8 + (int)(sub >> 1) * 4 + (int)(lane >> 3);
+    if (x < W && y < y1) shade_pixel<false, AUX, false, BOX, false, 1, 15>(sc, f, pl, W, H, x, y);
+  }
+  // last CTA out: reset the queue for the next launch, then tell the frame's owner that this GPU's pixels are stored
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (fl.n > 0) __threadfence_system();  // this CTA's pixel stores (possibly into a peer's memory) are ordered before its ticket
+    else __threadfence();
+    const unsigned ticket = atomicAdd(queue + 1, 1u);
+    if (ticket == gridDim.x - 1u) {
+      queue[0] = 0u;
+      queue[1] = 0u;
+      if (fl.n > 0) {
+        __threadfence_system();  // every CTA's stores (ordered before its ticket) are visible system-wide before the bumps
+        for (int i = 0; i < fl.n; i++) atomicAdd_system(fl.p[i], 1u);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -603,6 +652,7 @@ __global__ void k_fence_wait(volatile unsigned int *fence, volatile unsigned int
 // (casts, loop iterations, bytes of the reference-layout records the reference
 // would have fetched).  bench.py runs it once, outside the timed region, to get
 // the algorithmic bytes of the workload; tests compare it with the oracle.
+template <bool EXECUTED>  // false: the oracle's counters; true: what the production kernel executes (content box on, early exits)
 __global__ void __launch_bounds__(128) k_render_stats(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1,
                                                       unsigned long long *counters) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -610,7 +660,10 @@ __global__ void __launch_bounds__(128) k_render_stats(SceneView sc, FrameParams 
   const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
   RayStats rs;
   rs.casts = rs.iters = rs.record_bytes = 0u;
-  if (x < W && y < y1) shade_pixel<false, true, true>(sc, f, pl, W, H, x, y, &rs);
+  if (x < W && y < y1) {
+    if (EXECUTED) shade_pixel<false, false, 2, true, false, 1>(sc, f, pl, W, H, x, y, &rs);
+    else shade_pixel<false, true, 1>(sc, f, pl, W, H, x, y, &rs);
+  }
   const uint32_t c = __reduce_add_sync(0xffffffffu, rs.casts);
   const uint32_t i = __reduce_add_sync(0xffffffffu, rs.iters);
   const uint32_t b = __reduce_add_sync(0xffffffffu, rs.record_bytes);
@@ -804,6 +857,12 @@ __global__ void k_math_probe(int fn, const float *__restrict__ x, const float *_
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
+// Variant 9 keeps kSmemStackLevels stack entries per thread in shared memory (scales 9..22).  A cast stops descending at
+// maxDepth, or at coneDepth once the sticky cone cut has fired -- and if it is already deeper than coneDepth at that moment it
+// runs down to the tree's leaves -- so all three must fit; otherwise the default kernel renders the frame.
+static bool smem_stack_fits(const LaunchCfg &cfg, const FrameParams &f) {
+  return f.maxDepth <= kSmemStackLevels && f.coneDepth <= kSmemStackLevels && cfg.scene_levels <= kSmemStackLevels;
+}
 static bool split_applies(const LaunchCfg &cfg, const FrameParams &f) {
   return (cfg.kernel == 15 || cfg.kernel == 16) && !cfg.fast && !cfg.aux && cfg.band_stride == 0 && f.renderMode == 0 && f.casts >= 2 && cfg.split.q[0] != nullptr;
 }
@@ -860,7 +919,25 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
 #undef SVO_LAUNCH_BINNED
     return cudaGetLastError();
   }
-  if (cfg.kernel >= 9 && cfg.kernel <= 13 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || f.maxDepth <= kSmemStackLevels)) {
+  if (cfg.kernel >= 18 && cfg.kernel <= 21 && !cfg.fast && !cfg.aux && cfg.band_stride == 0) {  // ablations of variant 13's parts (production instance only)
+    const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
+    if (grid.x == 0 || grid.y == 0) return cudaSuccess;
+#define SVO_LAUNCH_BALMASK(B, M) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, M>)(sc, f, pl, W, H, y0, y1)
+#define SVO_LAUNCH_BAL(B)                                  \
+  do {                                                     \
+    if (cfg.kernel == 18) SVO_LAUNCH_BALMASK(B, 13);       \
+    else if (cfg.kernel == 19) SVO_LAUNCH_BALMASK(B, 7);   \
+    else if (cfg.kernel == 20) SVO_LAUNCH_BALMASK(B, 1);   \
+    else SVO_LAUNCH_BALMASK(B, 5);                         \
+  } while (0)
+    if (cfg.box) SVO_LAUNCH_BAL(true); else SVO_LAUNCH_BAL(false);
+#undef SVO_LAUNCH_BAL
+#undef SVO_LAUNCH_BALMASK
+    return cudaGetLastError();
+  }
+  if (cfg.kernel >= 18 && cfg.kernel <= 21) cfg.kernel = 13;
+  if (cfg.kernel == 9 && !smem_stack_fits(cfg, f)) cfg.kernel = 13;
+  if (cfg.kernel >= 9 && cfg.kernel <= 13 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || smem_stack_fits(cfg, f))) {
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
 #define SVO_LAUNCH_X(A, B)                                                                                           \
@@ -875,6 +952,24 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
     else if (cfg.box) SVO_LAUNCH_X(false, true);
     else SVO_LAUNCH_X(false, false);
 #undef SVO_LAUNCH_X
+    return cudaGetLastError();
+  }
+  if (cfg.kernel == 17 && !cfg.fast) {
+    const int stride = cfg.band_stride > 0 ? cfg.band_stride : 1, offset = cfg.band_stride > 0 ? cfg.band_offset : 0;
+    const int band_ctas = cfg.band_stride > 0 && cfg.band_ctas > 0 ? cfg.band_ctas : 1;
+    const int bands = ((y1 - y0 + 7) / 8 + band_ctas - 1) / band_ctas;
+    const unsigned nblocks_y = bands > offset ? (unsigned)(((bands - offset + stride - 1) / stride) * band_ctas) : 0u;
+    const unsigned blocks_x = (unsigned)(W + 15) / 16u;
+    const uint64_t nctas = (uint64_t)blocks_x * nblocks_y;  // one 16x8 block = four tiles = one CTA's worth of warps
+    const uint64_t cap = (uint64_t)cfg.sm_count * 8u;
+    const unsigned grid = (unsigned)(nctas < cap ? nctas : cap);
+    if (grid == 0) {  // nothing to render: the fences of the frame are still owed
+      if (cfg.fences.n > 0) SVO_LAUNCH(1, 32, stream, k_fence_signal)(cfg.fences);
+      return cudaGetLastError();
+    }
+    if (cfg.aux) SVO_LAUNCH(grid, 128, stream, k_render_tile_queue<true, false>)(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas, nblocks_y, cfg.tile_queue, cfg.fences);
+    else if (cfg.box) SVO_LAUNCH(grid, 128, stream, k_render_tile_queue<false, true>)(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas, nblocks_y, cfg.tile_queue, cfg.fences);
+    else SVO_LAUNCH(grid, 128, stream, k_render_tile_queue<false, false>)(sc, f, pl, W, H, y0, y1, stride, offset, band_ctas, nblocks_y, cfg.tile_queue, cfg.fences);
     return cudaGetLastError();
   }
   if ((cfg.kernel == 7 || cfg.kernel == 8) && cfg.band_stride == 0) {
@@ -932,11 +1027,12 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
 }
 
 cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1,
-                                unsigned long long *d_counters, cudaStream_t stream) {
+                                unsigned long long *d_counters, cudaStream_t stream, bool executed) {
   const dim3 block(128);
   const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
   if (grid.x == 0 || grid.y == 0) return cudaSuccess;
-  SVO_LAUNCH(grid, block, stream, k_render_stats)(sc, f, pl, W, H, y0, y1, d_counters);
+  if (executed) SVO_LAUNCH(grid, block, stream, k_render_stats<true>)(sc, f, pl, W, H, y0, y1, d_counters);
+  else SVO_LAUNCH(grid, block, stream, k_render_stats<false>)(sc, f, pl, W, H, y0, y1, d_counters);
   return cudaGetLastError();
 }
 

@@ -42,6 +42,8 @@ struct SplitQueue {
   uint64_t capacity;
 };
 
+struct FenceList { unsigned int *p[16]; int n; };  // fence words (possibly in peer memory) to bump by one
+
 struct LaunchCfg {
   bool fast;     // Ops<true>: fma-contracted t arithmetic
   bool aux;      // also write hit_id / iter / primary_t / radiance
@@ -49,10 +51,13 @@ struct LaunchCfg {
   int kernel;    // variant selector (SVO_OPT_KERNEL)
   int stream_kernel;  // ray streams: 0 grid-stride kernel, 1 persistent threads with warp-level ray fetch (SVO_OPT_STREAM_KERNEL)
   int sm_count;
+  int scene_levels;  // octree levels of the uploaded scene (variant 9 needs them to fit its shared-memory stack)
   int band_stride, band_offset;  // tile kernel: interleaved bands (stride 0 = all bands)
   int band_ctas;                 // CTA rows (8 image rows each) per band
   int ctas_per_sm;             // persistent grid = sm_count * ctas_per_sm
   unsigned int *tile_counter;  // device word: the persistent kernel's tile queue head
+  unsigned int *tile_queue;    // variant 17: two device words {next tile, CTAs that have left}, zero between launches
+  FenceList fences;            // variant 17: frame-complete fences the launch signals when its last CTA leaves (n = 0: none)
   SplitQueue split;            // variant 15 only (q[0] == nullptr: not allocated)
 };
 
@@ -76,8 +81,7 @@ cudaError_t launch_render(const LaunchCfg &cfg, const SceneView &sc, const Frame
 // kernels launch_render() enqueues for this frame (variant 15: two)
 int render_launches(const LaunchCfg &cfg, const FrameParams &f);
 cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H, int y0, int y1,
-                                unsigned long long *d_counters, cudaStream_t stream);
-struct FenceList { unsigned int *p[16]; int n; };
+                                unsigned long long *d_counters, cudaStream_t stream, bool executed = false);
 cudaError_t launch_fence_signal(const FenceList &fl, cudaStream_t stream);
 cudaError_t launch_fence_wait(unsigned int *fence, unsigned int *dead, unsigned int target, cudaStream_t stream);
 cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int blocks, uint32_t *sink, cudaStream_t stream);

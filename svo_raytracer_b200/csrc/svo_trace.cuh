@@ -284,7 +284,12 @@ SVO_DI uint2 stk_load(SmemStack s, int scale, uint32_t &pidx, float &t_max, cons
 // BAL: pipe-balanced loop body.  ncu puts the ALU pipe (LOP3 / SHF / SEL / FSETP / FMNMX / IADD3 / MOV) at 75 % busy with
 // math-pipe throttle among the top stall reasons while the FMA pipe idles at 20 %; BAL moves the integer adds, moves
 // and select chains of the loop onto the FMA pipe as IMADs (imad() below).  Same values, different instructions.
-template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false, bool BAL = false>
+// BAL is a mask so that the parts can be measured separately: 1 = child-index / step-mask assembly as predicated FADD + IMAD
+// (step_if_gt / step_if_le / move_if_gt), 2 = the h / t_max / t_min moves as IMADs, 4 = pidx and scale-1 in PUSH as IMADs,
+// 8 = the POP path's shifts, 2^(scale-23) and child index as IMADs.  15 = kernel variant 13.
+// STATS: 1 = the oracle's counters (what the REFERENCE would have fetched: a NaN ray counts its 1500 spins), 2 = what this
+// kernel executes (iterations actually run, with the content box and the early exits).
+template <bool FAST, int STATS = 0, bool BOX = false, bool TOP = false, int BAL = 0>
 struct Trav {
   typedef Ops<FAST> M;
   static __device__ __forceinline__ uint2 fetch(const SceneView &sc, uint32_t i) {
@@ -396,7 +401,7 @@ struct Trav {
   __device__ __forceinline__ bool nan_ray(RayStats *rs) {
     const float a = M::msub(px, cx, bx), b = M::msub(py, cy, by), c = M::msub(pz, cz, bz);
     if (!((a != a) && (b != b) && (c != c))) return false;
-    if (STATS) {  // the reference fetches the same child record 1500 times
+    if (STATS == 1) {  // the reference fetches the same child record 1500 times
       const uint32_t code = (pd.y >> (2u * (idx ^ oct))) & 3u;
       rs->iters += (uint32_t)kMaxIterations;
       rs->record_bytes += (uint32_t)kMaxIterations * (code == 1u ? 3u : (code == 3u ? 1u : 7u));
@@ -431,9 +436,9 @@ struct Trav {
       if (tc_max < h) { /* PUSH :316-319 */                                                                          \
         stk_store(stk, scale, pidx, t_max, pd);                                                                      \
       }                                                                                                              \
-      h = BAL ? fmove(tc_max, sc.one) : tc_max;                                                                      \
+      h = (BAL & 2) ? fmove(tc_max, sc.one) : tc_max;                                                                      \
       /* descriptors of the interior siblings below: bits [24, 24+cs) -- the funnel shift leaves exactly those */    \
-      pidx = BAL ? imad((uint32_t)__popc(__funnelshift_r(0u, pd.y >> 24, cs)), sc.one, pd.x)                         \
+      pidx = (BAL & 4) ? imad((uint32_t)__popc(__funnelshift_r(0u, pd.y >> 24, cs)), sc.one, pd.x)                         \
                  : pd.x + __popc(__funnelshift_r(0u, pd.y >> 24, cs));                                               \
       pd = fetch(sc, pidx);                                /* parent = child (:322) */                               \
       const float half = M::mul(scale_exp2, 0.5f);                                                                   \
@@ -441,21 +446,20 @@ struct Trav {
       const float ty_center = M::madd(half, cy, ty_corner);                                                          \
       const float tz_center = M::madd(half, cz, tz_corner);                                                          \
       scale_exp2 = half;                                                                                             \
-      if (BAL) {                                                                                                     \
-        scale = (int)imad((uint32_t)scale, sc.one, 0xFFFFFFFFu);                                                     \
+      if (BAL & 4) scale = (int)imad((uint32_t)scale, sc.one, 0xFFFFFFFFu); else --scale;                            \
+      if (BAL & 1) {                                                                                                 \
         idx = sc.zero; /* a zero the compiler cannot see: keeps the three steps below predicated IMADs */          \
         step_if_gt(tx_center, t_min, px, scale_exp2, idx, sc.one, sc.one); /* :328-330, exact adds */                \
         step_if_gt(ty_center, t_min, py, scale_exp2, idx, sc.one, sc.two);                                           \
         step_if_gt(tz_center, t_min, pz, scale_exp2, idx, sc.one, sc.four);                                          \
       } else {                                                                                                       \
-        --scale;                                                                                                     \
         const bool gx = tx_center > t_min, gy = ty_center > t_min, gz = tz_center > t_min; /* :328-330 */            \
         px = gx ? fadd(px, scale_exp2) : px; /* exact adds */                                                        \
         py = gy ? fadd(py, scale_exp2) : py;                                                                         \
         pz = gz ? fadd(pz, scale_exp2) : pz;                                                                         \
         idx = (gx ? 1u : 0u) | (gy ? 2u : 0u) | (gz ? 4u : 0u);                                                      \
       }                                                                                                              \
-      t_max = BAL ? fmove(tv_max, sc.one) : tv_max;                                                                  \
+      t_max = (BAL & 2) ? fmove(tv_max, sc.one) : tv_max;                                                                  \
       NEXT;                                                                                                          \
     }                                                                                                                \
   }                                                                                                                  \
@@ -464,7 +468,7 @@ struct Trav {
   if (NANCHECK && !(sx || sy || sz)) {                                                                               \
     /* all three corners are NaN (NaN direction from a zero or 555 normal): nothing changes any more and the   */    \
     /* reference spins to the cap (:264).  run() callers test this once, before the loop (nan_ray()).           */    \
-    if (STATS && iter <= (float)kMaxIterations) {                                                                    \
+    if (STATS == 1 && iter <= (float)kMaxIterations) {                                                               \
       const uint32_t code = (pd.y >> (2u * cs)) & 3u, left = (uint32_t)kMaxIterations - (uint32_t)iter;              \
       rs->iters += left;                                                                                             \
       rs->record_bytes += left * (code == 1u ? 3u : (code == 3u ? 1u : 7u));                                         \
@@ -473,12 +477,12 @@ struct Trav {
     EXIT(TRAV_MISS);                                                                                                 \
   }                                                                                                                  \
   uint32_t step_mask;                                                                                                \
-  if (BAL) {                                                                                                         \
+  if (BAL & 1) {                                                                                                     \
     step_mask = sc.zero;                                                                                             \
     step_if_le(tx_corner, tc_max, px, scale_exp2, step_mask, sc.one, sc.one);                                        \
     step_if_le(ty_corner, tc_max, py, scale_exp2, step_mask, sc.one, sc.two);                                        \
     step_if_le(tz_corner, tc_max, pz, scale_exp2, step_mask, sc.one, sc.four);                                       \
-    t_min = fmove(tc_max, sc.one);                                                                                   \
+    t_min = (BAL & 2) ? fmove(tc_max, sc.one) : tc_max;                                                              \
     move_if_gt(t_min, 0.05f, stop_scale, cone_stop, sc.one); /* :275-277 */                                          \
   } else {                                                                                                           \
     px = sx ? fsub(px, scale_exp2) : px;                                                                             \
@@ -504,13 +508,13 @@ struct Trav {
     if (sz) differing_bits |= __float_as_uint(pz) ^ __float_as_uint(fadd(pz, scale_exp2));                           \
     scale = (int)find_msb(differing_bits); /* findMSB */                                                             \
     if (scale >= kMaxScale) { EXIT(TRAV_MISS); } /* left the cube: the loop condition fails (:262) */                \
-    scale_exp2 = BAL ? __uint_as_float(imad((uint32_t)scale, sc.exp_unit, (uint32_t)(127 - kMaxScale) << 23))        \
+    scale_exp2 = (BAL & 8) ? __uint_as_float(imad((uint32_t)scale, sc.exp_unit, (uint32_t)(127 - kMaxScale) << 23))        \
                      : __uint_as_float((uint32_t)(scale - kMaxScale + 127) << 23);                                   \
     pd = stk_load<Trav>(stk, scale, pidx, t_max, sc);                                                                \
     const uint32_t shx = __float_as_uint(px) >> scale;                                                               \
     const uint32_t shy = __float_as_uint(py) >> scale;                                                               \
     const uint32_t shz = __float_as_uint(pz) >> scale;                                                               \
-    if (BAL) { /* x << scale as a multiplication by 2^scale; the child index assembled by IMADs */                  \
+    if (BAL & 8) { /* x << scale as a multiplication by 2^scale; the child index assembled by IMADs */                  \
       const uint32_t pow2 = sc.one << scale;                                                                         \
       px = __uint_as_float(imad(shx, pow2, 0u));                                                                     \
       py = __uint_as_float(imad(shy, pow2, 0u));                                                                     \
@@ -576,7 +580,7 @@ struct Trav {
 };
 
 // intersectOctree run to completion on the caller's stack.
-template <bool FAST, bool STATS, bool BOX, bool TOP, bool BAL = false, class Stk>
+template <bool FAST, int STATS, bool BOX, bool TOP, int BAL = 0, class Stk>
 __device__ __forceinline__ bool cast_ray_on(Stk stk, const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
                                             int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs, bool attrs) {
   Trav<FAST, STATS, BOX, TOP, BAL> T;
@@ -585,7 +589,7 @@ __device__ __forceinline__ bool cast_ray_on(Stk stk, const SceneView &sc, const 
   return T.finish(sc, T.run(sc, stk, rs), res, loops, attrs);
 }
 // ... on the default stack
-template <bool FAST, bool STATS = false, bool BOX = false, bool TOP = false>
+template <bool FAST, int STATS = 0, bool BOX = false, bool TOP = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
                                          int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr, bool attrs = true) {
   uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
@@ -835,7 +839,7 @@ SVO_DI void pixel_store(const SceneView &sc, const FrameParams &f, const Planes 
 
 // main (svotrace.comp:649-729) for pixel (x, y), run to completion.  STACK: 0 default, 1 WideStack, 2 SmemStack (`smem_stack` =
 // the thread's column of the CTA's shared-memory stack).
-template <bool FAST, bool AUX, bool STATS = false, bool BOX = false, bool TOP = false, int STACK = 0, bool BAL = false>
+template <bool FAST, bool AUX, int STATS = 0, bool BOX = false, bool TOP = false, int STACK = 0, int BAL = 0>
 __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FrameParams &f, const Planes &pl, int W, int H,
                                             int x, int y, RayStats *rs = nullptr, uint2 *smem_stack = nullptr) {
   Pixel P;

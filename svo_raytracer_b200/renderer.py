@@ -134,6 +134,11 @@ class SvoContext:
         """Render 8-row bands part, part+parts, ... in one launch (multi-GPU image partition)."""
         self._check(self._lib.svo_render_interleaved(self._h, C.byref(frame), int(part), int(parts)))
 
+    def render_interleaved_signal(self, frame: Frame, part: int, parts: int, fence_ptrs: Sequence[int] = (), slot: int = 0):
+        """render_interleaved + fence_signal(fence_ptrs, slot) in one launch (empty list: this context's own fence)."""
+        arr = (C.c_void_p * max(1, len(fence_ptrs)))(*[C.c_void_p(p) for p in fence_ptrs])
+        self._check(self._lib.svo_render_interleaved_signal(self._h, C.byref(frame), int(part), int(parts), arr, len(fence_ptrs), int(slot)))
+
     def beam(self, frame: Frame):
         self._check(self._lib.svo_beam(self._h, C.byref(frame)))
 
@@ -260,6 +265,12 @@ class SvoContext:
         """Instrumented render: the oracle's counters for this frame (see svo_render_stats)."""
         cnt = (C.c_uint64 * 3)()
         self._check(self._lib.svo_render_stats(self._h, C.byref(frame), C.byref(cnt)))
+        return {"casts": int(cnt[0]), "iters": int(cnt[1]), "record_bytes": int(cnt[2])}
+
+    def render_stats_executed(self, frame: Frame) -> dict:
+        """Counters of what the production kernel executes on this frame (content box on; see svo_render_stats_executed)."""
+        cnt = (C.c_uint64 * 3)()
+        self._check(self._lib.svo_render_stats_executed(self._h, C.byref(frame), C.byref(cnt)))
         return {"casts": int(cnt[0]), "iters": int(cnt[1]), "record_bytes": int(cnt[2])}
 
     def gather_probe(self, working_set_bytes: int, loads_per_thread: int = 256) -> float:

@@ -44,6 +44,8 @@ def lib():
         L.emu_launch_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int]
+        L.emu_fence_word.restype = C.c_uint
+        L.emu_fence_word.argtypes = [C.c_int]
         L.emu_launch_cast.restype = C.c_int
         L.emu_launch_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emu_cast.restype = C.c_int

@@ -24,6 +24,8 @@ static int g_last_launches = 0;
 
 extern "C" {
 
+unsigned int g_fence_words[2] = {0u, 0u};  // variant 17 bumps both when its last CTA leaves
+unsigned int emu_fence_word(int i) { return g_fence_words[i & 1]; }
 int emu_last_render_launches() { return g_last_launches; }  // kernels the last emu_launch_render enqueued (variant 15: 2)
 
 // svo_render_rows through the product's launch_render on the emulator.  kernel = SVO_OPT_KERNEL, ctas = CTAs of the
@@ -48,11 +50,17 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   cfg.kernel = kernel;
   cfg.stream_kernel = 0;
   cfg.sm_count = ctas;
+  cfg.scene_levels = 8;  // the emulator's worlds are at most 128^3
   cfg.ctas_per_sm = 1;
   cfg.band_stride = band_stride;
   cfg.band_offset = band_offset;
   cfg.band_ctas = band_rows / 8;
   cfg.tile_counter = &tile_counter;
+  unsigned int tile_queue[2] = {0u, 0u};  // variant 17: {next tile, CTAs that have left}
+  cfg.tile_queue = tile_queue;
+  cfg.fences.n = 0;
+  for (int i = 0; i < 16; i++) cfg.fences.p[i] = nullptr;
+  if (kernel == 17) { cfg.fences.n = 2; cfg.fences.p[0] = &g_fence_words[0]; cfg.fences.p[1] = &g_fence_words[1]; }
   std::vector<uint4> split_planes;
   unsigned int split_counters[2] = {0u, 0u};
   cfg.split = SplitQueue();
@@ -64,9 +72,11 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
     cfg.split.capacity = cap;
   }
   g_last_launches = render_launches(cfg, *f);
-  simt::g_os_threads = (kernel == 1 || kernel == 2) ? 1 : nthreads;  // persistent kernels: the queue is consumed by whichever block runs
+  simt::g_os_threads = (kernel == 1 || kernel == 2 || kernel == 17) ? 1 : nthreads;  // persistent kernels: the queue is consumed by whichever block runs
   if (kernel == 2) return emu_launch_wavefront(cfg, sc, *f, pl, W, H, y0, y1);  // wavefront_emu.cpp
-  return (int)launch_render(cfg, sc, *f, pl, W, H, y0, y1, nullptr);
+  const int rc = (int)launch_render(cfg, sc, *f, pl, W, H, y0, y1, nullptr);
+  if (kernel == 17 && (tile_queue[0] != 0u || tile_queue[1] != 0u)) return 700;  // the last CTA out must leave the queue ready for the next launch
+  return rc;
 }
 
 // svo_cast through the product's launch_cast on the emulator.  kernel 0 = grid-stride kernel, 1 = persistent threads with
@@ -82,10 +92,13 @@ int emu_launch_cast(const emu_scene *s, const void *rays, const uint32_t *order,
   cfg.kernel = 0;
   cfg.stream_kernel = kernel;
   cfg.sm_count = ctas;
+  cfg.scene_levels = 8;
   cfg.ctas_per_sm = 1;
   cfg.band_stride = cfg.band_offset = 0;
   cfg.band_ctas = 1;
   cfg.tile_counter = &counter;
+  cfg.tile_queue = nullptr;
+  cfg.fences.n = 0;
   cfg.split = SplitQueue();
   simt::g_os_threads = kernel == 1 ? 1 : nthreads;
   return (int)launch_cast(cfg, sc, rays, order, n, out, maxDepth, nullptr);

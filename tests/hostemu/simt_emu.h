@@ -144,6 +144,7 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
 static inline unsigned atomicAdd_system(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline long long clock64() { return 0; }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }

@@ -242,10 +242,13 @@ def test_errors_are_codes_not_crashes(svo, terrain128):
         assert (c.read_hit_id() == svo.NO_HIT).all()
 
 
-def test_interleaved_band_partition_single_gpu(svo, oracle, terrain128):
-    """svo_render_interleaved: parts 0..2 of 3 rendered one after the other fill the same frame the oracle renders."""
+@pytest.mark.parametrize("kernel", [17, 14, 0], ids=["tile_queue", "wide_bands", "tile"])
+def test_interleaved_band_partition_single_gpu(svo, oracle, terrain128, kernel):
+    """svo_render_interleaved: parts 0..2 of 3 rendered one after the other fill the same frame the oracle renders.
+    svo_render_interleaved_signal: the same plus the frame-complete fence, bumped once per launch."""
     W, H = 200, 117
     with svo.SvoContext(W, H) as c:
+        c.set_option(svo._lib.OPT_KERNEL, kernel)
         c.set_option(svo._lib.OPT_AUX_PLANES, 1)
         c.upload(terrain128)
         pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
@@ -259,6 +262,30 @@ def test_interleaved_band_partition_single_gpu(svo, oracle, terrain128):
             got = {"rgba8": c.read_color_rgba8(), "depth": c.read_depth(), "radiance": c.read_radiance(),
                    "hit_id": c.read_hit_id(), "iter": c.read_iter(), "primary_t": c.read_primary_t()}
             _assert_planes_equal(got, want, "interleaved %d rows x %d parts" % (band_rows, parts))
+        # fused signal on the context's own fence (slot 1): after `parts` launches the counter stands at `parts`
+        c.set_option(svo._lib.OPT_AUX_PLANES, 0)
+        c.set_option(svo._lib.OPT_BAND_ROWS, 8)
+        c.render(svo.camera_frame("A", frame_number=1, render_mode=3, max_depth=7))
+        for rep in range(2):
+            for part in range(5):
+                c.render_interleaved_signal(f, part, 5, (), slot=1)
+            c.fence_wait(5 * (rep + 1), slot=1)
+        c.sync()  # raises SVO_ERR_FENCE if a wait ran into the watchdog
+        assert np.array_equal(c.read_color_rgba8(), want["rgba8"]) and np.array_equal(c.read_depth().view(np.uint32), want["depth"].view(np.uint32))
+
+
+def test_fence_watchdog_is_reported(svo, terrain128):
+    """A wait nobody signals gives up after ~2 s; svo_sync reports it (the latch was invisible to the host)."""
+    with svo.SvoContext(64, 64) as c:
+        c.upload(terrain128)
+        c.fence_wait(1, slot=3)
+        with pytest.raises(svo.SvoError) as e:
+            c.sync()
+        assert e.value.code == svo._lib.ERR_FENCE
+        c.fence_reset()
+        c.fence_signal((), slot=3)
+        c.fence_wait(1, slot=3)
+        c.sync()
 
 
 def _ipc_worker(rank, world, port, q):
@@ -287,22 +314,40 @@ def _ipc_worker(rank, world, port, q):
         fh = [None] * world
         dist.all_gather_object(fh, ctx.fence_export())
         f = svo.camera_frame("B", frame_number=1, render_mode=2, max_depth=7)
-        for k in range(3):  # three frames: the peer may not overwrite a frame the owner has not consumed
-            if rank == 0:
-                peers = [ctx.ipc_import(fh[r]) for r in range(1, world)] if k == 0 else peers
-                ctx.render_interleaved(f, 0, world)
-                ctx.fence_signal()
-                ctx.fence_wait((k + 1) * world)
-                rgba, depth = ctx.read_color_rgba8(), ctx.read_depth()  # consume (stream-ordered after the wait)
-                ctx.fence_signal(peers)
-            else:
-                owner = [ctx.ipc_import(fh[0])] if k == 0 else owner
-                ctx.fence_wait(k)
-                ctx.render_interleaved(f, rank, world)
-                ctx.fence_signal(owner)
+        peers = [ctx.ipc_import(fh[r]) for r in range(1, world)] if rank == 0 else None
+        owner = [ctx.ipc_import(fh[0])] if rank != 0 else None
+        out = {}
+        k = 0
+        # 1) tile kernel + separate fence-signal launches; 2) the tile-queue kernel (variant 17) whose last CTA bumps the
+        # frame-complete fence itself: one launch per rank and frame.  Three frames each: the peer may not overwrite a
+        # frame the owner has not consumed.
+        for tag, kernel in (("separate", 0), ("fused", 17)):
+            ctx.set_option(L.OPT_KERNEL, kernel)
+            for _ in range(3):
+                if rank == 0:
+                    if tag == "fused":
+                        ctx.render_interleaved_signal(f, 0, world)
+                    else:
+                        ctx.render_interleaved(f, 0, world)
+                        ctx.fence_signal()
+                    ctx.fence_wait((k + 1) * world)
+                    out[tag] = (ctx.read_color_rgba8(), ctx.read_depth())  # consume (stream-ordered after the wait)
+                    ctx.fence_signal(peers)
+                else:
+                    ctx.fence_wait(k)
+                    if tag == "fused":
+                        ctx.render_interleaved_signal(f, rank, world, owner)
+                    else:
+                        ctx.render_interleaved(f, rank, world)
+                        ctx.fence_signal(owner)
+                k += 1
+            if rank == 0:  # scribble over the planes between the two passes
+                ctx.render(svo.camera_frame("A", frame_number=1, render_mode=3, max_depth=7))
+                ctx.sync()
+            dist.barrier()
         ctx.sync()
         if rank == 0:
-            q.put((rgba, depth))
+            q.put(out)
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -324,7 +369,7 @@ def test_two_gpu_tiles_over_nvlink(svo, oracle):
     procs = [ctx.Process(target=_ipc_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rgba, depth = q.get(timeout=300)
+    out = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -332,7 +377,9 @@ def test_two_gpu_tiles_over_nvlink(svo, oracle):
     nodes = svo.build_terrain(hm, mm, 128, 64)
     pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
     want, _ = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=2, max_depth=7), 320, 200, nthreads=4)
-    assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32))
+    for tag in ("separate", "fused"):
+        rgba, depth = out[tag]
+        assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32)), tag
 
 
 @pytest.mark.parametrize("kernel", [0, 4, 6])

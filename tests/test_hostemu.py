@@ -228,7 +228,7 @@ def test_simt_model_invariants(svo, oracle, terrain128, scene128):
 
 
 KERNEL_IDS = {0: "tile", 5: "tile64", 1: "persistent", 2: "wavefront", 6: "binned", 4: "smem", 7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack",
-              11: "regs72", 13: "balanced", 14: "wide_bands", 15: "split", 16: "split_presetup"}
+              11: "regs72", 13: "balanced", 14: "wide_bands", 15: "split", 16: "split_presetup", 17: "tile_queue", 19: "balanced_mask7"}
 
 
 @pytest.mark.parametrize("kernel", list(KERNEL_IDS), ids=list(KERNEL_IDS.values()))
@@ -249,7 +249,9 @@ def test_global_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kern
             _assert_planes_equal(got, want, "kernel %d cam %s aux" % (kernel, cam))
         got = scene128.launch_render(f, W, H, kernel=kernel, aux=False, box=True)
         _assert_planes_equal(got, want, "kernel %d cam %s production" % (kernel, cam), planes=("rgba8", "depth"))
-    if kernel in (0, 5, 14):  # interleaved bands of the multi-GPU tile partition, one launch per part
+    if kernel == 17:  # every launch bumped both fence words once, from its last CTA
+        assert E.lib().emu_fence_word(0) == E.lib().emu_fence_word(1) > 0
+    if kernel in (0, 5, 14, 17):  # interleaved bands of the multi-GPU tile partition, one launch per part
         pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
         f = oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=7)
         want, _ = oracle.render(terrain128, f, W, H, nthreads=8)

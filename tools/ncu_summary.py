@@ -20,6 +20,16 @@ KEYS = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "launch__registers_per_thread": "registers",
     "smsp__warps_eligible.avg.per_cycle_active": "eligible_warps_per_cycle",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "global_load_sectors",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum": "l1_miss_sectors",
+    "lts__t_sectors_srcunit_tex_op_read.sum": "l2_read_sectors",
+    "lts__t_sectors_srcunit_tex_op_write.sum": "l2_write_sectors",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio": "stall_math_pipe_throttle",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio": "stall_not_selected",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio": "stall_branch_resolving",
 }
 rep, out = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -41,7 +51,8 @@ for r in rows[2:]:
     res.append(d)
 json.dump(res, open(out + ".json", "w"), indent=1)
 cols = ["kernel", "duration_ms", "dram_traffic_MB", "dram_pct", "l2_pct", "l1_hit_pct", "l2_hit_pct", "issue_slot_util_pct", "alu_pipe_pct",
-        "fma_pipe_pct", "active_lanes_per_inst", "achieved_occupancy_pct", "registers", "warp_instructions"]
+        "fma_pipe_pct", "active_lanes_per_inst", "achieved_occupancy_pct", "registers", "warp_instructions", "l1_miss_sectors",
+        "stall_wait", "stall_long_scoreboard", "stall_math_pipe_throttle", "stall_not_selected"]
 with open(out + ".md", "w") as f:
     f.write("| " + " | ".join(cols) + " |\n|" + "---|" * len(cols) + "\n")
     for d in res:
