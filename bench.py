@@ -149,6 +149,43 @@ def world(size: int, cache_dir: str, rank: int = 0, barrier=None, nthreads: int 
     return nodes, time.time() - t0, "built"
 
 
+def heightmaps(size: int, cache_dir: str, rank: int = 0, barrier=None, nthreads: int = 0):
+    """The synthetic height and material maps (host code), generated once per box like world()."""
+    t0 = time.time()
+    path = os.path.join(cache_dir, "svo_bench_maps_terrain_%d_seed1.npz" % size) if cache_dir else None
+
+    def load():
+        z = np.load(path)
+        return z["hm"], z["mm"]
+    if path and os.path.exists(path):
+        if barrier:
+            barrier()
+        hm, mm = load()
+        return hm, mm, time.time() - t0, "cached"
+    hm = mm = None
+    if rank == 0:
+        L = _worldgen()
+        hm = np.empty((size, size), np.uint16)
+        mm = np.empty((size, size), np.uint8)
+        if L.svo_terrain_generate(size, 1, hm.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), nthreads) != 0:
+            raise RuntimeError("svo_terrain_generate failed")
+        if path:
+            try:
+                tmp = path + ".tmp.%d.npz" % os.getpid()
+                np.savez(tmp, hm=hm, mm=mm)
+                os.replace(tmp, path)
+            except OSError:
+                path = None
+    if barrier:
+        barrier()
+    if hm is None:
+        if path and os.path.exists(path):
+            hm, mm = load()
+        else:
+            hm, mm = heightmaps(size, "", 0, None, nthreads)[:2]
+    return hm, mm, time.time() - t0, "generated"
+
+
 def depth_for(size: int) -> int:
     return min(13, max(1, int(np.log2(size))))  # MAX_DEPTH = log2 N (13 for the reference's 8192^3, svotrace.comp:40)
 
@@ -352,18 +389,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    nodes, build_s, world_how = world(a.size, a.world_cache, rank, (lambda: dist.barrier()) if dist is not None else None,
-                                      max(1, cores // world_size))
     ctx = svo.SvoContext(W, H, device=dev)
     ctx.set_option(L.OPT_FAST_MATH, a.fast_math)
     if a.kernel >= 0:
         ctx.set_option(L.OPT_KERNEL, a.kernel)
     kernel_id = ctx.get_option(L.OPT_KERNEL)
     ctx.set_option(L.OPT_BAND_ROWS, a.band_rows)
+    # The world: height / material maps on the host (once per box), then every rank builds its replica of the octree ON
+    # ITS GPU (svo_build_terrain_device: the node stream is written straight into HBM and transcoded there).
+    nodes = None
+    rank_barrier = (lambda: dist.barrier()) if dist is not None else None
+    hm, mm, maps_s, maps_how = heightmaps(a.size, a.world_cache, rank, rank_barrier, max(1, cores // world_size))
     t0 = time.time()
-    ctx.upload(np.ascontiguousarray(nodes))
+    try:
+        tree_bytes = ctx.build_terrain_device(hm, mm, a.size, min(a.size, 1024))
+        ctx.sync()
+        world_how = "built on the device (svo_build_terrain_device), maps %s on the host" % maps_how
+    except svo.SvoError:
+        nodes, _, _ = world(a.size, a.world_cache, rank, rank_barrier, max(1, cores // world_size))
+        ctx.upload(np.ascontiguousarray(nodes))
+        tree_bytes = int(nodes.size)
+        world_how = "host builder + svo_upload (shape not taken by the device builder)"
     upload_s = time.time() - t0
+    build_s = maps_s + upload_s
+    del hm, mm
     info = ctx.scene_info()
+
 
     def frame_for(s):
         fp = frame_params(s, a.size, a)
@@ -613,6 +664,8 @@ def main():
     parity = None
     cpu = None
     if world_size == 1 and not a.no_cpu_baseline:
+        if nodes is None:
+            nodes = ctx.download()  # the CPU arm traces the stream the device built
         v, kind, sample, _, kept = cpu_arm(nodes, a, 3, a.warmup, a.cpu_seconds, cores, keep_planes=True)
         cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample,
                "what": "svotrace.comp compiled for the CPU by g++ (oracle/build_ref.py)" if kind == "reference" else "C restatement of svotrace.comp (oracle/svo_oracle.c)"}
@@ -712,10 +765,10 @@ def main():
         "metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_of(a, world_size, nodes.size, partition),
+        "config": config_of(a, world_size, tree_bytes, partition),
         "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "descriptors": info["descriptors"], "levels": info["levels"],
                          "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
-                         "world": {"how": world_how, "seconds": round(build_s, 2)}, "upload_transcode_s": round(upload_s, 2),
+                         "world": {"how": world_how, "seconds": round(build_s, 2), "maps_s": round(maps_s, 2)}, "build_and_transcode_s": round(upload_s, 3),
                          "units": ("one frame per step, interleaved %d-row bands per rank, peers store into rank 0's planes over NVLink, "
                                    "frame-complete fence = %s" % (a.band_rows, "remote atomics over NVLink, bumped by the render kernel's last CTA" if a.fence == "p2p" else "NCCL all-reduce")) if tiles else
                                   ("rank r renders progressive sample s*N+r of each view; no data-path exchange" if world_size > 1 else "one GPU renders every frame")},

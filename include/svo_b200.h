@@ -128,6 +128,16 @@ int svo_upload(svo_ctx *ctx, const uint8_t *nodes, uint64_t nbytes);
  * Main.java:349-350): `nodes` is the base of the whole buffer, bytes
  * [start,end) changed.  end may exceed the previous length (appended nodes). */
 int svo_upload_range(svo_ctx *ctx, const uint8_t *nodes, uint64_t start, uint64_t end);
+/* World generation ON THE DEVICE: the stream svo_build_terrain writes, built by kernels (min/max pyramids, level-
+ * synchronous classify / size / offset / emit sweeps; csrc/svo_gpu_build.cu) straight into HBM and made the
+ * context's scene as svo_upload would -- the node stream never crosses PCIe.  Replaces, for heightmap worlds,
+ * Octree.constructCompleteOctree (Octree.java:192-353) + constructInnerOctree (:511-608) + genSurfaceNormal
+ * (:620-649) + checkBigNodeExposed (:651-670) + chunkgen-heightmap.comp:13-31 and the addSSBO that follows
+ * (Main.java:122).  height / mat: n x n host arrays (row = z).  *out_bytes = Octree.memOffset. */
+int svo_build_terrain_device(svo_ctx *ctx, const uint16_t *height, const uint8_t *mat, int n, int chunk, uint64_t *out_bytes);
+/* The current scene's node stream back to the host (Octree.writeBufferToFile's payload, Octree.java:974-993);
+ * dst_cap >= info[0] of svo_scene_info. */
+int svo_download(svo_ctx *ctx, uint8_t *dst, uint64_t dst_cap);
 /* counts after upload: info[0] node-stream bytes, [1] interior descriptors,
  * [2] octree levels, [3] device bytes used by the scene */
 int svo_scene_info(const svo_ctx *ctx, uint64_t info[4]);

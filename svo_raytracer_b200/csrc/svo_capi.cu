@@ -14,6 +14,7 @@
 
 #include <cuda_runtime.h>
 
+#include "svo_gpu_build.h"
 #include "svo_kernels.h"
 #include "svo_transcode.h"
 
@@ -456,7 +457,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
     case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 21)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 24)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       c->opt_kernel = (int)value;
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
@@ -542,6 +543,38 @@ int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t 
   }
   SVO_CUDA(c, cudaMemcpyAsync(c->d_raw + start, nodes + start, end - start, cudaMemcpyHostToDevice, c->stream));
   return retranscode(c);
+}
+
+int svo_build_terrain_device(svo_ctx *c, const uint16_t *height, const uint8_t *mat, int n, int chunk, uint64_t *out_bytes) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!height || !mat || n < 2 || (n & (n - 1)) || chunk < 2 || (chunk & (chunk - 1))) return fail(c, SVO_ERR_INVALID, "bad heightmap / size / chunk");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // kernels may still be reading the previous scene
+  uint8_t *stream = nullptr;
+  uint64_t nbytes = 0, cap = 0, nl = 0;
+  bool unsupported = false;
+  SVO_CUDA(c, gpu_build_terrain(height, mat, n, chunk, &stream, &nbytes, &cap, &unsupported, c->stream, &nl));
+  if (unsupported)
+    return fail(c, SVO_ERR_INVALID, "the device builder takes chunk >= 4, at most 65535 sub-octrees and streams < 4 GiB; "
+                                    "use svo_build_terrain + svo_upload for this shape");
+  c->launches += nl;
+  c->have_scene = false;
+  if (c->d_raw) cudaFree(c->d_raw);
+  c->d_raw = stream;
+  c->raw_cap = cap;
+  c->nbytes = nbytes;
+  if (out_bytes) *out_bytes = nbytes;
+  return retranscode(c);
+}
+
+int svo_download(svo_ctx *c, uint8_t *dst, uint64_t cap) {
+  if (!c || !dst) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_download before a scene exists");
+  if (cap < c->nbytes) return fail(c, SVO_ERR_INVALID, "dst too small");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (c->nbytes) SVO_CUDA(c, cudaMemcpyAsync(dst, c->d_raw, c->nbytes, cudaMemcpyDeviceToHost, c->stream));
+  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SVO_OK;
 }
 
 int svo_scene_info(const svo_ctx *c, uint64_t info[4]) {

@@ -221,9 +221,9 @@ __device__ __forceinline__ void tile_body(const SceneView &sc, const FrameParams
   if (x >= W || y >= y1) return;
   shade_pixel<false, AUX, false, BOX, false, STACK, BAL>(sc, f, pl, W, H, x, y, nullptr, &s_stack[0][threadIdx.x]);
 }
-template <bool AUX, bool BOX, int BAL = 15>  // BAL: which parts of the loop run as IMADs (mask, see Trav); 15 = variant 13
-__global__ void __launch_bounds__(128, 8) k_render_tile_balanced(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
-  tile_body<AUX, BOX, 1, BAL>(sc, f, pl, W, H, y0, y1);
+template <bool AUX, bool BOX, int BAL = 15, int MINB = 8>  // BAL: which parts of the loop run as IMADs (mask, see Trav); 15 = variant 13
+__global__ void __launch_bounds__(128, MINB) k_render_tile_balanced(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
+  tile_body<AUX, BOX, 1, BAL>(sc, f, pl, W, H, y0, y1);  // MINB 7 / 6: 72 / 80 registers, so that the loop's constants (sc.one, ...) need not be re-loaded every iteration
 }
 template <bool AUX, bool BOX, int STACK>
 __global__ void __launch_bounds__(128, 8) k_render_tile_stack(SceneView sc, FrameParams f, Planes pl, int W, int H, int y0, int y1) {
@@ -919,7 +919,7 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
 #undef SVO_LAUNCH_BINNED
     return cudaGetLastError();
   }
-  if (cfg.kernel >= 18 && cfg.kernel <= 21 && !cfg.fast && !cfg.aux && cfg.band_stride == 0) {  // ablations of variant 13's parts (production instance only)
+  if (cfg.kernel >= 18 && cfg.kernel <= 24 && !cfg.fast && !cfg.aux && cfg.band_stride == 0) {  // ablations of variant 13's parts (production instance only)
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
 #define SVO_LAUNCH_BALMASK(B, M) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, M>)(sc, f, pl, W, H, y0, y1)
@@ -928,14 +928,17 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
     if (cfg.kernel == 18) SVO_LAUNCH_BALMASK(B, 13);       \
     else if (cfg.kernel == 19) SVO_LAUNCH_BALMASK(B, 7);   \
     else if (cfg.kernel == 20) SVO_LAUNCH_BALMASK(B, 1);   \
-    else SVO_LAUNCH_BALMASK(B, 5);                         \
+    else if (cfg.kernel == 21) SVO_LAUNCH_BALMASK(B, 5);   \
+    else if (cfg.kernel == 22) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 7>)(sc, f, pl, W, H, y0, y1); \
+    else if (cfg.kernel == 23) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 1, 7>)(sc, f, pl, W, H, y0, y1);  \
+    else SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 6>)(sc, f, pl, W, H, y0, y1);                       \
   } while (0)
     if (cfg.box) SVO_LAUNCH_BAL(true); else SVO_LAUNCH_BAL(false);
 #undef SVO_LAUNCH_BAL
 #undef SVO_LAUNCH_BALMASK
     return cudaGetLastError();
   }
-  if (cfg.kernel >= 18 && cfg.kernel <= 21) cfg.kernel = 13;
+  if (cfg.kernel >= 18 && cfg.kernel <= 24) cfg.kernel = 13;
   if (cfg.kernel == 9 && !smem_stack_fits(cfg, f)) cfg.kernel = 13;
   if (cfg.kernel >= 9 && cfg.kernel <= 13 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || smem_stack_fits(cfg, f))) {
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);

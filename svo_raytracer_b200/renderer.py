@@ -112,6 +112,22 @@ class SvoContext:
             raise ValueError("end beyond the buffer")
         self._check(self._lib.svo_upload_range(self._h, nodes.ctypes.data_as(C.c_void_p), int(start), int(end)))
 
+    def build_terrain_device(self, height: np.ndarray, mat: np.ndarray, n: int, chunk: int = 1024) -> int:
+        """World generation on the device (svo_build_terrain_device); the result becomes this context's scene.  Returns the stream size."""
+        height = np.ascontiguousarray(height, dtype=np.uint16)
+        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        if height.shape != (n, n) or mat.shape != (n, n):
+            raise ValueError("height and mat must be (n, n)")
+        nb = C.c_uint64()
+        self._check(self._lib.svo_build_terrain_device(self._h, height.ctypes.data_as(C.c_void_p), mat.ctypes.data_as(C.c_void_p), n, chunk, C.byref(nb)))
+        return int(nb.value)
+
+    def download(self) -> np.ndarray:
+        """The scene's node stream back on the host."""
+        out = np.empty(self.scene_info()["stream_bytes"], dtype=np.uint8)
+        self._check(self._lib.svo_download(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
     def scene_probe(self):
         """Hash / counts / bounds of the descriptors held on the device (same 8 words as svo_transcode_probe)."""
         out = (C.c_uint64 * 8)()

@@ -11,9 +11,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.normpath(os.path.join(_HERE, "..", "..", "svo_raytracer_b200", "csrc"))
 _LIB_PATH = os.path.join(_HERE, "libsvo_hostemu.so")
-_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
+_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "gpu_build_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
 _SRCS = _CPP + [os.path.join(_HERE, f) for f in ("cuda_host_shim.h", "simt_emu.h", "emu_scene.h")] + \
-    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_wavefront.cu", "svo_transcode.h")]
+    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_wavefront.cu", "svo_transcode.h", "svo_gpu_build.cu", "svo_gpu_build.h")]
 CUDA_INCLUDE = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 
@@ -44,6 +44,8 @@ def lib():
         L.emu_launch_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int]
+        L.emu_gpu_build_terrain.restype = C.c_int
+        L.emu_gpu_build_terrain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
         L.emu_fence_word.restype = C.c_uint
         L.emu_fence_word.argtypes = [C.c_int]
         L.emu_launch_cast.restype = C.c_int
@@ -212,3 +214,16 @@ def selftest(blocks=3, os_threads=2):
 
 def math(fn: int, x: float, y: float = 0.0) -> float:
     return float(lib().emu_math(fn, float(x), float(y)))
+
+
+def gpu_build_terrain(height, mat, n, chunk, nthreads=8):
+    """svo_gpu_build.cu (world generation on the device) on the SIMT emulator.  Returns the node stream."""
+    height = np.ascontiguousarray(height, dtype=np.uint16)
+    mat = np.ascontiguousarray(mat, dtype=np.uint8)
+    nb = C.c_uint64(0)
+    rc = lib().emu_gpu_build_terrain(_ptr(height), _ptr(mat), n, chunk, None, 0, C.byref(nb), nthreads)
+    assert rc == 0, rc
+    out = np.zeros(int(nb.value), np.uint8)
+    rc = lib().emu_gpu_build_terrain(_ptr(height), _ptr(mat), n, chunk, _ptr(out), out.size, C.byref(nb), nthreads)
+    assert rc == 0, rc
+    return out

@@ -115,6 +115,21 @@ static inline T __shfl_sync(uint32_t, T v, int src) {
   memcpy(&out, &raw, sizeof(T));
   return out;
 }
+template <class T>
+static inline T __shfl_xor_sync(uint32_t, T v, int lane_mask) {
+  static_assert(sizeof(T) <= 8, "shfl of up to 8 bytes");
+  simt::Block *b = simt::g_block;
+  const int w = b->cur >> 5, l = b->cur & 31;
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  b->val[b->cur] = raw;
+  simt::warp_barrier();
+  raw = b->val[w * 32 + ((l ^ lane_mask) & 31)];
+  simt::warp_barrier();
+  T out;
+  memcpy(&out, &raw, sizeof(T));
+  return out;
+}
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
   simt::Block *b = simt::g_block;
   const int w = b->cur >> 5;
@@ -150,6 +165,10 @@ static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline uint16_t min(uint16_t a, uint16_t b) { return a < b ? a : b; }
+static inline uint16_t max(uint16_t a, uint16_t b) { return a > b ? a : b; }
+static inline uint8_t min(uint8_t a, uint8_t b) { return a < b ? a : b; }
+static inline uint8_t max(uint8_t a, uint8_t b) { return a > b ? a : b; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 

@@ -94,3 +94,34 @@ def test_terrain_generator_is_deterministic(svo):
     # pinned digest: the synthetic inputs of the benchmark never drift silently
     assert hashlib.sha256(hm1.tobytes() + mm1.tobytes()).hexdigest() == open(
         __import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "terrain256_seed1.sha256")).read().strip()
+
+
+def _adversarial_maps(n, rng):
+    cases = [(np.full((n, n), 30000, np.uint16), np.full((n, n), 1, np.uint8)),
+             (np.full((n, n), 30000, np.uint16), np.full((n, n), 3, np.uint8)),
+             (np.zeros((n, n), np.uint16), np.full((n, n), 2, np.uint8)),
+             (np.full((n, n), 65535, np.uint16), rng.integers(1, 4, (n, n)).astype(np.uint8))]
+    spikes = np.full((n, n), 8000, np.uint16)
+    spikes[::7, ::5] = 60000
+    cases.append((spikes, rng.integers(1, 4, (n, n)).astype(np.uint8)))
+    cases.append((rng.integers(0, 65536, (n, n)).astype(np.uint16), rng.integers(1, 4, (n, n)).astype(np.uint8)))
+    steps = (np.arange(n)[None, :] // 8 * 9000).astype(np.uint16) + np.zeros((n, 1), np.uint16)
+    cases.append((steps, np.where(np.arange(n)[:, None] % 2 == 0, 1, 2).astype(np.uint8) + np.zeros((1, n), np.uint8)))
+    return cases
+
+
+@pytest.mark.parametrize("n,chunk", [(8, 4), (32, 32), (64, 16), (128, 32), (128, 128)])
+def test_device_builder_kernels_on_simt_emulator(svo, n, chunk):
+    """svo_gpu_build.cu -- world generation ON THE DEVICE (pyramid kernels, level-synchronous classify / size / offset /
+    emit sweeps) -- run on the coroutine SIMT emulator: the stream equals svo_build_terrain's byte for byte (and with
+    it, by the tests above, the brute-force restatement of Octree.java).  The same comparison runs on the B200 in
+    tests/test_gpu_build.py."""
+    from hostemu import emu as E
+    for seed in (1, 7):
+        hm, mm = svo.terrain_inputs(n, seed=seed)
+        want = svo.build_terrain(hm, mm, n, chunk)
+        got = E.gpu_build_terrain(hm, mm, n, chunk)
+        assert got.size == want.size and np.array_equal(got, want), (n, chunk, seed)
+    if n == 64:
+        for hm, mm in _adversarial_maps(n, np.random.default_rng(11)):
+            assert np.array_equal(E.gpu_build_terrain(hm, mm, n, chunk), svo.build_terrain(hm, mm, n, chunk))
