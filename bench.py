@@ -428,9 +428,9 @@ def main():
         # ONE frame per step, image bands interleaved over the ranks, replicated octree.  Rank 0 owns the frame
         # buffer; every peer maps it (CUDA IPC over NVLink) and its kernel stores its bands straight into it.
         frames = [frame_for(s) for s in range(total + 3)]
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         drain = lambda: None
         if a.fence == "nccl":
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)  # the all-reduce runs on torch's stream
             handles = [ctx.ipc_export(p) for p in PL] if rank == 0 else [None, None]
             dist.broadcast_object_list(handles, src=0)
             if rank != 0:
@@ -470,7 +470,9 @@ def main():
                 for plane, ptr in zip(PL, sets[k & 1]):
                     ctx.bind_plane(plane, ptr)
 
+            # Frame k lives on lane k&1 (stream + plane set): frame k+1's kernel may start while frame k's last tiles drain.
             def finish(j, consume):
+                ctx.select_lane(j & 1)
                 ctx.fence_wait((j // 2 + 1) * world_size, slot=2 + (j & 1))  # every GPU has stored its bands of frame j
                 if consume is not None:
                     bind(j)
@@ -480,6 +482,7 @@ def main():
             def render_step(s, consume=None, release=False):
                 k = state["k"]
                 state["k"] = k + 1
+                ctx.select_lane(k & 1)
                 if rank == 0:
                     bind(k)
                     ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=2 + (k & 1))
@@ -508,6 +511,8 @@ def main():
         drain = lambda: None
 
         def render_step(s, consume=None, release=False):
+            if not a.accumulate:  # (a running mean lives in ONE plane set)
+                ctx.select_lane(s & 1)  # consecutive frames on alternating lanes (stream + plane set): frame s+1 may start while frame s's last tiles drain
             ctx.render(frames[s])
             if consume is not None:
                 consume()

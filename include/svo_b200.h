@@ -26,6 +26,7 @@ extern "C" {
 #define SVO_ABI_VERSION 1
 #define SVO_NO_HIT 0xFFFFFFFFu
 #define SVO_FRAME_ACCUMULATE 1
+#define SVO_FRAME_BEAM_FLOOR 2
 
 enum svo_status {
   SVO_OK = 0,
@@ -57,7 +58,8 @@ typedef struct svo_frame {
   int32_t casts;
   int32_t coneDepth;
   int32_t mirrorValue;
-  int32_t flags; /* bit 0 (SVO_FRAME_ACCUMULATE): progressive running mean over frameNumber, the block the shader
+  int32_t flags; /* bit 1 (SVO_FRAME_BEAM_FLOOR): the beam plane holds svo_beam_conservative's lower bounds; primary casts start there.
+                  * bit 0 (SVO_FRAME_ACCUMULATE): progressive running mean over frameNumber, the block the shader
                   * has commented out at svotrace.comp:712-719; other bits must be 0 */
 } svo_frame;
 
@@ -157,7 +159,24 @@ int svo_render_interleaved(svo_ctx *ctx, const svo_frame *frame, int part, int p
 int svo_render_interleaved_signal(svo_ctx *ctx, const svo_frame *frame, int part, int parts, void *const *fence_ptrs, int n, int slot);
 /* replaces dispatchCompute(beamShader, W/8/4, H/8/4, 1) (Main.java:257-266) */
 int svo_beam(svo_ctx *ctx, const svo_frame *frame);
+/* The beam optimisation done conservatively (what svobeam.comp set out to do; its own version is neither a lower bound
+ * nor in the fine pass's units): fills the beam plane with, per 4x4 pixel block, a PROVEN lower bound on the
+ * primary hit distance of its 16 pixels (+inf: all 16 miss) from normalised rays through the block corners with an LOD
+ * stop at 2*sqrt(2) lattice spacings, a min filter over +-4 lattice steps and the node-diagonal margin
+ * (csrc/svo_kernels.cu, k_beam_lattice / k_beam_minfilter).  A frame rendered with flags | SVO_FRAME_BEAM_FLOOR (and
+ * useBeam = 0) starts every primary cast's walk there: colour, depth and hit are unchanged bit for bit, only loop
+ * iterations are saved.  Like the content box it is ignored in render mode 1 and with SVO_OPT_AUX_PLANES (iteration counts
+ * are observable there). */
+int svo_beam_conservative(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
+/* Two lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
+ * `lane` (0 or 1) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
+ * Work on different lanes may overlap on the GPU: rendering frame k+1 on the other lane lets its first tiles fill the SMs
+ * that frame k's last, longest tiles leave idle (measured: a 1080p frame carries ~0.13 ms of such tail).  Frames on one
+ * lane stay ordered; svo_sync, svo_timer_*, uploads, the beam passes and svo_cast order both lanes.  svo_swap_buffers is
+ * svo_select_lane(other) + the wait for that set's last read-back.  With a caller-owned stream (svo_set_stream), with
+ * SVO_OPT_AUX_PLANES or with a kernel variant whose workspace exists once (1, 2, 15, 16) both lanes share one stream. */
+int svo_select_lane(svo_ctx *ctx, int lane);
 
 /* -- readback: replaces glGetTexImage(depth) every frame (Main.java:132-146).
  *    dst is host memory (pinned or pageable), width*height elements. */

@@ -60,6 +60,7 @@ SYMBOLS = {
     "svo_render_interleaved": (_i, [_vp, C.POINTER(Frame), _i, _i]),
     "svo_render_interleaved_signal": (_i, [_vp, C.POINTER(Frame), _i, _i, C.POINTER(_vp), _i, _i]),
     "svo_beam": (_i, [_vp, C.POINTER(Frame)]),
+    "svo_beam_conservative": (_i, [_vp, C.POINTER(Frame)]),
     "svo_sync": (_i, [_vp]),
     "svo_read_plane": (_i, [_vp, _i, _vp, _u64]),
     "svo_read_plane_rows": (_i, [_vp, _i, _i, _i, _vp, _u64]),
@@ -72,6 +73,7 @@ SYMBOLS = {
     "svo_read_radiance_f32": (_i, [_vp, _vp]),
     "svo_read_planes_async": (_i, [_vp, _vp, _vp]),
     "svo_swap_buffers": (_i, [_vp]),
+    "svo_select_lane": (_i, [_vp, _i]),
     "svo_read_wait": (_i, [_vp]),
     "svo_device_ptr": (_vp, [_vp, _i]),
     "svo_bind_plane": (_i, [_vp, _i, _vp]),

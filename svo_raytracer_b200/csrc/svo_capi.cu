@@ -29,6 +29,12 @@ struct svo_ctx {
   int device = 0;
   int W = 0, H = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // Two lanes (svo_select_lane): a stream and a colour/depth plane set each.  Work enqueued on different lanes may overlap on
+  // the GPU: frame k+1's first tiles fill the SMs that frame k's last, longest tiles leave idle (the tail of a 1080p frame is
+  // ~0.13 ms of a 0.4-1.4 ms kernel).  `stream` is always the current lane's stream.
+  cudaStream_t own_stream2 = nullptr, lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_lane[2] = {nullptr, nullptr};
+  int lane = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0;
   // scene
@@ -65,6 +71,7 @@ struct svo_ctx {
   std::vector<IpcMap> ipc_maps;  // peer blocks opened by svo_ipc_import
   WaveWorkspace ws{};  // wavefront variant, allocated on first use
   void *ws_block = nullptr;
+  float *d_beam_lattice = nullptr;  // conservative beam pre-pass: (W/4+1) x (H/4+1) lattice-ray distances
   void *split_block = nullptr;  // variant 15: record queue
   SplitQueue split = {};
   int ctas_per_sm = 8;
@@ -73,6 +80,30 @@ struct svo_ctx {
 };
 
 static int ensure_pipeline(svo_ctx *c);
+
+// kernels whose workspace exists once per context (wavefront queues, split queue, the persistent kernel's counter) and the
+// validation planes (one set) cannot run on two lanes at once: both lanes then share lane 0's stream
+static bool lanes_share_stream(const svo_ctx *c) {
+  return c->opt_aux || c->opt_kernel == 1 || c->opt_kernel == 2 || c->opt_kernel == 15 || c->opt_kernel == 16 || c->lane_stream[0] == c->lane_stream[1];
+}
+static void refresh_stream(svo_ctx *c) { c->stream = lanes_share_stream(c) ? c->lane_stream[0] : c->lane_stream[c->lane]; }
+// order everything enqueued on the other lane before what the current lane enqueues next
+static cudaError_t join_lanes(svo_ctx *c) {
+  if (c->lane_stream[0] == c->lane_stream[1]) return cudaSuccess;
+  for (int l = 0; l < 2; l++) {
+    if (c->lane_stream[l] == c->stream) continue;
+    cudaError_t e = cudaEventRecord(c->ev_lane[l], c->lane_stream[l]);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(c->stream, c->ev_lane[l], 0)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+static cudaError_t sync_lanes(svo_ctx *c) {
+  cudaError_t e = cudaStreamSynchronize(c->lane_stream[0]);
+  if (e != cudaSuccess) return e;
+  if (c->lane_stream[1] != c->lane_stream[0]) e = cudaStreamSynchronize(c->lane_stream[1]);
+  return e;
+}
 
 namespace {
 
@@ -193,7 +224,7 @@ LaunchCfg launch_cfg(const svo_ctx *c) {
   l.band_ctas = c->opt_band_rows / 8;
   l.ctas_per_sm = c->ctas_per_sm;
   l.tile_counter = c->d_tile_counter;
-  l.tile_queue = c->d_tile_counter + 2;  // words 2, 3: zero between launches (the last CTA out resets them)
+  l.tile_queue = c->d_tile_counter + 2 + 2 * c->lane;  // two words per lane, zero between launches (the last CTA out resets them)
   l.fences.n = 0;
   for (int i = 0; i < 16; i++) l.fences.p[i] = nullptr;
   l.split = c->split;
@@ -216,7 +247,9 @@ int check_frame(svo_ctx *c, const svo_frame *f) {
   if (f->maxDepth < 1 || f->maxDepth > 23) return fail(c, SVO_ERR_INVALID, "maxDepth must be in [1,23]");
   if (f->coneDepth < 1 || f->coneDepth > 23) return fail(c, SVO_ERR_INVALID, "coneDepth must be in [1,23]");
   if (f->casts < 0 || f->casts > 64) return fail(c, SVO_ERR_INVALID, "casts must be in [0,64]");
-  if ((f->flags & ~SVO_FRAME_ACCUMULATE) != 0) return fail(c, SVO_ERR_INVALID, "unknown bits in flags");
+  if ((f->flags & ~(SVO_FRAME_ACCUMULATE | SVO_FRAME_BEAM_FLOOR)) != 0) return fail(c, SVO_ERR_INVALID, "unknown bits in flags");
+  if ((f->flags & SVO_FRAME_BEAM_FLOOR) && f->useBeam)
+    return fail(c, SVO_ERR_INVALID, "the beam plane holds either upstream's beam distances (useBeam) or conservative bounds (SVO_FRAME_BEAM_FLOOR), not both");
   return SVO_OK;
 }
 
@@ -256,7 +289,7 @@ int retranscode(svo_ctx *c) {
   bool done = false;
   c->have_scene = false;  // until the descriptor arrays match d_raw again (a refused stream leaves the context without a scene)
   // the kernels may still be reading the previous arrays
-  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  SVO_CUDA(c, sync_lanes(c));
   if (c->opt_gpu_transcode) {
     // a tree has at most one interior record per 7 bytes; anything larger is aliased/cyclic and goes to the host
     // path, which reports it
@@ -398,7 +431,13 @@ int svo_create(svo_ctx **out, int device, int width, int height) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaGetDeviceProperties"); break; }
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream2, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
+    c->lane_stream[0] = c->own_stream;
+    c->lane_stream[1] = c->own_stream2;
     c->stream = c->own_stream;
+    for (int l = 0; l < 2; l++)
+      if ((e = cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming)) != cudaSuccess) break;
+    if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
     if ((e = cudaMalloc((void **)&c->d_tile_counter, 64)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(counter)"); break; }
     cudaMemsetAsync(c->d_tile_counter, 0, 64, c->stream);
@@ -422,6 +461,7 @@ void svo_destroy(svo_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  if (c->own_stream2) cudaStreamSynchronize(c->own_stream2);
   for (auto &m : c->ipc_maps) cudaIpcCloseMemHandle(m.base);
   for (int p = 0; p < 7; p++)
     if (c->own[p]) cudaFree(c->own[p]);
@@ -442,9 +482,13 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_fence) cudaFree(c->d_fence);
   if (c->ws_block) cudaFree(c->ws_block);
   if (c->split_block) cudaFree(c->split_block);
+  if (c->d_beam_lattice) cudaFree(c->d_beam_lattice);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->own_stream2) cudaStreamDestroy(c->own_stream2);
+  for (int l = 0; l < 2; l++)
+    if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]);
   cudaGetLastError();
   delete c;
 }
@@ -454,11 +498,17 @@ const char *svo_last_error(const svo_ctx *c) { return c ? c->err.c_str() : g_err
 int svo_set_option(svo_ctx *c, int option, int64_t value) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   switch (option) {
-    case SVO_OPT_AUX_PLANES: c->opt_aux = value != 0; return SVO_OK;
+    case SVO_OPT_AUX_PLANES:
+      if (cudaSetDevice(c->device) == cudaSuccess) sync_lanes(c);
+      c->opt_aux = value != 0;
+      refresh_stream(c);
+      return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
       if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 24)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (cudaSetDevice(c->device) == cudaSuccess) sync_lanes(c);
       c->opt_kernel = (int)value;
+      refresh_stream(c);
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
     case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
@@ -494,8 +544,11 @@ int svo_get_option(const svo_ctx *c, int option, int64_t *value) {
 int svo_set_stream(svo_ctx *c, void *cuda_stream) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
-  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  SVO_CUDA(c, sync_lanes(c));
+  // a caller-owned stream carries both lanes (no overlap between frames); NULL restores the context's two streams
+  c->lane_stream[0] = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  c->lane_stream[1] = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream2;
+  refresh_stream(c);
   return SVO_OK;
 }
 
@@ -505,8 +558,9 @@ int svo_upload(svo_ctx *c, const uint8_t *nodes, uint64_t nbytes) {
   if (nbytes >= (1ull << 32)) return fail(c, SVO_ERR_INVALID, "node stream must be < 4 GiB");
   SVO_CUDA(c, cudaSetDevice(c->device));
   c->have_scene = false;
+  SVO_CUDA(c, join_lanes(c));
   if (nbytes + 16 > c->raw_cap) {
-    SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVO_CUDA(c, sync_lanes(c));
     if (c->d_raw) cudaFree(c->d_raw);
     c->d_raw = nullptr;
     c->raw_cap = 0;
@@ -526,11 +580,12 @@ int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t 
   if (!nodes || start >= end) return fail(c, SVO_ERR_INVALID, "Update SSBO error: Invalid parameters.");
   if (end >= (1ull << 32)) return fail(c, SVO_ERR_INVALID, "node stream must be < 4 GiB");
   SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, join_lanes(c));
   if (end + 16 > c->raw_cap) {  // appended nodes outgrew the allocation: move the stream
     uint8_t *nr = nullptr;
     const uint64_t cap = end + end / 4 + 4096;
     SVO_CUDA(c, cudaMalloc((void **)&nr, cap));
-    SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVO_CUDA(c, sync_lanes(c));
     if (c->nbytes) SVO_CUDA(c, cudaMemcpy(nr, c->d_raw, c->nbytes, cudaMemcpyDeviceToDevice));
     cudaFree(c->d_raw);
     c->d_raw = nr;
@@ -549,7 +604,7 @@ int svo_build_terrain_device(svo_ctx *c, const uint16_t *height, const uint8_t *
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (!height || !mat || n < 2 || (n & (n - 1)) || chunk < 2 || (chunk & (chunk - 1))) return fail(c, SVO_ERR_INVALID, "bad heightmap / size / chunk");
   SVO_CUDA(c, cudaSetDevice(c->device));
-  SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // kernels may still be reading the previous scene
+  SVO_CUDA(c, sync_lanes(c));  // kernels may still be reading the previous scene
   uint8_t *stream = nullptr;
   uint64_t nbytes = 0, cap = 0, nl = 0;
   bool unsupported = false;
@@ -658,6 +713,7 @@ int svo_beam(svo_ctx *c, const svo_frame *frame) {
   int rc = check_frame(c, frame);
   if (rc) return rc;
   SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, join_lanes(c));  // one beam plane per context
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
   SVO_CUDA(c, launch_beam(launch_cfg(c), scene_view(c), fp, (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
@@ -665,10 +721,25 @@ int svo_beam(svo_ctx *c, const svo_frame *frame) {
   return SVO_OK;
 }
 
+int svo_beam_conservative(svo_ctx *c, const svo_frame *frame) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_beam_conservative before svo_upload");
+  int rc = check_frame(c, frame);
+  if (rc) return rc;
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  if (!c->d_beam_lattice) SVO_CUDA(c, cudaMalloc((void **)&c->d_beam_lattice, (size_t)(c->W / 4 + 1) * (size_t)(c->H / 4 + 1) * sizeof(float) + 16));
+  SVO_CUDA(c, join_lanes(c));  // one beam plane and one lattice scratch per context
+  FrameParams fp;
+  memcpy(&fp, frame, sizeof fp);
+  SVO_CUDA(c, launch_beam_conservative(scene_view(c), fp, c->d_beam_lattice, (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
+  c->launches += 2;
+  return SVO_OK;
+}
+
 int svo_sync(svo_ctx *c) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
-  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  SVO_CUDA(c, sync_lanes(c));
   if (c->fence_waits_unchecked) {  // did a frame-complete wait give up (k_fence_wait's watchdog)?  Frames since then are incomplete.
     unsigned int dead = 0;
     SVO_CUDA(c, cudaMemcpy(&dead, c->d_fence + 7, sizeof dead, cudaMemcpyDeviceToHost));
@@ -736,7 +807,23 @@ int svo_swap_buffers(svo_ctx *c) {
   int rc = ensure_pipeline(c);
   if (rc) return rc;
   c->render_set ^= 1;
+  c->lane = c->render_set;  // the other set is drawn on the other lane: consecutive frames may overlap on the GPU
+  refresh_stream(c);
   // the next render overwrites this set: wait (on the device) until its last read-back has left it
+  SVO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[c->render_set], 0));
+  return SVO_OK;
+}
+
+int svo_select_lane(svo_ctx *c, int lane) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (lane != 0 && lane != 1) return fail(c, SVO_ERR_INVALID, "lane must be 0 or 1");
+  if (lane == c->lane) return SVO_OK;
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_pipeline(c);
+  if (rc) return rc;
+  c->lane = lane;
+  c->render_set = lane;
+  refresh_stream(c);
   SVO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[c->render_set], 0));
   return SVO_OK;
 }
@@ -818,6 +905,7 @@ int svo_fence_wait(svo_ctx *c, int slot, uint32_t target) {
 int svo_fence_reset(svo_ctx *c) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, sync_lanes(c));
   SVO_CUDA(c, cudaMemsetAsync(c->d_fence, 0, 256, c->stream));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
   return SVO_OK;
@@ -850,7 +938,7 @@ int svo_ipc_close(svo_ctx *c, void *device_ptr) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   (void)device_ptr;
   SVO_CUDA(c, cudaSetDevice(c->device));
-  SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+  SVO_CUDA(c, sync_lanes(c));
   for (auto &m : c->ipc_maps) cudaIpcCloseMemHandle(m.base);
   c->ipc_maps.clear();
   cudaGetLastError();
@@ -863,6 +951,7 @@ int svo_cast_device(svo_ctx *c, const void *d_rays, uint64_t n, void *d_out, int
   if (maxDepth < 1 || maxDepth > 23) return fail(c, SVO_ERR_INVALID, "maxDepth must be in [1,23]");
   if (n && (!d_rays || !d_out)) return fail(c, SVO_ERR_INVALID, "NULL ray or hit buffer");
   SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, join_lanes(c));  // sort scratch and the persistent stream kernel's counter exist once
   const uint32_t *order = nullptr;
   if (c->opt_sort && n >= 65536 && n < (1ull << 31)) {  // bin by octant + origin Morton code; results go back to the caller's order
     if (n > c->sort_cap) {
@@ -914,12 +1003,17 @@ int svo_cast(svo_ctx *c, const svo_ray *rays, uint64_t n, svo_hit *out, int maxD
 int svo_timer_begin(svo_ctx *c) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, join_lanes(c));  // the interval starts after everything enqueued so far, on either lane ...
   SVO_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  // ... and nothing enqueued on the other lane from now on may start before it
+  for (int l = 0; l < 2; l++)
+    if (c->lane_stream[l] != c->stream) SVO_CUDA(c, cudaStreamWaitEvent(c->lane_stream[l], c->ev0, 0));
   return SVO_OK;
 }
 int svo_timer_end(svo_ctx *c, float *ms) {
   if (!c || !ms) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
   SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, join_lanes(c));  // ... and ends when both lanes have drained
   SVO_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   SVO_CUDA(c, cudaEventSynchronize(c->ev1));
   SVO_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -990,6 +1084,7 @@ static int render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]
   if (rc) return rc;
   SVO_CUDA(c, cudaSetDevice(c->device));
   if ((rc = ensure_aux(c)) != SVO_OK) return rc;
+  SVO_CUDA(c, join_lanes(c));
   DevBuf dbuf;
   SVO_CUDA(c, dbuf.alloc(3 * sizeof(unsigned long long)));
   unsigned long long *d = dbuf.as<unsigned long long>();

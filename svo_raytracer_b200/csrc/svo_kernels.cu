@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(128, 8) k_split_bounce(SceneView sc, FramePara
       P.color = mk3(0.0f, 0.0f, 0.0f);
       P.depth = 0.0f;
       P.beamDist = 0.0f;
+      P.t_floor = 0.0f;
       P.hit_id = kNoHit;
       P.iter = 0;
       P.primary_t = 0.0f;
@@ -838,6 +839,86 @@ __global__ void __launch_bounds__(128) k_beam(SceneView sc, FrameParams f, float
   uint32_t loops = 0;
   const bool hit = cast_ray<FAST>(sc, mk3(f.camPos[0], f.camPos[1], f.camPos[2]), dir, f.maxDepth, false, f.coneDepth, res, loops);
   beam[(size_t)gy * (size_t)bw + (size_t)gx] = hit ? res.t : 0.0f;
+}
+
+// ---------------------------------------------------------------------------
+// Conservative beam pre-pass (what svobeam.comp:617-636 set out to do, done so that the frame cannot
+// change).  Upstream casts ONE un-normalised ray through the first pixel of every 4x4 block and starts the block's 16
+// fine rays at its hit distance: not a lower bound (a block's other pixels can hit earlier), in different units than
+// the fine pass's normalised rays, undefined on a miss.  Here:
+//  1. k_beam_lattice casts a NORMALISED ray through every corner of the 4x4 pixel grid ((W/4+1) x (H/4+1) lattice rays)
+//     with an LOD stop: a non-empty node no larger than kappa x the lattice spacing at that distance counts as solid.
+//     It reports t_entry - sqrt(3) * node size: no ray from the same origin can enter that node earlier.
+//  2. k_beam_minfilter gives every block the minimum over the lattice rays within R lattice steps.  With kappa = 2*sqrt(2)
+//     every reported node is at least sqrt(2) x the lattice spacing wide, so any non-empty node that meets a block's
+//     frustum contains a lattice ray within 3.2 spacings of the block (convexity: its projection contains a disc of
+//     diameter >= sqrt(2) d on the way from the block to its inscribed disc); R = 4 covers that.  So the block's value is
+//     a true lower bound on the hit distance of each of its 16 pixels (+inf: they all miss), less a safety margin.
+//  3. The fine pass (svo_frame.flags bit 1) starts the PRIMARY cast's walk at that distance (Trav::setup t_floor): the
+//     cells skipped are empty, the first non-empty cell met is the one the full walk meets, entered from the same
+//     empty cell: colour, depth and hit are unchanged bit for bit; only the iteration count falls.
+// ---------------------------------------------------------------------------
+constexpr float kBeamKappa = 2.8284271f;
+constexpr int kBeamRadius = 4;
+
+__device__ __forceinline__ vec3 beam_lattice_dir(const FrameParams &f, int gx, int gy, int W, int H) {
+  const float fx = (float)(4 * gx) / (float)W, fy = (float)(4 * gy) / (float)H;
+  vec3 d;
+  d.x = mixf(mixf(f.l1[0], f.l2[0], fy), mixf(f.r1[0], f.r2[0], fy), fx);
+  d.y = mixf(mixf(f.l1[1], f.l2[1], fy), mixf(f.r1[1], f.r2[1], fy), fx);
+  d.z = mixf(mixf(f.l1[2], f.l2[2], fy), mixf(f.r1[2], f.r2[2], fy), fx);
+  return normalize3(d);
+}
+
+__global__ void __launch_bounds__(128) k_beam_lattice(SceneView sc, FrameParams f, float *__restrict__ lattice, int W, int H) {
+  const int lw = (W >> 2) + 1, lh = (H >> 2) + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+  const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  if (gx >= lw || gy >= lh) return;
+  const vec3 d0 = beam_lattice_dir(f, gx, gy, W, H), dx = beam_lattice_dir(f, gx + 1, gy, W, H), dy = beam_lattice_dir(f, gx, gy + 1, W, H);
+  const vec3 ex = mk3(dx.x - d0.x, dx.y - d0.y, dx.z - d0.z), ey = mk3(dy.x - d0.x, dy.y - d0.y, dy.z - d0.z);
+  // lattice spacing per unit distance around this ray, with slack for its variation over the filter window
+  const float spacing = 1.25f * sqrtf(fmaxf(ex.x * ex.x + ex.y * ex.y + ex.z * ex.z, ey.x * ey.x + ey.y * ey.y + ey.z * ey.z));
+  const float inf = __uint_as_float(0x7f800000u);
+  float out = inf;
+  Trav<true> T;
+  uint2 stk[kMaxScale + 1];
+  T.setup(sc, mk3(f.camPos[0], f.camPos[1], f.camPos[2]), d0, f.maxDepth, false, f.coneDepth, nullptr);
+  if (!(d0.x == d0.x && d0.y == d0.y && d0.z == d0.z)) {
+    out = 0.0f;  // degenerate camera: no bound
+  } else if (!T.nan_ray(nullptr)) {
+    for (;;) {
+      const uint32_t m = T.pd.y >> (T.idx ^ T.oct);
+      if ((m & 0x10000u) != 0u && T.t_min <= T.t_max && T.scale_exp2 <= kBeamKappa * spacing * T.t_min) {  // LOD stop
+        out = T.t_min - 1.7320508f * T.scale_exp2;
+        break;
+      }
+      const int st = T.step(sc, stk, nullptr);
+      if (st == TRAV_HIT) { out = T.t_min - 1.7320508f * T.scale_exp2; break; }
+      if (st == TRAV_MISS) {
+        if (T.iter > (float)kMaxIterations) out = 0.0f;  // the walk was cut short by the iteration cap: no bound
+        break;
+      }
+    }
+  } else {
+    out = 0.0f;
+  }
+  lattice[(size_t)gy * (size_t)lw + (size_t)gx] = fmaxf(out, 0.0f);
+}
+
+__global__ void __launch_bounds__(128) k_beam_minfilter(const float *__restrict__ lattice, float *__restrict__ beam, int W, int H) {
+  const int bw = W >> 2, bh = H >> 2, lw = bw + 1, lh = bh + 1;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
+  if (bx >= bw || by >= bh) return;
+  float v = __uint_as_float(0x7f800000u);
+  const int x0 = max(bx - kBeamRadius, 0), x1 = min(bx + 1 + kBeamRadius, lw - 1);
+  const int y0 = max(by - kBeamRadius, 0), y1 = min(by + 1 + kBeamRadius, lh - 1);
+  for (int y = y0; y <= y1; y++)
+    for (int x = x0; x <= x1; x++) v = fminf(v, __ldg(lattice + (size_t)y * (size_t)lw + (size_t)x));
+  // safety margin: the lattice pass contracts its t arithmetic into FMAs, the fine pass rounds every operation
+  if (v < __uint_as_float(0x7f800000u)) v = fmaxf(v * 0.9999f - 1e-5f, 0.0f);
+  beam[(size_t)by * (size_t)bw + (size_t)bx] = v;
 }
 
 __global__ void k_math_probe(int fn, const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ out, uint64_t n) {
@@ -1083,6 +1164,16 @@ cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FramePa
   const dim3 block(128), grid((bw + 15) / 16, (bh + 7) / 8);
   if (cfg.fast) SVO_LAUNCH(grid, block, stream, k_beam<true>)(sc, f, beam, W, H);
   else SVO_LAUNCH(grid, block, stream, k_beam<false>)(sc, f, beam, W, H);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_beam_conservative(const SceneView &sc, const FrameParams &f, float *lattice, float *beam, int W, int H, cudaStream_t stream) {
+  const int bw = W >> 2, bh = H >> 2;
+  if (bw == 0 || bh == 0) return cudaSuccess;
+  const dim3 lgrid((bw + 1 + 15) / 16, (bh + 1 + 7) / 8);
+  SVO_LAUNCH(lgrid, 128, stream, k_beam_lattice)(sc, f, lattice, W, H);
+  const dim3 fgrid((bw + 127) / 128, bh);
+  SVO_LAUNCH(fgrid, 128, stream, k_beam_minfilter)(lattice, beam, W, H);
   return cudaGetLastError();
 }
 

@@ -89,6 +89,8 @@ cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d
                         void *d_out, int maxDepth, cudaStream_t stream);
 cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, float *beam, int W, int H,
                         cudaStream_t stream);
+// conservative beam pre-pass: lattice = scratch of (W/4+1) x (H/4+1) floats, beam = the (W/4) x (H/4) beam plane
+cudaError_t launch_beam_conservative(const SceneView &sc, const FrameParams &f, float *lattice, float *beam, int W, int H, cudaStream_t stream);
 struct CellBox;
 cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, uint32_t *refbase, uint64_t cap, uint64_t *ndesc,
                           uint32_t *nlevels, CellBox *leaf_box, CellBox *depth_box, bool *overflow, cudaStream_t stream);

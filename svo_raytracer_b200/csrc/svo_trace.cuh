@@ -310,8 +310,10 @@ struct Trav {
                             // increment runs on the FMA pipe -- the loop is bound by the ALU pipe
   uint2 pd;
 
+  // t_floor > 0: a proven lower bound on the cast's hit distance (conservative beam pre-pass): the walk starts at the cell
+  // that contains the ray at that parameter instead of at the cube's entry.  Same hit, fewer iterations.
   __device__ __forceinline__ void setup(const SceneView &sc, const vec3 o, vec3 d, int maxDepth, bool coneTrace,
-                                        int coneDepth, RayStats *rs) {
+                                        int coneDepth, RayStats *rs, float t_floor = 0.0f) {
     const float kEps = 3.552713678800501e-15f;                // :31
     if (fabsf(d.x) < kEps) d.x = fmul(kEps, sign_glsl(d.x));  // :226-228
     if (fabsf(d.y) < kEps) d.y = fmul(kEps, sign_glsl(d.y));
@@ -329,6 +331,7 @@ struct Trav {
     t_min = fmaxf(fmaxf(M::msub(2.0f, cx, bx), M::msub(2.0f, cy, by)), M::msub(2.0f, cz, bz));  // :243
     t_max = fminf(fminf(M::sub(cx, bx), M::sub(cy, by)), M::sub(cz, bz));                       // :244
     t_min = fmaxf(t_min, 0.0f);                                                                  // :245
+    if (t_floor > 0.0f) t_min = fmaxf(t_min, t_floor);
     h = t_max;                                                                                   // :247
     idx = 0;
     px = py = pz = 1.0f;
@@ -582,18 +585,18 @@ struct Trav {
 // intersectOctree run to completion on the caller's stack.
 template <bool FAST, int STATS, bool BOX, bool TOP, int BAL = 0, class Stk>
 __device__ __forceinline__ bool cast_ray_on(Stk stk, const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
-                                            int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs, bool attrs) {
+                                            int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs, bool attrs, float t_floor = 0.0f) {
   Trav<FAST, STATS, BOX, TOP, BAL> T;
-  T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs);
+  T.setup(sc, o, d, maxDepth, coneTrace, coneDepth, rs, t_floor);
   if (T.outside_box() || T.nan_ray(rs)) return T.finish(sc, TRAV_MISS, res, loops, attrs);  // no iteration can change anything
   return T.finish(sc, T.run(sc, stk, rs), res, loops, attrs);
 }
 // ... on the default stack
 template <bool FAST, int STATS = 0, bool BOX = false, bool TOP = false>
 __device__ __forceinline__ bool cast_ray(const SceneView &sc, const vec3 o, const vec3 d, int maxDepth, bool coneTrace,
-                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr, bool attrs = true) {
+                                         int coneDepth, CastRes &res, uint32_t &loops, RayStats *rs = nullptr, bool attrs = true, float t_floor = 0.0f) {
   uint2 stk[kMaxScale + 1];  // octstack (:199-202): (parent index, t_max) per scale
-  return cast_ray_on<FAST, STATS, BOX, TOP>(stk, sc, o, d, maxDepth, coneTrace, coneDepth, res, loops, rs, attrs);
+  return cast_ray_on<FAST, STATS, BOX, TOP>(stk, sc, o, d, maxDepth, coneTrace, coneDepth, res, loops, rs, attrs, t_floor);
 }
 
 SVO_DI void matcolor_table(uint32_t value, vec3 &mc) {  // :514-522, :578-586
@@ -618,6 +621,7 @@ struct Pixel {
   CastRes res;       // `res`, stale fields and all
   vec3 color;        // finalcolor
   float depth, beamDist;
+  float t_floor;     // conservative beam pre-pass (svo_frame.flags bit 1): lower bound on the primary hit distance; +inf = the block misses
   uint32_t hit_id, iter;
   float primary_t;
 };
@@ -627,6 +631,9 @@ SVO_DI bool pixel_begin(const FrameParams &f, const Planes &pl, int W, int H, in
   P.x = x;
   P.y = y;
   P.beamDist = 0.0f;
+  P.t_floor = 0.0f;
+  if ((f.flags & 2) && pl.beam && (x >> 2) < (W >> 2) && (y >> 2) < (H >> 2))
+    P.t_floor = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));
   // :656-658.  The beam image has (W/4) x (H/4) texels (Main.java:82-83); imageLoad outside an image returns 0
   if (f.useBeam && pl.beam && (x >> 2) < (W >> 2) && (y >> 2) < (H >> 2))
     P.beamDist = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));
@@ -849,17 +856,22 @@ __device__ __forceinline__ void shade_pixel(const SceneView &sc, const FramePara
       uint32_t loops = 0;
       const bool attrs = cast_needs_attrs(f, P);
       bool hit;
+      // the primary cast may start at the beam pre-pass's lower bound; a block the pre-pass proved empty is not cast at all
+      const float t_floor = (BOX && P.cast_i == 0) ? P.t_floor : 0.0f;
+      if (BOX && t_floor == __uint_as_float(0x7f800000u)) {
+        hit = false;
+      } else
       if (STACK == 1) {
         uint4 wide[kMaxScale + 1];
         WideStack ws;
         ws.p = wide;
-        hit = cast_ray_on<FAST, STATS, BOX, TOP, BAL>(ws, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+        hit = cast_ray_on<FAST, STATS, BOX, TOP, BAL>(ws, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs, t_floor);
       } else if (STACK == 2) {
         SmemStack ss;
         ss.p = smem_stack;
-        hit = cast_ray_on<FAST, STATS, BOX, TOP, BAL>(ss, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+        hit = cast_ray_on<FAST, STATS, BOX, TOP, BAL>(ss, sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs, t_floor);
       } else {
-        hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs);
+        hit = cast_ray<FAST, STATS, BOX, TOP>(sc, P.origin, P.dir, f.maxDepth, P.cone, f.coneDepth, P.res, loops, rs, attrs, t_floor);
       }
       if (!attrs && hit && f.renderMode == 0) {
         pixel_after_last_hit(P);

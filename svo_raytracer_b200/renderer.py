@@ -158,6 +158,10 @@ class SvoContext:
     def beam(self, frame: Frame):
         self._check(self._lib.svo_beam(self._h, C.byref(frame)))
 
+    def beam_conservative(self, frame: Frame):
+        """Fill the beam plane with proven per-block lower bounds on the primary hit distance (svo_beam_conservative)."""
+        self._check(self._lib.svo_beam_conservative(self._h, C.byref(frame)))
+
     def sync(self):
         self._check(self._lib.svo_sync(self._h))
 
@@ -208,6 +212,10 @@ class SvoContext:
 
     def swap_buffers(self):
         self._check(self._lib.svo_swap_buffers(self._h))
+
+    def select_lane(self, lane: int):
+        """Make lane 0 / 1 (stream + colour/depth set) current; frames on different lanes may overlap on the GPU."""
+        self._check(self._lib.svo_select_lane(self._h, int(lane)))
 
     def read_wait(self):
         self._check(self._lib.svo_read_wait(self._h))

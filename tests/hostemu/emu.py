@@ -46,6 +46,8 @@ def lib():
                                         C.c_int, C.c_int]
         L.emu_gpu_build_terrain.restype = C.c_int
         L.emu_gpu_build_terrain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+        L.emu_beam_conservative.restype = C.c_int
+        L.emu_beam_conservative.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.emu_fence_word.restype = C.c_uint
         L.emu_fence_word.argtypes = [C.c_int]
         L.emu_launch_cast.restype = C.c_int
@@ -149,6 +151,13 @@ class Scene:
         if order is not None:
             order = np.ascontiguousarray(order, dtype=np.uint32)
         rc = lib().emu_launch_cast(self._h, _ptr(rays), _ptr(order), rays.shape[0], _ptr(out), max_depth, kernel, ctas, nthreads)
+        assert rc == 0, rc
+        return out
+
+    def beam_conservative(self, frame, width, height, nthreads=8):
+        """svo_beam_conservative on the emulator: per 4x4 block a lower bound on the primary hit distance (+inf = all miss)."""
+        out = np.zeros((height // 4, width // 4), np.float32)
+        rc = lib().emu_beam_conservative(self._h, C.byref(frame), width, height, _ptr(out), nthreads)
         assert rc == 0, rc
         return out
 

@@ -79,6 +79,14 @@ int emu_launch_render(const emu_scene *s, const FrameParams *f, int W, int H, in
   return rc;
 }
 
+// svo_beam_conservative through the product's launcher: beam = (W/4) x (H/4) floats
+int emu_beam_conservative(const emu_scene *s, const FrameParams *f, int W, int H, float *beam, int nthreads) {
+  const SceneView sc = emu_view_of(s, nullptr);
+  std::vector<float> lattice((size_t)(W / 4 + 1) * (size_t)(H / 4 + 1) + 4);
+  simt::g_os_threads = nthreads;
+  return (int)launch_beam_conservative(sc, *f, lattice.data(), beam, W, H, nullptr);
+}
+
 // svo_cast through the product's launch_cast on the emulator.  kernel 0 = grid-stride kernel, 1 = persistent threads with
 // warp-level ray fetch; order = optional permutation (the binned order of SVO_OPT_RAY_SORT).
 int emu_launch_cast(const emu_scene *s, const void *rays, const uint32_t *order, uint64_t n, void *out, int maxDepth, int kernel, int ctas,

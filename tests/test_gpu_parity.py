@@ -274,6 +274,79 @@ def test_interleaved_band_partition_single_gpu(svo, oracle, terrain128, kernel):
         assert np.array_equal(c.read_color_rgba8(), want["rgba8"]) and np.array_equal(c.read_depth().view(np.uint32), want["depth"].view(np.uint32))
 
 
+def test_two_lanes_overlap_frames_without_mixing_them(svo, oracle, terrain512):
+    """svo_select_lane: frames rendered back to back on alternating lanes (two streams, two plane sets) may overlap on the
+    GPU; each lane must end up holding exactly the last frame drawn on it, and the pipelined read-back path
+    (svo_read_planes_async + svo_swap_buffers, which alternates lanes) must deliver every frame intact."""
+    W, H = 640, 360
+    cams = ["A", "B", "C", "C", "B", "A", "C"]
+    want = []
+    for i, cam in enumerate(cams):
+        pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+        p, _ = oracle.render(terrain512, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=i + 1, render_mode=0), W, H, nthreads=8,
+                             planes=("rgba8", "depth"))
+        want.append(p)
+    for kernel in (13, 17, 0):
+        with svo.SvoContext(W, H) as c:
+            c.set_option(svo._lib.OPT_KERNEL, kernel)
+            c.upload(terrain512)
+            c.timer_begin()
+            for i, cam in enumerate(cams):
+                c.select_lane(i & 1)
+                c.render(svo.camera_frame(cam, frame_number=i + 1, render_mode=0))
+            assert c.timer_end() > 0
+            for lane, i in ((0, 6), (1, 5)):
+                c.select_lane(lane)
+                assert np.array_equal(c.read_color_rgba8(), want[i]["rgba8"]), (kernel, lane)
+                assert np.array_equal(c.read_depth().view(np.uint32), want[i]["depth"].view(np.uint32)), (kernel, lane)
+            # pipelined read-back: every frame lands in its host buffer
+            import torch
+            bufs = [(torch.empty((H, W, 4), dtype=torch.uint8).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory()) for _ in cams]
+            for i, cam in enumerate(cams):
+                c.render(svo.camera_frame(cam, frame_number=i + 1, render_mode=0))
+                c.read_planes_async(bufs[i][0].data_ptr(), bufs[i][1].data_ptr())
+                c.swap_buffers()
+            c.read_wait()
+            for i in range(len(cams)):
+                assert np.array_equal(bufs[i][0].numpy(), want[i]["rgba8"]), (kernel, i)
+                assert np.array_equal(bufs[i][1].numpy().view(np.uint32), want[i]["depth"].view(np.uint32)), (kernel, i)
+
+
+def test_conservative_beam_full_size(svo, oracle):
+    """svo_beam_conservative at 1920x1080 on the 2048^3 world: every block's bound is below the primary hit distance of its
+    16 pixels, blocks marked +inf contain no hit, the frame rendered with SVO_FRAME_BEAM_FLOOR equals the frame without
+    it bit for bit (colour and depth), and primary iterations are saved."""
+    size, W, H = 2048, 1920, 1080
+    hm, mm = svo.terrain_inputs(size)
+    with svo.SvoContext(W, H) as c:
+        c.build_terrain_device(hm, mm, size, 1024)
+        for cam in ("A", "B", "C"):
+            c.set_option(svo._lib.OPT_AUX_PLANES, 1)
+            f3 = svo.camera_frame(cam, frame_number=1, render_mode=3, max_depth=11)
+            c.render(f3)
+            ids, t = c.read_hit_id(), c.read_primary_t()
+            c.set_option(svo._lib.OPT_AUX_PLANES, 0)
+            c.beam_conservative(f3)
+            beam = c.read_plane(svo._lib.PLANE_BEAM)
+            tt = np.where(ids != svo.NO_HIT, t, np.inf).astype(np.float32)
+            tmin = tt.reshape(H // 4, 4, W // 4, 4).min(axis=(1, 3))
+            assert (beam <= tmin).all(), "cam %s: %d blocks not conservative" % (cam, int((beam > tmin).sum()))
+            hit = np.isfinite(tmin)
+            if hit.any():
+                assert np.median(beam[hit] / tmin[hit]) > 0.9, float(np.median(beam[hit] / tmin[hit]))
+            for mode in (0, 2):
+                f = svo.camera_frame(cam, frame_number=2, render_mode=mode, max_depth=11)
+                c.render(f)
+                rgba, depth = c.read_color_rgba8(), c.read_depth()
+                st0 = c.render_stats_executed(f)
+                fb = svo.camera_frame(cam, frame_number=2, render_mode=mode, max_depth=11, flags=2)
+                c.render(fb)
+                assert np.array_equal(c.read_color_rgba8(), rgba), (cam, mode)
+                assert np.array_equal(c.read_depth().view(np.uint32), depth.view(np.uint32)), (cam, mode)
+                st1 = c.render_stats_executed(fb)
+                assert st1["iters"] < st0["iters"], (cam, mode, st0, st1)
+
+
 def test_fence_watchdog_is_reported(svo, terrain128):
     """A wait nobody signals gives up after ~2 s; svo_sync reports it (the latch was invisible to the host)."""
     with svo.SvoContext(64, 64) as c:

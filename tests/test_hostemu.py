@@ -352,3 +352,34 @@ def test_split_kernels_on_simt_emulator(svo, oracle, terrain128, scene128, kerne
         got = scene128.launch_render(f, 160, 90, kernel=kernel, aux=False, box=True, prev_rgba8=prev)
         assert np.array_equal(got["rgba8"], want["rgba8"]), frame
         prev = want["rgba8"]
+
+
+@pytest.mark.parametrize("cam", ["A", "B", "C"])
+def test_conservative_beam_prepass_on_simt_emulator(svo, oracle, terrain128, scene128, cam):
+    """svo_beam_conservative (k_beam_lattice + k_beam_minfilter): every block's value is a lower bound on the primary hit
+    distance of its 16 pixels (+inf only where all 16 miss), it is not vacuous, and a frame whose primary casts start
+    there (flags bit 1) is bit-identical in colour and depth to the frame without it while running fewer iterations."""
+    W, H = 160, 96
+    pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+    kw = dict(frame_number=3, render_mode=0, max_depth=7)
+    f0 = oracle.make_frame(pos, l1, l2, r1, r2, **kw)
+    want, _ = oracle.render(terrain128, f0, W, H, nthreads=8)
+    beam = scene128.beam_conservative(f0, W, H)
+    t = np.where(want["hit_id"] != 0xFFFFFFFF, want["primary_t"], np.inf).astype(np.float32)
+    tmin = t.reshape(H // 4, 4, W // 4, 4).min(axis=(1, 3))
+    assert (beam <= tmin).all(), "not conservative in %d blocks" % int((beam > tmin).sum())
+    hit_blocks = np.isfinite(tmin)
+    if hit_blocks.any():
+        assert (beam[hit_blocks] > 0).mean() > 0.5 and np.median(beam[hit_blocks] / tmin[hit_blocks]) > 0.3  # a useful bound even at this tiny resolution (the margins are in lattice spacings)
+    f1 = oracle.make_frame(pos, l1, l2, r1, r2, flags=2, **kw)
+    for kernel in (13, 17, 0):
+        got = scene128.launch_render(f1, W, H, kernel=kernel, aux=False, box=True, beam=beam)
+        _assert_planes_equal(got, want, "beam floor kernel %d cam %s" % (kernel, cam), planes=("rgba8", "depth"))
+    # validation instance (aux planes): the floor is ignored, iteration counts are the reference's
+    got = scene128.launch_render(f1, W, H, kernel=13, aux=True, beam=beam)
+    _assert_planes_equal(got, want, "beam floor ignored with aux planes")
+    # mode 2 (the engine's default: primary + shadow ray)
+    kw2 = dict(frame_number=3, render_mode=2, max_depth=7)
+    want2, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, **kw2), W, H, nthreads=8, planes=("rgba8", "depth"))
+    got2 = scene128.launch_render(oracle.make_frame(pos, l1, l2, r1, r2, flags=2, **kw2), W, H, kernel=13, aux=False, box=True, beam=beam)
+    _assert_planes_equal(got2, want2, "beam floor mode 2", planes=("rgba8", "depth"))
