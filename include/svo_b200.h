@@ -165,8 +165,9 @@ int svo_beam(svo_ctx *ctx, const svo_frame *frame);
  * stop at 2*sqrt(2) lattice spacings, a min filter over +-4 lattice steps and the node-diagonal margin
  * (csrc/svo_kernels.cu, k_beam_lattice / k_beam_minfilter).  A frame rendered with flags | SVO_FRAME_BEAM_FLOOR (and
  * useBeam = 0) starts every primary cast's walk there: colour, depth and hit are unchanged bit for bit, only loop
- * iterations are saved.  Like the content box it is ignored in render mode 1 and with SVO_OPT_AUX_PLANES (iteration counts
- * are observable there). */
+ * iterations are saved.  It applies to render modes 0 and 3; it is ignored where the primary cast's iteration count is
+ * observable: mode 1 (heat map), mode 2 (the penumbra term reads the primary's stale count when the shadow ray misses,
+ * svotrace.comp:616-619) and with SVO_OPT_AUX_PLANES. */
 int svo_beam_conservative(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
 /* Two lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes

@@ -632,7 +632,9 @@ SVO_DI bool pixel_begin(const FrameParams &f, const Planes &pl, int W, int H, in
   P.y = y;
   P.beamDist = 0.0f;
   P.t_floor = 0.0f;
-  if ((f.flags & 2) && pl.beam && (x >> 2) < (W >> 2) && (y >> 2) < (H >> 2))
+  // (not in render mode 2: its penumbra term reads the PRIMARY cast's stale iteration count when the shadow ray misses,
+  // svotrace.comp:616-619, so the count is observable there; mode 1 shows it outright)
+  if ((f.flags & 2) && (f.renderMode == 0 || f.renderMode == 3) && pl.beam && (x >> 2) < (W >> 2) && (y >> 2) < (H >> 2))
     P.t_floor = __ldg(pl.beam + (size_t)(y >> 2) * (size_t)(W >> 2) + (size_t)(x >> 2));
   // :656-658.  The beam image has (W/4) x (H/4) texels (Main.java:82-83); imageLoad outside an image returns 0
   if (f.useBeam && pl.beam && (x >> 2) < (W >> 2) && (y >> 2) < (H >> 2))
