@@ -77,6 +77,7 @@ def parse():
     ap.add_argument("--accumulate", type=int, default=0, help="1: progressive running mean (svo_frame.flags bit 0), frameNumber = step + 1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..4; 0 = 2 on one GPU, 4 in the tile partition)")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
@@ -423,6 +424,11 @@ def main():
 
     tiles = world_size > 1 and partition == "tiles"
     total = a.warmup + a.steps
+    # frames in flight per GPU: a frame's kernel ends with the critical path of its longest rays (~0.1 ms whatever share of the
+    # frame the GPU renders); the next frames' tiles fill the SMs meanwhile (lanes = stream + plane set each)
+    LANES = max(1, min(4, a.lanes if a.lanes > 0 else (4 if tiles else 2)))
+    if a.accumulate:
+        LANES = 1  # a running mean lives in ONE plane set
     PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
     if tiles:
         # ONE frame per step, image bands interleaved over the ranks, replicated octree.  Rank 0 owns the frame
@@ -446,18 +452,18 @@ def main():
                 if release:
                     dist.all_reduce(fence)  # the frame has been consumed: peers may overwrite the planes
         else:
-            # No collective in the data path.  Rank 0 owns TWO colour/depth sets; frame k goes to set k&1, so two
+            # No collective in the data path.  Rank 0 owns LANES colour/depth sets; frame k goes to set k % LANES, so LANES
             # frames are in flight.  Fences are counters in GPU memory bumped by remote atomics over NVLink:
-            # slot 2+(k&1) of rank 0's counter = "bands of frame k stored" (complete at (k//2+1)*N) -- bumped by the
+            # slot 2+(k%LANES) of rank 0's counter = "bands of frame k stored" (complete at (k//LANES+1)*N) -- bumped by the
             # LAST CTA of each rank's render kernel (svo_render_interleaved_signal: one launch per rank and frame) --
             # slot 0 of every peer's counter = "frames consumed by rank 0".
-            handles = [ctx.ipc_export(p | s) for s in (0, L.PLANE_BACK) for p in PL] if rank == 0 else [None] * 4
+            handles = [ctx.ipc_export(p | (l << 8)) for l in range(LANES) for p in PL] if rank == 0 else [None] * (2 * LANES)
             dist.broadcast_object_list(handles, src=0)
             if rank == 0:
-                sets = [[ctx.device_ptr(p | s) for p in PL] for s in (0, L.PLANE_BACK)]
+                sets = [[ctx.device_ptr(p | (l << 8)) for p in PL] for l in range(LANES)]
             else:
                 ptrs = [ctx.ipc_import(h) for h in handles]
-                sets = [ptrs[0:2], ptrs[2:4]]
+                sets = [ptrs[2 * l:2 * l + 2] for l in range(LANES)]
             fh = [None] * world_size
             dist.all_gather_object(fh, ctx.fence_export())
             if rank == 0:
@@ -467,13 +473,13 @@ def main():
             state = {"k": 0, "pending": None}
 
             def bind(k):
-                for plane, ptr in zip(PL, sets[k & 1]):
+                for plane, ptr in zip(PL, sets[k % LANES]):
                     ctx.bind_plane(plane, ptr)
 
-            # Frame k lives on lane k&1 (stream + plane set): frame k+1's kernel may start while frame k's last tiles drain.
+            # Frame k lives on lane k % LANES (stream + plane set): the kernels of the next frames start while frame k's last tiles drain.
             def finish(j, consume):
-                ctx.select_lane(j & 1)
-                ctx.fence_wait((j // 2 + 1) * world_size, slot=2 + (j & 1))  # every GPU has stored its bands of frame j
+                ctx.select_lane(j % LANES)
+                ctx.fence_wait((j // LANES + 1) * world_size, slot=2 + (j % LANES))  # every GPU has stored its bands of frame j
                 if consume is not None:
                     bind(j)
                     consume()
@@ -482,17 +488,17 @@ def main():
             def render_step(s, consume=None, release=False):
                 k = state["k"]
                 state["k"] = k + 1
-                ctx.select_lane(k & 1)
+                ctx.select_lane(k % LANES)
                 if rank == 0:
                     bind(k)
-                    ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=2 + (k & 1))
+                    ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=2 + (k % LANES))
                     if state["pending"] is not None:
                         finish(*state["pending"])
                     state["pending"] = (k, consume)
                 else:
-                    ctx.fence_wait(max(k - 1, 0), slot=0)  # rank 0 has consumed frames 0..k-2: set k&1 is free
+                    ctx.fence_wait(max(k - LANES + 1, 0), slot=0)  # rank 0 has consumed frames 0..k-LANES: this lane's set is free
                     bind(k)
-                    ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=2 + (k & 1))
+                    ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=2 + (k % LANES))
 
             def drain():
                 if rank == 0 and state["pending"] is not None:
@@ -511,8 +517,8 @@ def main():
         drain = lambda: None
 
         def render_step(s, consume=None, release=False):
-            if not a.accumulate:  # (a running mean lives in ONE plane set)
-                ctx.select_lane(s & 1)  # consecutive frames on alternating lanes (stream + plane set): frame s+1 may start while frame s's last tiles drain
+            if LANES > 1:
+                ctx.select_lane(s % LANES)  # consecutive frames on alternating lanes (stream + plane set): frame s+1 may start while frame s's last tiles drain
             ctx.render(frames[s])
             if consume is not None:
                 consume()
@@ -771,7 +777,7 @@ def main():
         "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_of(a, world_size, tree_bytes, partition),
-        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "descriptors": info["descriptors"], "levels": info["levels"],
+        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "descriptors": info["descriptors"], "levels": info["levels"],
                          "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
                          "world": {"how": world_how, "seconds": round(build_s, 2), "maps_s": round(maps_s, 2)}, "build_and_transcode_s": round(upload_s, 3),
                          "units": ("one frame per step, interleaved %d-row bands per rank, peers store into rank 0's planes over NVLink, "

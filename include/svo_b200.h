@@ -77,7 +77,8 @@ enum svo_plane {
   SVO_PLANE_PRIMARY_T = 5,   /* new: primary res.t */
   SVO_PLANE_RADIANCE = 6,    /* new: finalcolor before the rgba8 store, float4 */
   SVO_PLANE_BACK = 0x100     /* OR-ed to COLOR_RGBA8 / DEPTH in svo_device_ptr and svo_ipc_export: the second set
-                              * (svo_swap_buffers); without it they name the first set */
+                              * (svo_swap_buffers, lane 1); without it they name the first set.  In general
+                              * plane | (lane << 8) names the set of lane 1..3 (svo_select_lane) */
 };
 
 enum svo_option {
@@ -130,6 +131,15 @@ int svo_upload(svo_ctx *ctx, const uint8_t *nodes, uint64_t nbytes);
  * Main.java:349-350): `nodes` is the base of the whole buffer, bytes
  * [start,end) changed.  end may exceed the previous length (appended nodes). */
 int svo_upload_range(svo_ctx *ctx, const uint8_t *nodes, uint64_t start, uint64_t end);
+/* How the last svo_upload_range was absorbed: out[0] descriptors whose record or child block really changed, [1] subtrees
+ * re-walked, [2] descriptors appended, [3] 1 if it fell back to a whole transcode (edit too wide, arrays full, or a quarter
+ * of the array already patched-in).  The range is stored and compared with the old bytes in one pass; only the subtrees
+ * the changed bytes belong to are transcoded again (csrc/svo_gpu_transcode.cu, gpu_patch).  All zero: nothing changed. */
+int svo_upload_stats(const svo_ctx *ctx, uint64_t out[4]);
+/* Layout-independent fingerprint of the scene's descriptor tree (depth-first from the root): out[0] reachable descriptors,
+ * [1] hash of their masks / reference offsets / depths, [2] deepest level, [3] descriptors stored.  Equal for a scene
+ * patched by svo_upload_range and the same stream uploaded whole. */
+int svo_scene_canonical(svo_ctx *ctx, uint64_t out[4]);
 /* World generation ON THE DEVICE: the stream svo_build_terrain writes, built by kernels (min/max pyramids, level-
  * synchronous classify / size / offset / emit sweeps; csrc/svo_gpu_build.cu) straight into HBM and made the
  * context's scene as svo_upload would -- the node stream never crosses PCIe.  Replaces, for heightmap worlds,
@@ -170,11 +180,12 @@ int svo_beam(svo_ctx *ctx, const svo_frame *frame);
  * svotrace.comp:616-619) and with SVO_OPT_AUX_PLANES. */
 int svo_beam_conservative(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
-/* Two lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
- * `lane` (0 or 1) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
+/* Four lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
+ * `lane` (0..3) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
  * Work on different lanes may overlap on the GPU: rendering frame k+1 on the other lane lets its first tiles fill the SMs
- * that frame k's last, longest tiles leave idle (measured: a 1080p frame carries ~0.13 ms of such tail).  Frames on one
- * lane stay ordered; svo_sync, svo_timer_*, uploads, the beam passes and svo_cast order both lanes.  svo_swap_buffers is
+ * that frame k's last, longest tiles leave idle (measured: a 1080p frame carries ~0.13 ms of such tail -- the critical
+ * path of its longest rays -- whatever share of the frame a GPU renders, so the 8-GPU tile partition keeps 4 frames in
+ * flight).  Frames on one lane stay ordered; svo_sync, svo_timer_*, uploads, the beam passes and svo_cast order both lanes.  svo_swap_buffers is
  * svo_select_lane(other) + the wait for that set's last read-back.  With a caller-owned stream (svo_set_stream), with
  * SVO_OPT_AUX_PLANES or with a kernel variant whose workspace exists once (1, 2, 15, 16) both lanes share one stream. */
 int svo_select_lane(svo_ctx *ctx, int lane);

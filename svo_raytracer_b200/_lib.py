@@ -54,6 +54,8 @@ SYMBOLS = {
     "svo_upload_range": (_i, [_vp, _vp, _u64, _u64]),
     "svo_build_terrain_device": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_u64)]),
     "svo_download": (_i, [_vp, _vp, _u64]),
+    "svo_upload_stats": (_i, [_vp, C.POINTER(_u64 * 4)]),
+    "svo_scene_canonical": (_i, [_vp, C.POINTER(_u64 * 4)]),
     "svo_scene_info": (_i, [_vp, C.POINTER(_u64 * 4)]),
     "svo_render": (_i, [_vp, C.POINTER(Frame)]),
     "svo_render_rows": (_i, [_vp, C.POINTER(Frame), _i, _i]),

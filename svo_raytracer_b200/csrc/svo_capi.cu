@@ -25,6 +25,8 @@ static_assert(sizeof(svo_ray) == 24 && sizeof(svo_hit) == 16, "ray-stream record
 
 static thread_local std::string g_error;
 
+constexpr int kLanes = 4;  // svo_select_lane: streams + colour/depth plane sets that may be in flight together
+
 struct svo_ctx {
   int device = 0;
   int W = 0, H = 0;
@@ -32,8 +34,8 @@ struct svo_ctx {
   // Two lanes (svo_select_lane): a stream and a colour/depth plane set each.  Work enqueued on different lanes may overlap on
   // the GPU: frame k+1's first tiles fill the SMs that frame k's last, longest tiles leave idle (the tail of a 1080p frame is
   // ~0.13 ms of a 0.4-1.4 ms kernel).  `stream` is always the current lane's stream.
-  cudaStream_t own_stream2 = nullptr, lane_stream[2] = {nullptr, nullptr};
-  cudaEvent_t ev_lane[2] = {nullptr, nullptr};
+  cudaStream_t own_lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr}, lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_lane[kLanes] = {nullptr, nullptr, nullptr, nullptr};
   int lane = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0;
@@ -42,7 +44,13 @@ struct svo_ctx {
   uint64_t raw_cap = 0, nbytes = 0;
   uint2 *d_desc = nullptr;
   uint32_t *d_refbase = nullptr;
+  uint2 *d_meta = nullptr;     // per descriptor: own record offset, parent index (incremental transcode)
+  uint8_t *d_flag = nullptr;   // per descriptor: scratch of the incremental transcode, all zero between calls
   uint64_t desc_cap = 0;
+  uint64_t ndesc_live = 0;     // descriptors reachable after the last whole transcode (the rest up to ndesc: patched-in, or garbage)
+  uint8_t *d_stage = nullptr, *d_bitmap = nullptr;  // svo_upload_range: the caller's bytes before they are stored, changed-byte bitmap
+  uint64_t stage_cap = 0, nbytes_before_range = 0;
+  uint64_t patch_stats[4] = {0, 0, 0, 0};  // last svo_upload_range: dirty nodes, re-walked roots, descriptors appended, 1 = fell back to a whole transcode
   uint32_t ndesc = 0, nlevels = 0;
   uint32_t first_word_zero = 1;
   bool have_scene = false;
@@ -50,10 +58,10 @@ struct svo_ctx {
   void *own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *bound[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // second colour/depth set for pipelined read-back (svo_swap_buffers / svo_read_planes_async)
-  void *back[2] = {nullptr, nullptr};
-  int render_set = 0;  // 0: own[], 1: back[]
+  void *back[kLanes][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // sets 1..3 ([0] unused: set 0 = own[])
+  int render_set = 0;  // which colour/depth set renders draw into and reads take from: 0 = own[], s = back[s]
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_rendered = nullptr, ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_rendered = nullptr, ev_copied[kLanes] = {nullptr, nullptr, nullptr, nullptr};
   // ray-stream scratch
   void *d_rays = nullptr, *d_hits = nullptr;
   uint64_t cast_cap = 0;
@@ -79,7 +87,7 @@ struct svo_ctx {
   std::string err;
 };
 
-static int ensure_pipeline(svo_ctx *c);
+static int ensure_pipeline(svo_ctx *c, int set = 1);
 
 // kernels whose workspace exists once per context (wavefront queues, split queue, the persistent kernel's counter) and the
 // validation planes (one set) cannot run on two lanes at once: both lanes then share lane 0's stream
@@ -90,7 +98,7 @@ static void refresh_stream(svo_ctx *c) { c->stream = lanes_share_stream(c) ? c->
 // order everything enqueued on the other lane before what the current lane enqueues next
 static cudaError_t join_lanes(svo_ctx *c) {
   if (c->lane_stream[0] == c->lane_stream[1]) return cudaSuccess;
-  for (int l = 0; l < 2; l++) {
+  for (int l = 0; l < kLanes; l++) {
     if (c->lane_stream[l] == c->stream) continue;
     cudaError_t e = cudaEventRecord(c->ev_lane[l], c->lane_stream[l]);
     if (e != cudaSuccess) return e;
@@ -100,8 +108,8 @@ static cudaError_t join_lanes(svo_ctx *c) {
 }
 static cudaError_t sync_lanes(svo_ctx *c) {
   cudaError_t e = cudaStreamSynchronize(c->lane_stream[0]);
-  if (e != cudaSuccess) return e;
-  if (c->lane_stream[1] != c->lane_stream[0]) e = cudaStreamSynchronize(c->lane_stream[1]);
+  for (int l = 1; l < kLanes && e == cudaSuccess; l++)
+    if (c->lane_stream[l] != c->lane_stream[0]) e = cudaStreamSynchronize(c->lane_stream[l]);
   return e;
 }
 
@@ -146,7 +154,7 @@ size_t plane_elems(const svo_ctx *c, int plane) {
 }
 void *plane_ptr(const svo_ctx *c, int plane) {
   if (c->bound[plane]) return c->bound[plane];
-  if (plane <= SVO_PLANE_DEPTH && c->render_set == 1 && c->back[plane]) return c->back[plane];
+  if (plane <= SVO_PLANE_DEPTH && c->render_set >= 1 && c->back[c->render_set][plane]) return c->back[c->render_set][plane];
   return c->own[plane];
 }
 
@@ -290,31 +298,42 @@ int retranscode(svo_ctx *c) {
   c->have_scene = false;  // until the descriptor arrays match d_raw again (a refused stream leaves the context without a scene)
   // the kernels may still be reading the previous arrays
   SVO_CUDA(c, sync_lanes(c));
+  // final arrays: 25 % head-room, which the incremental transcode (svo_upload_range) appends into
+  auto ensure_arrays = [&](uint64_t n) -> int {
+    if (n + n / 8 <= c->desc_cap && c->d_meta && c->d_flag) return SVO_OK;
+    if (c->d_desc) cudaFree(c->d_desc);
+    if (c->d_refbase) cudaFree(c->d_refbase);
+    if (c->d_meta) cudaFree(c->d_meta);
+    if (c->d_flag) cudaFree(c->d_flag);
+    c->d_desc = nullptr; c->d_refbase = nullptr; c->d_meta = nullptr; c->d_flag = nullptr;
+    c->desc_cap = 0;
+    const uint64_t want = n + n / 4 + 4096;
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, want * sizeof(uint2)));
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, want * sizeof(uint32_t)));
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_meta, want * sizeof(uint2)));
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_flag, want));
+    c->desc_cap = want;
+    return SVO_OK;
+  };
   if (c->opt_gpu_transcode) {
     // a tree has at most one interior record per 7 bytes; anything larger is aliased/cyclic and goes to the host
     // path, which reports it
     const uint64_t cap = c->nbytes / 7 + 4096;
-    DevBuf tmp_desc, tmp_ref;
+    DevBuf tmp_desc, tmp_ref, tmp_meta;
     SVO_CUDA(c, tmp_desc.alloc(cap * sizeof(uint2)));
     SVO_CUDA(c, tmp_ref.alloc(cap * sizeof(uint32_t)));
+    SVO_CUDA(c, tmp_meta.alloc(cap * sizeof(uint2)));
     bool overflow = false;
-    SVO_CUDA(c, gpu_transcode(c->d_raw, c->nbytes, tmp_desc.as<uint2>(), tmp_ref.as<uint32_t>(), cap, &nd, &nlevels, &leaf_box, depth_box,
-                              &overflow, c->stream));
+    SVO_CUDA(c, gpu_transcode(c->d_raw, c->nbytes, tmp_desc.as<uint2>(), tmp_ref.as<uint32_t>(), tmp_meta.as<uint2>(), cap, &nd, &nlevels, &leaf_box,
+                              depth_box, &overflow, c->stream));
     c->launches += 2 + 3 * (uint64_t)nlevels;
     if (!overflow) {
-      if (nd > c->desc_cap) {
-        if (c->d_desc) cudaFree(c->d_desc);
-        if (c->d_refbase) cudaFree(c->d_refbase);
-        c->d_desc = nullptr;
-        c->d_refbase = nullptr;
-        c->desc_cap = 0;
-        const uint64_t want = nd + nd / 8 + 64;
-        SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, want * sizeof(uint2)));
-        SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, want * sizeof(uint32_t)));
-        c->desc_cap = want;
-      }
+      int rc = ensure_arrays(nd);
+      if (rc) return rc;
       SVO_CUDA(c, cudaMemcpyAsync(c->d_desc, tmp_desc.p, nd * sizeof(uint2), cudaMemcpyDeviceToDevice, c->stream));
       SVO_CUDA(c, cudaMemcpyAsync(c->d_refbase, tmp_ref.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+      SVO_CUDA(c, cudaMemcpyAsync(c->d_meta, tmp_meta.p, nd * sizeof(uint2), cudaMemcpyDeviceToDevice, c->stream));
+      SVO_CUDA(c, cudaMemsetAsync(c->d_flag, 0, c->desc_cap, c->stream));
       SVO_CUDA(c, cudaStreamSynchronize(c->stream));
       done = true;
     }
@@ -326,24 +345,18 @@ int retranscode(svo_ctx *c) {
     std::string err;
     if (!transcode_stream(h_raw.data(), c->nbytes, t, err)) return fail(c, SVO_ERR_FORMAT, err);
     nd = t.desc.size();
-    if (nd > c->desc_cap) {
-      if (c->d_desc) cudaFree(c->d_desc);
-      if (c->d_refbase) cudaFree(c->d_refbase);
-      c->d_desc = nullptr;
-      c->d_refbase = nullptr;
-      c->desc_cap = 0;
-      const uint64_t cap = nd + nd / 8 + 64;
-      SVO_CUDA(c, cudaMalloc((void **)&c->d_desc, cap * sizeof(uint2)));
-      SVO_CUDA(c, cudaMalloc((void **)&c->d_refbase, cap * sizeof(uint32_t)));
-      c->desc_cap = cap;
-    }
+    int rc = ensure_arrays(nd);
+    if (rc) return rc;
     SVO_CUDA(c, cudaMemcpyAsync(c->d_desc, t.desc.data(), nd * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
     SVO_CUDA(c, cudaMemcpyAsync(c->d_refbase, t.refbase.data(), nd * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    SVO_CUDA(c, cudaMemcpyAsync(c->d_meta, t.meta.data(), nd * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    SVO_CUDA(c, cudaMemsetAsync(c->d_flag, 0, c->desc_cap, c->stream));
     SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // t goes out of scope
     nlevels = (uint32_t)t.level_start.size();
     leaf_box = t.leaf_box;
     for (int d = 0; d < 24; d++) depth_box[d] = t.depth_box[d];
   }
+  c->ndesc_live = nd;
   c->ndesc = (uint32_t)nd;
   c->nlevels = nlevels;
   uint32_t w0 = 0;
@@ -380,15 +393,19 @@ int retranscode(svo_ctx *c) {
 }  // namespace
 
 // ---- pipelined read-back: render frame s+1 while frame s travels to the host -----------------------------------
-static int ensure_pipeline(svo_ctx *c) {
-  if (c->copy_stream) return SVO_OK;
-  SVO_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
-  for (int p = 0; p < 2; p++) SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[p], cudaEventDisableTiming));
-  for (int p = 0; p < 2; p++) {
-    const size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
-    SVO_CUDA(c, cudaMalloc(&c->back[p], bytes));
-    SVO_CUDA(c, cudaMemsetAsync(c->back[p], 0, bytes, c->stream));
+static int ensure_pipeline(svo_ctx *c, int set) {
+  if (!c->copy_stream) {
+    SVO_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
+    for (int p = 0; p < kLanes; p++) SVO_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[p], cudaEventDisableTiming));
+  }
+  if (set >= 1 && set < kLanes && !c->back[set][0]) {
+    for (int p = 0; p < 2; p++) {
+      const size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
+      SVO_CUDA(c, cudaMalloc(&c->back[set][p], bytes));
+      SVO_CUDA(c, cudaMemsetAsync(c->back[set][p], 0, bytes, c->stream));
+    }
+    SVO_CUDA(c, cudaStreamSynchronize(c->stream));  // other lanes may use the set next
   }
   return SVO_OK;
 }
@@ -431,11 +448,12 @@ int svo_create(svo_ctx **out, int device, int width, int height) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaGetDeviceProperties"); break; }
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
-    if ((e = cudaStreamCreateWithFlags(&c->own_stream2, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
-    c->lane_stream[0] = c->own_stream;
-    c->lane_stream[1] = c->own_stream2;
+    c->own_lane_stream[0] = c->own_stream;
+    for (int l = 1; l < kLanes && e == cudaSuccess; l++) e = cudaStreamCreateWithFlags(&c->own_lane_stream[l], cudaStreamNonBlocking);
+    if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
+    for (int l = 0; l < kLanes; l++) c->lane_stream[l] = c->own_lane_stream[l];
     c->stream = c->own_stream;
-    for (int l = 0; l < 2; l++)
+    for (int l = 0; l < kLanes; l++)
       if ((e = cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming)) != cudaSuccess) break;
     if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
@@ -461,20 +479,26 @@ void svo_destroy(svo_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  if (c->own_stream2) cudaStreamSynchronize(c->own_stream2);
+  for (int l = 1; l < kLanes; l++)
+    if (c->own_lane_stream[l]) cudaStreamSynchronize(c->own_lane_stream[l]);
   for (auto &m : c->ipc_maps) cudaIpcCloseMemHandle(m.base);
   for (int p = 0; p < 7; p++)
     if (c->own[p]) cudaFree(c->own[p]);
   if (c->d_raw) cudaFree(c->d_raw);
   if (c->d_desc) cudaFree(c->d_desc);
   if (c->d_refbase) cudaFree(c->d_refbase);
+  if (c->d_meta) cudaFree(c->d_meta);
+  if (c->d_flag) cudaFree(c->d_flag);
+  if (c->d_stage) cudaFree(c->d_stage);
+  if (c->d_bitmap) cudaFree(c->d_bitmap);
   if (c->d_rays) cudaFree(c->d_rays);
   if (c->d_hits) cudaFree(c->d_hits);
-  for (int p = 0; p < 2; p++)
-    if (c->back[p]) cudaFree(c->back[p]);
+  for (int l = 1; l < kLanes; l++)
+    for (int p = 0; p < 2; p++)
+      if (c->back[l][p]) cudaFree(c->back[l][p]);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
-  for (int p = 0; p < 2; p++)
+  for (int p = 0; p < kLanes; p++)
     if (c->ev_copied[p]) cudaEventDestroy(c->ev_copied[p]);
   if (c->d_sort) cudaFree(c->d_sort);
   if (c->d_sort_temp) cudaFree(c->d_sort_temp);
@@ -486,8 +510,9 @@ void svo_destroy(svo_ctx *c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  if (c->own_stream2) cudaStreamDestroy(c->own_stream2);
-  for (int l = 0; l < 2; l++)
+  for (int l = 1; l < kLanes; l++)
+    if (c->own_lane_stream[l]) cudaStreamDestroy(c->own_lane_stream[l]);
+  for (int l = 0; l < kLanes; l++)
     if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]);
   cudaGetLastError();
   delete c;
@@ -546,8 +571,7 @@ int svo_set_stream(svo_ctx *c, void *cuda_stream) {
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, sync_lanes(c));
   // a caller-owned stream carries both lanes (no overlap between frames); NULL restores the context's two streams
-  c->lane_stream[0] = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
-  c->lane_stream[1] = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream2;
+  for (int l = 0; l < kLanes; l++) c->lane_stream[l] = cuda_stream ? (cudaStream_t)cuda_stream : c->own_lane_stream[l];
   refresh_stream(c);
   return SVO_OK;
 }
@@ -591,13 +615,57 @@ int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t 
     c->d_raw = nr;
     c->raw_cap = cap;
   }
+  c->nbytes_before_range = c->nbytes;
   if (end > c->nbytes) {
     // bytes between the old end and `start` were never uploaded: they read as zero
     if (start > c->nbytes) SVO_CUDA(c, cudaMemsetAsync(c->d_raw + c->nbytes, 0, start - c->nbytes, c->stream));
     c->nbytes = end;
   }
-  SVO_CUDA(c, cudaMemcpyAsync(c->d_raw + start, nodes + start, end - start, cudaMemcpyHostToDevice, c->stream));
-  return retranscode(c);
+  // Store the bytes and find out which of them really changed (the engine's ranges run from the first to the last touched
+  // record: mostly unchanged bytes), then re-walk only the subtrees those bytes belong to (gpu_patch).
+  const uint64_t len = end - start, old_nbytes = c->nbytes_before_range;
+  if (len + 16 > c->stage_cap) {
+    SVO_CUDA(c, sync_lanes(c));
+    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->d_bitmap) cudaFree(c->d_bitmap);
+    c->d_stage = c->d_bitmap = nullptr;
+    c->stage_cap = 0;
+    const uint64_t cap = len + len / 2 + 4096;
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_stage, cap));
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_bitmap, cap / 8 + 16));
+    c->stage_cap = cap;
+  }
+  SVO_CUDA(c, cudaMemcpyAsync(c->d_stage, nodes + start, len, cudaMemcpyHostToDevice, c->stream));
+  uint64_t span[2] = {0, 0};
+  SVO_CUDA(c, gpu_diff_apply(c->d_raw, c->d_stage, start, end, old_nbytes, c->d_bitmap, span, c->stream));
+  c->launches++;
+  for (int k = 0; k < 4; k++) c->patch_stats[k] = 0;
+  if (span[0] >= span[1]) return SVO_OK;  // nothing changed: the descriptors are still right
+  bool fallback = !c->opt_gpu_transcode || !c->d_meta || !c->d_flag;
+  if (!fallback) {
+    uint64_t nd = c->ndesc;
+    c->have_scene = false;
+    SVO_CUDA(c, gpu_patch(c->d_raw, c->nbytes, c->d_bitmap, start, end, span, c->d_desc, c->d_refbase, c->d_meta, c->d_flag, c->desc_cap, &nd,
+                          &c->leaf_box, c->depth_box, &fallback, c->patch_stats, c->stream));
+    c->launches += 8;
+    if (!fallback) {
+      c->ndesc = (uint32_t)nd;
+      // whole transcodes recompute what patches only ever grow (content boxes) and drop what they leave behind (unreachable
+      // descriptors): do one when the patched-in part has grown to a quarter of the array
+      if (c->ndesc - c->ndesc_live > c->ndesc_live / 4 + 4096) fallback = true;
+    }
+  }
+  if (fallback) {
+    c->patch_stats[3] = 1;
+    return retranscode(c);
+  }
+  if (span[0] < 4) {  // octreeBuffer[0] == 0 feeds the debug overlay (svotrace.comp:696)
+    uint32_t w0 = 0;
+    SVO_CUDA(c, cudaMemcpy(&w0, c->d_raw, c->nbytes < 4 ? c->nbytes : 4, cudaMemcpyDeviceToHost));
+    c->first_word_zero = (w0 == 0);
+  }
+  c->have_scene = true;
+  return SVO_OK;
 }
 
 int svo_build_terrain_device(svo_ctx *c, const uint16_t *height, const uint8_t *mat, int n, int chunk, uint64_t *out_bytes) {
@@ -637,7 +705,7 @@ int svo_scene_info(const svo_ctx *c, uint64_t info[4]) {
   info[0] = c->nbytes;
   info[1] = c->ndesc;
   info[2] = c->nlevels;
-  info[3] = c->raw_cap + c->desc_cap * (sizeof(uint2) + sizeof(uint32_t));
+  info[3] = c->raw_cap + c->desc_cap * (sizeof(uint2) + sizeof(uint32_t) + sizeof(uint2) + 1);
   return SVO_OK;
 }
 
@@ -806,7 +874,7 @@ int svo_swap_buffers(svo_ctx *c) {
   SVO_CUDA(c, cudaSetDevice(c->device));
   int rc = ensure_pipeline(c);
   if (rc) return rc;
-  c->render_set ^= 1;
+  c->render_set = c->render_set == 0 ? 1 : 0;  // (lanes 2, 3 are reached with svo_select_lane only)
   c->lane = c->render_set;  // the other set is drawn on the other lane: consecutive frames may overlap on the GPU
   refresh_stream(c);
   // the next render overwrites this set: wait (on the device) until its last read-back has left it
@@ -816,10 +884,10 @@ int svo_swap_buffers(svo_ctx *c) {
 
 int svo_select_lane(svo_ctx *c, int lane) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
-  if (lane != 0 && lane != 1) return fail(c, SVO_ERR_INVALID, "lane must be 0 or 1");
+  if (lane < 0 || lane >= kLanes) return fail(c, SVO_ERR_INVALID, "lane must be in [0, 4)");
   if (lane == c->lane) return SVO_OK;
   SVO_CUDA(c, cudaSetDevice(c->device));
-  int rc = ensure_pipeline(c);
+  int rc = ensure_pipeline(c, lane);
   if (rc) return rc;
   c->lane = lane;
   c->render_set = lane;
@@ -836,9 +904,9 @@ int svo_read_wait(svo_ctx *c) {
 }
 
 void *svo_device_ptr(svo_ctx *c, int plane) {
-  if (c && (plane == (SVO_PLANE_COLOR_RGBA8 | SVO_PLANE_BACK) || plane == (SVO_PLANE_DEPTH | SVO_PLANE_BACK))) {
+  if (c && (plane >> 8) >= 1 && (plane >> 8) < kLanes && (plane & 0xFF) <= SVO_PLANE_DEPTH) {  // plane | (set << 8): the sets of lanes 1..3
     cudaSetDevice(c->device);
-    return ensure_pipeline(c) == SVO_OK ? c->back[plane & 0xFF] : nullptr;
+    return ensure_pipeline(c, plane >> 8) == SVO_OK ? c->back[plane >> 8][plane & 0xFF] : nullptr;
   }
   if (!c || plane < 0 || plane > SVO_PLANE_RADIANCE) return nullptr;
   if (plane <= SVO_PLANE_DEPTH) return c->own[plane];  // the front set, whatever is bound or current
@@ -858,11 +926,11 @@ int svo_bind_plane(svo_ctx *c, int plane, void *device_ptr) {
 
 int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[72]) {
   if (!c || !handle) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
-  if (plane == (SVO_PLANE_COLOR_RGBA8 | SVO_PLANE_BACK) || plane == (SVO_PLANE_DEPTH | SVO_PLANE_BACK)) {
+  if ((plane >> 8) >= 1 && (plane >> 8) < kLanes && (plane & 0xFF) <= SVO_PLANE_DEPTH) {
     SVO_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_pipeline(c);
+    int rc = ensure_pipeline(c, plane >> 8);
     if (rc) return rc;
-    return export_handle(c, c->back[plane & 0xFF], handle);
+    return export_handle(c, c->back[plane >> 8][plane & 0xFF], handle);
   }
   if (plane < 0 || plane > SVO_PLANE_RADIANCE) return fail(c, SVO_ERR_INVALID, "bad plane");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
@@ -1006,7 +1074,7 @@ int svo_timer_begin(svo_ctx *c) {
   SVO_CUDA(c, join_lanes(c));  // the interval starts after everything enqueued so far, on either lane ...
   SVO_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   // ... and nothing enqueued on the other lane from now on may start before it
-  for (int l = 0; l < 2; l++)
+  for (int l = 0; l < kLanes; l++)
     if (c->lane_stream[l] != c->stream) SVO_CUDA(c, cudaStreamWaitEvent(c->lane_stream[l], c->ev0, 0));
   return SVO_OK;
 }
@@ -1097,6 +1165,48 @@ static int render_stats(svo_ctx *c, const svo_frame *frame, uint64_t counters[3]
   SVO_CUDA(c, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 3; i++) counters[i] = h[i];
+  return SVO_OK;
+}
+
+// Layout-independent fingerprint of the descriptor tree: a depth-first walk from the root over the downloaded arrays.
+// Two scenes that hold the same octree give the same numbers however their descriptors are ordered (whole transcode:
+// breadth-first; after svo_upload_range: patched subtrees live at the tail).
+int svo_scene_canonical(svo_ctx *c, uint64_t out[4]) {
+  if (!c || !out) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_scene_canonical before svo_upload");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  SVO_CUDA(c, sync_lanes(c));
+  std::vector<uint2> desc(c->ndesc);
+  std::vector<uint32_t> ref(c->ndesc);
+  SVO_CUDA(c, cudaMemcpy(desc.data(), c->d_desc, (size_t)c->ndesc * sizeof(uint2), cudaMemcpyDeviceToHost));
+  SVO_CUDA(c, cudaMemcpy(ref.data(), c->d_refbase, (size_t)c->ndesc * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint64_t h = 1469598103934665603ull, reachable = 0, max_depth = 0;
+  auto mix = [&](uint32_t v) { for (int i = 0; i < 4; i++) { h ^= (v >> (8 * i)) & 0xFFu; h *= 1099511628211ull; } };
+  std::vector<std::pair<uint32_t, uint32_t>> stack;  // (descriptor index, depth)
+  if (c->ndesc) stack.push_back({0u, 0u});
+  while (!stack.empty()) {
+    const uint32_t i = stack.back().first, d = stack.back().second;
+    stack.pop_back();
+    if (i >= c->ndesc || reachable > c->ndesc) return fail(c, SVO_ERR_FORMAT, "descriptor tree is broken (index out of range or cycle)");
+    reachable++;
+    if (d > max_depth) max_depth = d;
+    mix(desc[i].y);
+    mix(ref[i]);
+    mix(d);
+    const uint32_t has = desc[i].y >> 24;
+    uint32_t k = (uint32_t)__builtin_popcount(has);
+    for (int cidx = 7; cidx >= 0; cidx--)  // push in reverse so that children pop in child order
+      if ((has >> cidx) & 1u) stack.push_back({desc[i].x + --k, d + 1u});
+  }
+  out[0] = reachable;
+  out[1] = h;
+  out[2] = max_depth;
+  out[3] = c->ndesc;
+  return SVO_OK;
+}
+int svo_upload_stats(const svo_ctx *c, uint64_t out[4]) {
+  if (!c || !out) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  for (int k = 0; k < 4; k++) out[k] = c->patch_stats[k];
   return SVO_OK;
 }
 

@@ -19,53 +19,24 @@
 // The few hundred nodes above the chunks (fill levels, chunk children, the 7-byte gap after every spliced sub-octree,
 // Octree.java:336) are laid out on the host from the per-unit sizes.  The stream never leaves HBM: svo_build_terrain_device
 // hands it to the same transcode svo_upload runs.
-#ifndef SVO_HOST_EMU
-#include <cub/cub.cuh>
-#endif
-
 #include <cstdio>
-#include <cstdlib>
-#include <cstring>
 #include <vector>
 
 #include "../../include/svo_b200.h"
+#include "svo_dev.h"
 #include "svo_gpu_build.h"
-
-// The CPU test suite compiles this file with g++ and runs the kernels on the coroutine SIMT emulator
-// (tests/hostemu/simt_emu.h, SVO_HOST_EMU): "device" memory is then host memory and the scan is a loop.
-#ifdef SVO_HOST_EMU
-#define SVO_LAUNCH(grid, block, stream, ...) simt::launcher(grid, block, __VA_ARGS__)
-#else
-#define SVO_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<grid, block, 0, stream>>>
-#endif
 
 namespace svo {
 namespace {
 
-#ifdef SVO_HOST_EMU
-cudaError_t dev_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-void dev_free(void *p) { free(p); }
-cudaError_t dev_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memcpy(dst, src, bytes); return cudaSuccess; }
-cudaError_t dev_memset(void *p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
-cudaError_t dev_sync(cudaStream_t) { return cudaSuccess; }
-cudaError_t dev_last_error() { return cudaSuccess; }
-cudaError_t exclusive_scan(void *, size_t &temp_bytes, uint32_t *data, int n, cudaStream_t) {
-  if (temp_bytes == 0) { temp_bytes = 1; return cudaSuccess; }  // size query
-  uint32_t run = 0;
-  for (int i = 0; i < n; i++) { const uint32_t v = data[i]; data[i] = run; run += v; }
-  return cudaSuccess;
-}
-#else
-cudaError_t dev_alloc(void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16); }
-void dev_free(void *p) { cudaFree(p); }
-cudaError_t dev_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) { return cudaMemcpyAsync(dst, src, bytes, kind, st); }
-cudaError_t dev_memset(void *p, int v, size_t bytes, cudaStream_t st) { return cudaMemsetAsync(p, v, bytes, st); }
-cudaError_t dev_sync(cudaStream_t st) { return cudaStreamSynchronize(st); }
-cudaError_t dev_last_error() { return cudaGetLastError(); }
-cudaError_t exclusive_scan(void *temp, size_t &temp_bytes, uint32_t *data, int n, cudaStream_t st) {
-  return cub::DeviceScan::ExclusiveSum(temp_bytes == 0 ? nullptr : temp, temp_bytes, data, data, n, st);  // in place
-}
-#endif
+using dev::Pool;
+inline cudaError_t dev_alloc(void **p, size_t bytes) { return dev::alloc(p, bytes); }
+inline void dev_free(void *p) { dev::release(p); }
+inline cudaError_t dev_copy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) { return dev::copy(dst, src, bytes, kind, st); }
+inline cudaError_t dev_memset(void *p, int v, size_t bytes, cudaStream_t st) { return dev::fill(p, v, bytes, st); }
+inline cudaError_t dev_sync(cudaStream_t st) { return dev::sync(st); }
+inline cudaError_t dev_last_error() { return dev::last_error(); }
+inline cudaError_t exclusive_scan(void *temp, size_t &temp_bytes, uint32_t *data, int n, cudaStream_t st) { return dev::exclusive_scan(temp, temp_bytes, data, n, st); }
 
 enum { T_INTERIOR = 0, T_SURFACE = 1, T_SUBDIV = 2, T_NONSURF = 3 };
 
@@ -359,17 +330,6 @@ void fill_empty(HostTree &t, size_t parent, int levels, const int p[3], int chun
   for (int i = 0; i < 8; i++) fill_empty(t, children[i], levels - 1, cp[i], chunk, chunks);
   t.set_cp(parent, children[0]);
 }
-
-struct Pool {  // device allocations of one build, freed together
-  std::vector<void *> blocks;
-  ~Pool() { for (void *p : blocks) dev_free(p); }
-  template <class T> cudaError_t get(T **p, size_t count) {
-    void *q = nullptr;
-    cudaError_t e = dev_alloc(&q, (count ? count : 1) * sizeof(T));
-    if (e == cudaSuccess) { blocks.push_back(q); *p = (T *)q; }
-    return e;
-  }
-};
 
 #define GB_CUDA(call)                    \
   do {                                   \

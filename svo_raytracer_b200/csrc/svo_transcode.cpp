@@ -29,7 +29,8 @@ struct NodeOut {
 };
 
 inline uint32_t visit(const uint8_t *raw, uint64_t nbytes, const Pending &nd, int depth, uint32_t child_base, Pending *next_out,
-                      uint2 *desc_out, uint32_t *refbase_out, CellBox *leaf_box, CellBox *depth_box) {
+                      uint2 *desc_out, uint32_t *refbase_out, CellBox *leaf_box, CellBox *depth_box, uint2 *meta_out = nullptr,
+                      uint32_t my_index = 0) {
   const uint32_t ref_base = nd.off + nd.cp;  // uint wrap-around as in extractChild (:134)
   uint32_t p = ref_base, nonzero = 0, has_desc = 0, n_next = 0;
   for (uint32_t c = 0; c < 8; c++) {
@@ -51,6 +52,7 @@ inline uint32_t visit(const uint8_t *raw, uint64_t nbytes, const Pending &nd, in
       if (ccp != 0u && depth < 22) {  // child.cp != 0: the traversal may PUSH into it
         has_desc |= 1u << c;
         if (next_out) next_out[n_next] = {p, ccp, rd_be16(raw, nbytes, p + 5u), cx, cy, cz};
+        if (meta_out) meta_out[n_next] = make_uint2(p, my_index);
         n_next++;
       }
     }
@@ -84,6 +86,8 @@ void parallel_chunks(size_t n, int nthreads, F f) {  // f(chunk_index, begin, en
 bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std::string &err, int nthreads) {
   out.desc.clear();
   out.refbase.clear();
+  out.meta.clear();
+  out.meta.push_back(make_uint2(0u, 0xFFFFFFFFu));
   out.level_start.clear();
   out.leaf_box = CellBox();
   for (CellBox &b : out.depth_box) b = CellBox();
@@ -119,11 +123,13 @@ bool transcode_stream(const uint8_t *raw, uint64_t nbytes, Transcoded &out, std:
     out.refbase.resize(level_base + n);
     next.resize(total);
     const uint64_t next_base = level_base + n;
+    out.meta.resize(next_base + total);
     std::vector<CellBox> leaf_boxes((size_t)nthreads), depth_boxes((size_t)nthreads);
     parallel_chunks(n, nthreads, [&](size_t t, size_t b, size_t e) {
       for (size_t i = b; i < e; i++)
         visit(raw, nbytes, cur[i], depth, (uint32_t)(next_base + counts[i]), next.data() + counts[i], &out.desc[level_base + i],
-              &out.refbase[level_base + i], &leaf_boxes[t], &depth_boxes[t]);
+              &out.refbase[level_base + i], &leaf_boxes[t], &depth_boxes[t], out.meta.data() + next_base + counts[i],
+              (uint32_t)(level_base + i));
     });
     for (int t = 0; t < nthreads; t++) {
       out.leaf_box.add(leaf_boxes[(size_t)t]);

@@ -34,6 +34,8 @@ struct CellBox {
 struct Transcoded {
   std::vector<uint2> desc;
   std::vector<uint32_t> refbase;
+  std::vector<uint2> meta;            // per node: .x = byte offset of its own record, .y = index of its parent (root: 0xFFFFFFFF);
+                                      // what the incremental transcode (svo_upload_range) needs to find the nodes an edit touches
   std::vector<uint32_t> level_start;  // desc index where each BFS level begins
   // Where a cast can end in a hit: `leaf_box` bounds every record with value != 0 that the traversal treats
   // as a leaf (child.cp == 0, svotrace.comp:311), `depth_box[d]` bounds every record with value != 0 at tree

@@ -128,6 +128,18 @@ class SvoContext:
         self._check(self._lib.svo_download(self._h, out.ctypes.data_as(C.c_void_p), out.size))
         return out
 
+    def upload_stats(self) -> dict:
+        """How the last upload_range was absorbed (svo_upload_stats)."""
+        o = (C.c_uint64 * 4)()
+        self._check(self._lib.svo_upload_stats(self._h, C.byref(o)))
+        return {"dirty": int(o[0]), "roots": int(o[1]), "appended": int(o[2]), "whole_transcode": bool(o[3])}
+
+    def scene_canonical(self) -> dict:
+        """Layout-independent fingerprint of the descriptor tree (svo_scene_canonical)."""
+        o = (C.c_uint64 * 4)()
+        self._check(self._lib.svo_scene_canonical(self._h, C.byref(o)))
+        return {"reachable": int(o[0]), "hash": int(o[1]), "depth": int(o[2]), "stored": int(o[3])}
+
     def scene_probe(self):
         """Hash / counts / bounds of the descriptors held on the device (same 8 words as svo_transcode_probe)."""
         out = (C.c_uint64 * 8)()

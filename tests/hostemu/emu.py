@@ -11,9 +11,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.normpath(os.path.join(_HERE, "..", "..", "svo_raytracer_b200", "csrc"))
 _LIB_PATH = os.path.join(_HERE, "libsvo_hostemu.so")
-_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "gpu_build_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
+_CPP = [os.path.join(_HERE, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "gpu_build_emu.cpp", "transcode_emu.cpp", "simt_emu.cpp")] + [os.path.join(_CSRC, "svo_transcode.cpp")]
 _SRCS = _CPP + [os.path.join(_HERE, f) for f in ("cuda_host_shim.h", "simt_emu.h", "emu_scene.h")] + \
-    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_wavefront.cu", "svo_transcode.h", "svo_gpu_build.cu", "svo_gpu_build.h")]
+    [os.path.join(_CSRC, f) for f in ("svo_trace.cuh", "detmath.cuh", "svo_kernels.h", "svo_kernels.cu", "svo_wavefront.cu", "svo_transcode.h", "svo_gpu_build.cu", "svo_gpu_build.h", "svo_gpu_transcode.cu", "svo_dev.h")]
 CUDA_INCLUDE = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
 
@@ -48,6 +48,10 @@ def lib():
         L.emu_gpu_build_terrain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
         L.emu_beam_conservative.restype = C.c_int
         L.emu_beam_conservative.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.emu_gpu_transcode_check.restype = C.c_int
+        L.emu_gpu_transcode_check.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+        L.emu_patch_check.restype = C.c_int
+        L.emu_patch_check.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.emu_fence_word.restype = C.c_uint
         L.emu_fence_word.argtypes = [C.c_int]
         L.emu_launch_cast.restype = C.c_int
@@ -236,3 +240,21 @@ def gpu_build_terrain(height, mat, n, chunk, nthreads=8):
     rc = lib().emu_gpu_build_terrain(_ptr(height), _ptr(mat), n, chunk, _ptr(out), out.size, C.byref(nb), nthreads)
     assert rc == 0, rc
     return out
+
+
+def gpu_transcode_check(nodes, nthreads=8) -> int:
+    """svo_gpu_transcode.cu's whole transcode on the emulator against the host transcode; 0 = identical."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint8)
+    return int(lib().emu_gpu_transcode_check(_ptr(nodes), nodes.size, nthreads))
+
+
+def patch_check(old, new, ranges, nthreads=8) -> dict:
+    """Incremental transcode (gpu_diff_apply + gpu_patch) of `ranges` = [(start, end), ...] turning stream `old` into `new`."""
+    old = np.ascontiguousarray(old, dtype=np.uint8)
+    new = np.ascontiguousarray(new, dtype=np.uint8)
+    r = np.ascontiguousarray(np.array(ranges, dtype=np.uint64).reshape(-1))
+    out = np.zeros(8, np.uint64)
+    rc = lib().emu_patch_check(_ptr(old), old.size, _ptr(new), new.size, _ptr(r), len(ranges), _ptr(out), nthreads)
+    assert rc == 0, rc
+    return {"status": int(out[0]), "dirty": int(out[1]), "roots": int(out[2]), "appended": int(out[3]), "fell_back": int(out[4]),
+            "reachable": int(out[5]), "stored": int(out[6])}

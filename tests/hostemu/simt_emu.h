@@ -141,6 +141,29 @@ static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
   simt::warp_barrier();
   return r;
 }
+static inline uint32_t __reduce_min_sync(uint32_t, uint32_t v) {
+  simt::Block *b = simt::g_block;
+  const int w = b->cur >> 5;
+  b->val[b->cur] = v;
+  simt::warp_barrier();
+  uint32_t r = 0xFFFFFFFFu;
+  for (int l = 0; l < 32; l++)
+    if (simt::lane_alive(w, l) && (uint32_t)b->val[w * 32 + l] < r) r = (uint32_t)b->val[w * 32 + l];
+  simt::warp_barrier();
+  return r;
+}
+static inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) {
+  simt::Block *b = simt::g_block;
+  const int w = b->cur >> 5;
+  b->val[b->cur] = v;
+  simt::warp_barrier();
+  uint32_t r = 0;
+  for (int l = 0; l < 32; l++)
+    if (simt::lane_alive(w, l) && (uint32_t)b->val[w * 32 + l] > r) r = (uint32_t)b->val[w * 32 + l];
+  simt::warp_barrier();
+  return r;
+}
+static inline int __any_sync(uint32_t m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline void __syncwarp(uint32_t = 0xffffffffu) { simt::warp_barrier(); }
 static inline void __syncthreads() { simt::cta_barrier(); }
 static inline int __syncthreads_or(int pred) {
@@ -156,6 +179,11 @@ static inline int __syncthreads_or(int pred) {
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicMin(unsigned *p, unsigned v) { unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { unsigned long long o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline unsigned atomicAdd_system(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

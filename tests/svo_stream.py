@@ -137,3 +137,115 @@ def slab_hit(o, d, lo, hi):
     tf = np.where(np.isnan(tf), np.inf, tf)
     t_in, t_out = max(tn.max(), 0.0), tf.min()
     return float(t_in) if t_in <= t_out else None
+
+
+class StreamEditor:
+    """In-place edits of a node stream the way the engine's SDF brush makes them (Octree.java:700-885): values set in
+    existing records, subdividable leaves (7-byte records) turned into interior nodes whose eight children are APPENDED at
+    memOffset, interior children collapsed back into leaves.  Tracks the two byte ranges the engine would push with
+    Renderer.updateSSBO (ChangeBounds, Octree.java:676-698): [start0, end0) over touched existing records and
+    [start1, end1) over appended ones."""
+
+    def __init__(self, nodes: np.ndarray, slack: int = 1 << 16):
+        self.buf = bytearray(nodes.tobytes()) + bytearray(slack)
+        self.mem = int(nodes.size)  # memOffset
+        self.start0, self.end0 = self.mem, 0
+        self.start1 = self.end1 = self.mem
+
+    # -- record access -------------------------------------------------------------------------------------------
+    def cp(self, off):
+        return struct.unpack(">i", self.buf[off + 1:off + 5])[0]
+
+    def mask(self, off):
+        return struct.unpack(">H", self.buf[off + 5:off + 7])[0]
+
+    def child(self, parent_off, n):
+        """(record offset, type code) of child n of the interior record at parent_off."""
+        m, p = self.mask(parent_off), parent_off + self.cp(parent_off)
+        for i in range(n):
+            p += SIZES[(m >> (2 * i)) & 3]
+        return p, (m >> (2 * n)) & 3
+
+    def walk(self, path):
+        """Follow child indices from the root.  Returns (parent offset, child index, record offset, code) of the last step."""
+        off, parent, code = 0, None, 0
+        for n in path:
+            assert code == 0 and self.cp(off) != 0, "path leaves the interior nodes"
+            parent = off
+            off, code = self.child(off, n)
+        return parent, path[-1], off, code
+
+    def _touch(self, a, b):  # updateExistingNodeBounds
+        if a < self.start1:
+            self.start0 = min(self.start0, a)
+            self.end0 = max(self.end0, min(b, self.start1))
+
+    # -- edits ---------------------------------------------------------------------------------------------------
+    def set_value(self, path, value):
+        _, _, off, _ = self.walk(path)
+        self.buf[off] = value
+        self._touch(off, off + 7)
+
+    def set_code(self, parent_off, n, code):
+        m = self.mask(parent_off)
+        m = (m & ~(3 << (2 * n))) | (code << (2 * n))
+        self.buf[parent_off + 5:parent_off + 7] = struct.pack(">H", m)
+        self._touch(parent_off, parent_off + 7)
+
+    def subdivide(self, path, values, surface=False, normal=595):
+        """subdivideNode (Octree.java:829-885): the 7-byte leaf at `path` becomes an interior node with eight appended
+        children (subdividable leaves, or 3-byte surface leaves when `surface`) holding `values`."""
+        parent, n, off, code = self.walk(path)
+        assert code == 2, "only subdividable leaves have room for a child pointer"
+        self.set_code(parent, n, 0)
+        first, m = self.mem, 0
+        for i, v in enumerate(values):
+            if surface:
+                self.buf[self.mem:self.mem + 3] = bytes([v]) + struct.pack("<H", normal)
+                self.mem += 3
+                m |= 1 << (2 * i)
+            else:
+                self.buf[self.mem:self.mem + 7] = bytes([v]) + b"\0" * 6
+                self.mem += 7
+                m |= 2 << (2 * i)
+        self.buf[off + 1:off + 5] = struct.pack(">i", first - off)
+        self.buf[off + 5:off + 7] = struct.pack(">H", m)
+        if any(values) and self.buf[off] == 0:
+            self.buf[off] = max(values)
+        self._touch(off, off + 7)
+        self.end1 = self.mem
+
+    def collapse(self, path, value):
+        """An interior child becomes a subdividable leaf again (the 'fully inside the volume' case, Octree.java:770-784)."""
+        parent, n, off, code = self.walk(path)
+        assert code == 0
+        self.buf[off] = value
+        self.set_code(parent, n, 2)
+        self._touch(off, off + 7)
+
+    def stream(self) -> np.ndarray:
+        return np.frombuffer(bytes(self.buf[:self.mem]), dtype=np.uint8).copy()
+
+    def ranges(self):
+        r = []
+        if self.end0 > self.start0:
+            r.append((self.start0, self.end0))
+        if self.end1 > self.start1:
+            r.append((self.start1, self.end1))
+        return r
+
+    def find_leaf(self, want_code, want_nonzero, rng, min_depth=2, tries=4000):
+        """A random path to a record of the given type (value zero / non-zero as asked)."""
+        for _ in range(tries):
+            off, path, code = 0, [], 0
+            while True:
+                if code != 0 or self.cp(off) == 0:
+                    break
+                n = int(rng.integers(0, 8))
+                off, code = self.child(off, n)
+                path.append(n)
+                if len(path) > 20:
+                    break
+            if code == want_code and (self.buf[off] != 0) == want_nonzero and len(path) >= min_depth:
+                return path
+        raise AssertionError("no such record found")
