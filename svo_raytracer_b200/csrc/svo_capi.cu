@@ -50,6 +50,8 @@ struct svo_ctx {
   uint64_t ndesc_live = 0;     // descriptors reachable after the last whole transcode (the rest up to ndesc: patched-in, or garbage)
   uint8_t *d_stage = nullptr, *d_bitmap = nullptr;  // svo_upload_range: the caller's bytes before they are stored, changed-byte bitmap
   uint64_t stage_cap = 0, nbytes_before_range = 0;
+  void *d_patch_arena = nullptr;  // scratch of the incremental transcode (work lists, counters): allocated once
+  static constexpr size_t kPatchArena = 48u << 20;
   uint64_t patch_stats[4] = {0, 0, 0, 0};  // last svo_upload_range: dirty nodes, re-walked roots, descriptors appended, 1 = fell back to a whole transcode
   uint32_t ndesc = 0, nlevels = 0;
   uint32_t first_word_zero = 1;
@@ -491,6 +493,7 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->d_bitmap) cudaFree(c->d_bitmap);
+  if (c->d_patch_arena) cudaFree(c->d_patch_arena);
   if (c->d_rays) cudaFree(c->d_rays);
   if (c->d_hits) cudaFree(c->d_hits);
   for (int l = 1; l < kLanes; l++)
@@ -635,9 +638,10 @@ int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t 
     SVO_CUDA(c, cudaMalloc((void **)&c->d_bitmap, cap / 8 + 16));
     c->stage_cap = cap;
   }
+  if (!c->d_patch_arena) SVO_CUDA(c, cudaMalloc(&c->d_patch_arena, svo_ctx::kPatchArena));
   SVO_CUDA(c, cudaMemcpyAsync(c->d_stage, nodes + start, len, cudaMemcpyHostToDevice, c->stream));
   uint64_t span[2] = {0, 0};
-  SVO_CUDA(c, gpu_diff_apply(c->d_raw, c->d_stage, start, end, old_nbytes, c->d_bitmap, span, c->stream));
+  SVO_CUDA(c, gpu_diff_apply(c->d_raw, c->d_stage, start, end, old_nbytes, c->d_bitmap, span, c->d_patch_arena, svo_ctx::kPatchArena, c->stream));
   c->launches++;
   for (int k = 0; k < 4; k++) c->patch_stats[k] = 0;
   if (span[0] >= span[1]) return SVO_OK;  // nothing changed: the descriptors are still right
@@ -646,7 +650,7 @@ int svo_upload_range(svo_ctx *c, const uint8_t *nodes, uint64_t start, uint64_t 
     uint64_t nd = c->ndesc;
     c->have_scene = false;
     SVO_CUDA(c, gpu_patch(c->d_raw, c->nbytes, c->d_bitmap, start, end, span, c->d_desc, c->d_refbase, c->d_meta, c->d_flag, c->desc_cap, &nd,
-                          &c->leaf_box, c->depth_box, &fallback, c->patch_stats, c->stream));
+                          &c->leaf_box, c->depth_box, &fallback, c->patch_stats, c->d_patch_arena, svo_ctx::kPatchArena, c->stream));
     c->launches += 8;
     if (!fallback) {
       c->ndesc = (uint32_t)nd;

@@ -259,6 +259,23 @@ void load_boxes(const uint32_t *hb, CellBox *leaf_box, CellBox *depth_box) {
   for (int d = 0; d < 24; d++) load(depth_box[d], hb + 6 * (d + 1));
 }
 
+// Scratch of the incremental path: a caller-owned arena (no cudaMalloc per edit: each costs more than the whole patch),
+// spilling into fresh allocations only for edits that outgrow it.
+struct Scratch {
+  uint8_t *base;
+  size_t cap, used;
+  dev::Pool pool;
+  template <class T> cudaError_t get(T **p, size_t count) {
+    const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (base && used + bytes <= cap) {
+      *p = (T *)(base + used);
+      used += bytes;
+      return cudaSuccess;
+    }
+    return pool.get(p, count);
+  }
+};
+
 #define GT_CUDA(call)                   \
   do {                                  \
     cudaError_t e_ = (call);            \
@@ -351,8 +368,8 @@ cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, ui
 // Stores fresh[0, end - start) at d_raw[start, end) and records which bytes changed: bitmap has (end - start + 7) / 8 bytes,
 // span[0..1] = [first changed byte, last changed byte + 1) (span[0] > span[1]: nothing changed).
 cudaError_t gpu_diff_apply(uint8_t *d_raw, const uint8_t *d_fresh, uint64_t start, uint64_t end, uint64_t old_nbytes, uint8_t *d_bitmap,
-                           uint64_t span[2], cudaStream_t stream) {
-  dev::Pool pool;
+                           uint64_t span[2], void *arena, size_t arena_bytes, cudaStream_t stream) {
+  Scratch pool = {(uint8_t *)arena, arena_bytes, 0, {}};
   unsigned long long *d_span = nullptr;
   GT_CUDA(pool.get(&d_span, 2));
   const unsigned long long init[2] = {~0ull, 0ull};
@@ -372,12 +389,12 @@ cudaError_t gpu_diff_apply(uint8_t *d_raw, const uint8_t *d_fresh, uint64_t star
 // transcode.  stats[0] dirty nodes, [1] roots, [2] descriptors appended.
 cudaError_t gpu_patch(const uint8_t *d_raw, uint64_t nbytes, const uint8_t *d_bitmap, uint64_t start, uint64_t end, const uint64_t span[2],
                       uint2 *desc, uint32_t *refbase, uint2 *meta, uint8_t *flag, uint64_t cap, uint64_t *ndesc, CellBox *leaf_box,
-                      CellBox *depth_box, bool *fallback, uint64_t stats[3], cudaStream_t stream) {
+                      CellBox *depth_box, bool *fallback, uint64_t stats[3], void *arena, size_t arena_bytes, cudaStream_t stream) {
   *fallback = false;
   stats[0] = stats[1] = stats[2] = 0;
   const uint32_t nd = (uint32_t)*ndesc;
   if (span[0] >= span[1] || nd == 0) return cudaSuccess;
-  dev::Pool pool;
+  Scratch pool = {(uint8_t *)arena, arena_bytes, 0, {}};
   const uint32_t list_cap = 1u << 20;
   uint32_t *list = nullptr, *counters = nullptr, *root_index = nullptr, *bounds = nullptr;
   Work *roots = nullptr;
@@ -451,7 +468,7 @@ cudaError_t gpu_patch(const uint8_t *d_raw, uint64_t nbytes, const uint8_t *d_bi
     cur = nxt;
     cur_depth = nxt_depth;
     n = total;
-    if (pool.n > 240) { *fallback = true; return cudaSuccess; }  // (cannot happen: at most 24 levels x 4 blocks)
+    if (pool.pool.n > 240) { *fallback = true; return cudaSuccess; }  // (cannot happen: at most 24 levels x 4 blocks)
   }
   GT_CUDA(dev::copy(hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, stream));
   GT_CUDA(dev::sync(stream));

@@ -96,10 +96,10 @@ cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, ui
                           uint32_t *nlevels, CellBox *leaf_box, CellBox *depth_box, bool *overflow, cudaStream_t stream);
 // incremental transcode (svo_upload_range): store + diff a byte range, then re-walk only the subtrees the changed bytes touch
 cudaError_t gpu_diff_apply(uint8_t *d_raw, const uint8_t *d_fresh, uint64_t start, uint64_t end, uint64_t old_nbytes, uint8_t *d_bitmap,
-                           uint64_t span[2], cudaStream_t stream);
+                           uint64_t span[2], void *arena, size_t arena_bytes, cudaStream_t stream);
 cudaError_t gpu_patch(const uint8_t *d_raw, uint64_t nbytes, const uint8_t *d_bitmap, uint64_t start, uint64_t end, const uint64_t span[2],
                       uint2 *desc, uint32_t *refbase, uint2 *meta, uint8_t *flag, uint64_t cap, uint64_t *ndesc, CellBox *leaf_box,
-                      CellBox *depth_box, bool *fallback, uint64_t stats[3], cudaStream_t stream);
+                      CellBox *depth_box, bool *fallback, uint64_t stats[3], void *arena, size_t arena_bytes, cudaStream_t stream);
 size_t ray_sort_temp_bytes(uint64_t n);
 cudaError_t launch_ray_sort(const void *d_rays, uint64_t n, uint32_t *keys, uint32_t *keys_alt, uint32_t *idx, uint32_t *order_out,
                             void *temp, size_t temp_bytes, cudaStream_t stream);

@@ -97,6 +97,7 @@ int emu_patch_check(const uint8_t *old_raw, uint64_t old_n, const uint8_t *new_r
   memcpy(raw.data(), old_raw, old_n);
   uint64_t nbytes = old_n;
   simt::g_os_threads = nthreads;
+  std::vector<uint8_t> arena(1 << 20);  // odd ranges use the arena (and spill from it), even ones plain allocations
   bool whole = false;
   for (int r = 0; r < nranges; r++) {
     const uint64_t start = ranges[2 * r], end = ranges[2 * r + 1];
@@ -105,11 +106,11 @@ int emu_patch_check(const uint8_t *old_raw, uint64_t old_n, const uint8_t *new_r
     if (end > nbytes) nbytes = end;
     std::vector<uint8_t> bitmap((end - start + 7) / 8 + 16, 0);
     uint64_t span[2];
-    if (gpu_diff_apply(raw.data(), new_raw + start, start, end, before, bitmap.data(), span, nullptr) != cudaSuccess) return 4;
+    if (gpu_diff_apply(raw.data(), new_raw + start, start, end, before, bitmap.data(), span, arena.data(), arena.size(), nullptr) != cudaSuccess) return 4;
     bool fallback = false;
     uint64_t stats[3];
     if (gpu_patch(raw.data(), nbytes, bitmap.data(), start, end, span, desc.data(), ref.data(), meta.data(), flag.data(), cap, &nd, &lb, db, &fallback,
-                  stats, nullptr) != cudaSuccess)
+                  stats, r % 2 ? arena.data() : nullptr, r % 2 ? arena.size() : 0, nullptr) != cudaSuccess)
       return 5;
     out[1] += stats[0]; out[2] += stats[1]; out[3] += stats[2];
     if (fallback) { out[4]++; whole = true; break; }
