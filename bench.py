@@ -77,7 +77,7 @@ def parse():
     ap.add_argument("--accumulate", type=int, default=0, help="1: progressive running mean (svo_frame.flags bit 0), frameNumber = step + 1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..4; 0 = 2 on one GPU, 4 in the tile partition)")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..6; 0 = 2 on one GPU, 4 in the tile partition)")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
@@ -426,7 +426,7 @@ def main():
     total = a.warmup + a.steps
     # frames in flight per GPU: a frame's kernel ends with the critical path of its longest rays (~0.1 ms whatever share of the
     # frame the GPU renders); the next frames' tiles fill the SMs meanwhile (lanes = stream + plane set each)
-    LANES = max(1, min(4, a.lanes if a.lanes > 0 else (4 if tiles else 2)))
+    LANES = max(1, min(6, a.lanes if a.lanes > 0 else (4 if tiles else 2)))
     if a.accumulate:
         LANES = 1  # a running mean lives in ONE plane set
     PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
@@ -436,7 +436,9 @@ def main():
         frames = [frame_for(s) for s in range(total + 3)]
         drain = lambda: None
         if a.fence == "nccl":
-            ctx.set_stream(torch.cuda.current_stream().cuda_stream)  # the all-reduce runs on torch's stream
+            nccl_stream = torch.cuda.Stream()  # (torch's default stream is handle 0 = "the context's own stream" to svo_set_stream)
+            torch.cuda.set_stream(nccl_stream)
+            ctx.set_stream(nccl_stream.cuda_stream)  # the all-reduce runs on torch's stream
             handles = [ctx.ipc_export(p) for p in PL] if rank == 0 else [None, None]
             dist.broadcast_object_list(handles, src=0)
             if rank != 0:
@@ -479,10 +481,12 @@ def main():
             # Frame k lives on lane k % LANES (stream + plane set): the kernels of the next frames start while frame k's last tiles drain.
             def finish(j, consume):
                 ctx.select_lane(j % LANES)
+                if consume is None:  # device-resident loop: "every GPU has stored frame j" -> "frame j consumed" in one launch
+                    ctx.fence_wait_signal((j // LANES + 1) * world_size, 2 + (j % LANES), peer_fences, 0)
+                    return
                 ctx.fence_wait((j // LANES + 1) * world_size, slot=2 + (j % LANES))  # every GPU has stored its bands of frame j
-                if consume is not None:
-                    bind(j)
-                    consume()
+                bind(j)
+                consume()
                 ctx.fence_signal(peer_fences, slot=0)  # frame j consumed: its plane set may be overwritten
 
             def render_step(s, consume=None, release=False):

@@ -78,7 +78,7 @@ enum svo_plane {
   SVO_PLANE_RADIANCE = 6,    /* new: finalcolor before the rgba8 store, float4 */
   SVO_PLANE_BACK = 0x100     /* OR-ed to COLOR_RGBA8 / DEPTH in svo_device_ptr and svo_ipc_export: the second set
                               * (svo_swap_buffers, lane 1); without it they name the first set.  In general
-                              * plane | (lane << 8) names the set of lane 1..3 (svo_select_lane) */
+                              * plane | (lane << 8) names the set of lane 1..5 (svo_select_lane) */
 };
 
 enum svo_option {
@@ -180,11 +180,11 @@ int svo_beam(svo_ctx *ctx, const svo_frame *frame);
  * svotrace.comp:616-619) and with SVO_OPT_AUX_PLANES. */
 int svo_beam_conservative(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
-/* Four lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
- * `lane` (0..3) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
+/* Six lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
+ * `lane` (0..5) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
  * Work on different lanes may overlap on the GPU: rendering frame k+1 on the other lane lets its first tiles fill the SMs
  * that frame k's last, longest tiles leave idle (measured: a 1080p frame carries ~0.13 ms of such tail -- the critical
- * path of its longest rays -- whatever share of the frame a GPU renders, so the 8-GPU tile partition keeps 4 frames in
+ * path of its longest rays -- whatever share of the frame a GPU renders, so the 8-GPU tile partition keeps several frames in
  * flight).  Frames on one lane stay ordered; svo_sync, svo_timer_*, uploads, the beam passes and svo_cast order both lanes.  svo_swap_buffers is
  * svo_select_lane(other) + the wait for that set's last read-back.  With a caller-owned stream (svo_set_stream), with
  * SVO_OPT_AUX_PLANES or with a kernel variant whose workspace exists once (1, 2, 15, 16) both lanes share one stream. */
@@ -236,6 +236,9 @@ int svo_ipc_close(svo_ctx *ctx, void *device_ptr);
 int svo_fence_export(svo_ctx *ctx, uint8_t handle[SVO_IPC_HANDLE_BYTES]);
 int svo_fence_signal(svo_ctx *ctx, void *const *fence_ptrs, int n, int slot);
 int svo_fence_wait(svo_ctx *ctx, int slot, uint32_t target);
+/* svo_fence_wait(slot, target) followed by svo_fence_signal(fence_ptrs, n, signal_slot) in ONE launch: what the frame's
+ * owner runs per frame in the device-resident loop ("every GPU has stored frame k" -> "frame k consumed"). */
+int svo_fence_wait_signal(svo_ctx *ctx, int slot, uint32_t target, void *const *fence_ptrs, int n, int signal_slot);
 int svo_fence_reset(svo_ctx *ctx);
 
 /* -- ray streams (new): n independent intersectOctree calls.

@@ -85,6 +85,7 @@ SYMBOLS = {
     "svo_fence_export": (_i, [_vp, _vp]),
     "svo_fence_signal": (_i, [_vp, C.POINTER(_vp), _i, _i]),
     "svo_fence_wait": (_i, [_vp, _i, C.c_uint32]),
+    "svo_fence_wait_signal": (_i, [_vp, _i, C.c_uint32, C.POINTER(_vp), _i, _i]),
     "svo_fence_reset": (_i, [_vp]),
     "svo_cast": (_i, [_vp, _vp, _u64, _vp, _i]),
     "svo_cast_device": (_i, [_vp, _vp, _u64, _vp, _i]),

@@ -25,7 +25,7 @@ static_assert(sizeof(svo_ray) == 24 && sizeof(svo_hit) == 16, "ray-stream record
 
 static thread_local std::string g_error;
 
-constexpr int kLanes = 4;  // svo_select_lane: streams + colour/depth plane sets that may be in flight together
+constexpr int kLanes = 6;  // svo_select_lane: streams + colour/depth plane sets that may be in flight together
 
 struct svo_ctx {
   int device = 0;
@@ -888,7 +888,7 @@ int svo_swap_buffers(svo_ctx *c) {
 
 int svo_select_lane(svo_ctx *c, int lane) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
-  if (lane < 0 || lane >= kLanes) return fail(c, SVO_ERR_INVALID, "lane must be in [0, 4)");
+  if (lane < 0 || lane >= kLanes) return fail(c, SVO_ERR_INVALID, "lane must be in [0, 6)");
   if (lane == c->lane) return SVO_OK;
   SVO_CUDA(c, cudaSetDevice(c->device));
   int rc = ensure_pipeline(c, lane);
@@ -970,6 +970,19 @@ int svo_fence_wait(svo_ctx *c, int slot, uint32_t target) {
   if (slot < 0 || slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, launch_fence_wait(c->d_fence + 8 * slot, c->d_fence + 7, target, c->stream));
+  c->fence_waits_unchecked = true;
+  c->launches++;
+  return SVO_OK;
+}
+int svo_fence_wait_signal(svo_ctx *c, int slot, uint32_t target, void *const *fence_ptrs, int n, int signal_slot) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (slot < 0 || slot >= 8 || signal_slot < 0 || signal_slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
+  if (n < 1 || n > 16 || !fence_ptrs) return fail(c, SVO_ERR_INVALID, "bad fence list (1..16)");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  FenceList fl;
+  fl.n = n;
+  for (int i = 0; i < 16; i++) fl.p[i] = i < n ? (unsigned int *)fence_ptrs[i] + 8 * signal_slot : nullptr;
+  SVO_CUDA(c, launch_fence_wait_signal(c->d_fence + 8 * slot, c->d_fence + 7, target, fl, c->stream));
   c->fence_waits_unchecked = true;
   c->launches++;
   return SVO_OK;

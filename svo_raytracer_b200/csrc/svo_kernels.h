@@ -84,6 +84,7 @@ cudaError_t launch_render_stats(const SceneView &sc, const FrameParams &f, const
                                 unsigned long long *d_counters, cudaStream_t stream, bool executed = false);
 cudaError_t launch_fence_signal(const FenceList &fl, cudaStream_t stream);
 cudaError_t launch_fence_wait(unsigned int *fence, unsigned int *dead, unsigned int target, cudaStream_t stream);
+cudaError_t launch_fence_wait_signal(unsigned int *fence, unsigned int *dead, unsigned int target, const FenceList &fl, cudaStream_t stream);
 cudaError_t launch_gather_probe(const void *buf, uint64_t words, int loads, int blocks, uint32_t *sink, cudaStream_t stream);
 cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d_rays, const uint32_t *d_order, uint64_t n,
                         void *d_out, int maxDepth, cudaStream_t stream);

@@ -266,6 +266,11 @@ class SvoContext:
         """Enqueue: wait until slot `slot` of this context's own counter reaches `target` (modulo 2^32)."""
         self._check(self._lib.svo_fence_wait(self._h, slot, target & 0xFFFFFFFF))
 
+    def fence_wait_signal(self, target: int, slot: int, fence_ptrs: Sequence[int], signal_slot: int = 0):
+        """fence_wait(target, slot) then fence_signal(fence_ptrs, signal_slot) in one launch."""
+        arr = (C.c_void_p * len(fence_ptrs))(*[C.c_void_p(p) for p in fence_ptrs])
+        self._check(self._lib.svo_fence_wait_signal(self._h, int(slot), target & 0xFFFFFFFF, arr, len(fence_ptrs), int(signal_slot)))
+
     def fence_reset(self):
         self._check(self._lib.svo_fence_reset(self._h))
 

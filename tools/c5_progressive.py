@@ -19,7 +19,7 @@ ap.add_argument("--size", type=int, default=8192)
 ap.add_argument("--res", type=int, default=8192)
 ap.add_argument("--spp", type=int, default=64)
 ap.add_argument("--camera", default="B")
-ap.add_argument("--check-rows", type=int, default=8)
+ap.add_argument("--check-rows", type=int, default=16)
 a = ap.parse_args()
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -34,7 +34,9 @@ ctx.build_terrain_device(hm, mm, a.size, min(a.size, 1024))
 # the context draws into torch-owned planes so that NCCL can reduce them
 color = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
 depthp = torch.zeros((H, W), dtype=torch.float32, device="cuda")
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()  # (torch's default stream is handle 0, which svo_set_stream reads as "the context's own stream")
+torch.cuda.set_stream(stream)
+ctx.set_stream(stream.cuda_stream)
 ctx.bind_plane(L.PLANE_COLOR_RGBA8, color.data_ptr())
 ctx.bind_plane(L.PLANE_DEPTH, depthp.data_ptr())
 frames = [svo.camera_frame(a.camera, frame_number=s + 1, render_mode=0, max_depth=depth, flags=1) for s in range(a.spp)]
@@ -70,7 +72,7 @@ if rank == 0:
     if a.check_rows > 0:
         from oracle import oracle as O
         nodes = ctx.download()
-        y0 = (H // 2) // 8 * 8
+        y0 = ((H // 2) // 8 + 3) * 8  # bands 515, 516: ranks 3 and 4 of 8 -- pixels that crossed NVLink in the gather
         y1 = y0 + a.check_rows
         pos, l1, l2, r1, r2 = svo.CAMERAS[a.camera]
         prev = np.zeros((H, W, 4), np.uint8)
