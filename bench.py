@@ -77,7 +77,9 @@ def parse():
     ap.add_argument("--accumulate", type=int, default=0, help="1: progressive running mean (svo_frame.flags bit 0), frameNumber = step + 1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..6; 0 = 2 on one GPU, 4 in the tile partition)")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..6; 0 = 2 on one GPU, 6 in the tile partition)")
+    ap.add_argument("--beam", type=int, default=-1, help="conservative beam pre-pass per frame (svo_beam_conservative + SVO_FRAME_BEAM_FLOOR; the frame does not "
+                                                         "change): -1 = on for one GPU / replica mode in render modes 0 and 3, off in the tile partition")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
@@ -417,16 +419,20 @@ def main():
     info = ctx.scene_info()
 
 
+    tiles = world_size > 1 and partition == "tiles"
+    BEAM = (a.beam == 1 or (a.beam < 0 and not tiles)) and MODE in (0, 3) and not a.accumulate
+
     def frame_for(s):
         fp = frame_params(s, a.size, a)
+        if BEAM:
+            fp["flags"] |= 2  # SVO_FRAME_BEAM_FLOOR
         return svo.make_frame(fp["cam_pos"], fp["l1"], fp["l2"], fp["r1"], fp["r2"], frame_number=fp["frame_number"], render_mode=fp["render_mode"],
                               max_depth=fp["max_depth"], casts=fp["casts"], cone_depth=fp["cone_depth"], mirror_value=fp["mirror_value"], flags=fp["flags"])
 
-    tiles = world_size > 1 and partition == "tiles"
     total = a.warmup + a.steps
     # frames in flight per GPU: a frame's kernel ends with the critical path of its longest rays (~0.1 ms whatever share of the
     # frame the GPU renders); the next frames' tiles fill the SMs meanwhile (lanes = stream + plane set each)
-    LANES = max(1, min(6, a.lanes if a.lanes > 0 else (4 if tiles else 2)))
+    LANES = max(1, min(6, a.lanes if a.lanes > 0 else (6 if tiles else 2)))
     if a.accumulate:
         LANES = 1  # a running mean lives in ONE plane set
     PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
@@ -523,6 +529,8 @@ def main():
         def render_step(s, consume=None, release=False):
             if LANES > 1:
                 ctx.select_lane(s % LANES)  # consecutive frames on alternating lanes (stream + plane set): frame s+1 may start while frame s's last tiles drain
+            if BEAM:
+                ctx.beam_conservative(frames[s])  # per-block lower bounds on the primary hit distance (this lane's beam plane)
             ctx.render(frames[s])
             if consume is not None:
                 consume()
@@ -532,8 +540,10 @@ def main():
     per_cam, per_cam_exec = {}, {}
     for ci, cam in enumerate(CAM_CYCLE):
         f = frame_for(ci)
-        f.flags = 0
+        f.flags = 2 if BEAM else 0
         per_cam[cam] = ctx.render_stats(f)
+        if BEAM:
+            ctx.beam_conservative(f)
         per_cam_exec[cam] = ctx.render_stats_executed(f)
     rays_per_step = [per_cam[CAM_CYCLE[s % 3]]["casts"] for s in range(total)]
     alg_bytes_per_step = [per_cam[CAM_CYCLE[s % 3]]["record_bytes"] + 8 * W * H for s in range(total)]
@@ -609,6 +619,8 @@ def main():
         host_sets = ((color_h, depth_h), (color_h2, depth_h2))
 
         def e2e_step_pipelined(s):
+            if BEAM:
+                ctx.beam_conservative(frames[s])
             ctx.render(frames[s])
             ch, dh = host_sets[s & 1]
             ctx.read_planes_async(ch.data_ptr(), dh.data_ptr())
@@ -781,7 +793,7 @@ def main():
         "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_of(a, world_size, tree_bytes, partition),
-        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "descriptors": info["descriptors"], "levels": info["levels"],
+        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "conservative_beam_prepass": bool(BEAM), "descriptors": info["descriptors"], "levels": info["levels"],
                          "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
                          "world": {"how": world_how, "seconds": round(build_s, 2), "maps_s": round(maps_s, 2)}, "build_and_transcode_s": round(upload_s, 3),
                          "units": ("one frame per step, interleaved %d-row bands per rank, peers store into rank 0's planes over NVLink, "

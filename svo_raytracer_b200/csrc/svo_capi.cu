@@ -81,7 +81,8 @@ struct svo_ctx {
   std::vector<IpcMap> ipc_maps;  // peer blocks opened by svo_ipc_import
   WaveWorkspace ws{};  // wavefront variant, allocated on first use
   void *ws_block = nullptr;
-  float *d_beam_lattice = nullptr;  // conservative beam pre-pass: (W/4+1) x (H/4+1) lattice-ray distances
+  float *d_beam_lattice[kLanes] = {nullptr, nullptr, nullptr, nullptr};  // conservative beam pre-pass: (W/4+1) x (H/4+1) lattice-ray distances, per lane
+  float *lane_beam[kLanes] = {nullptr, nullptr, nullptr, nullptr};       // beam planes of lanes 1.. (lane 0: own[SVO_PLANE_BEAM]); allocated on first use
   void *split_block = nullptr;  // variant 15: record queue
   SplitQueue split = {};
   int ctas_per_sm = 8;
@@ -157,6 +158,7 @@ size_t plane_elems(const svo_ctx *c, int plane) {
 void *plane_ptr(const svo_ctx *c, int plane) {
   if (c->bound[plane]) return c->bound[plane];
   if (plane <= SVO_PLANE_DEPTH && c->render_set >= 1 && c->back[c->render_set][plane]) return c->back[c->render_set][plane];
+  if (plane == SVO_PLANE_BEAM && c->render_set >= 1 && c->lane_beam[c->render_set]) return c->lane_beam[c->render_set];
   return c->own[plane];
 }
 
@@ -509,7 +511,10 @@ void svo_destroy(svo_ctx *c) {
   if (c->d_fence) cudaFree(c->d_fence);
   if (c->ws_block) cudaFree(c->ws_block);
   if (c->split_block) cudaFree(c->split_block);
-  if (c->d_beam_lattice) cudaFree(c->d_beam_lattice);
+  for (int l = 0; l < kLanes; l++) {
+    if (c->d_beam_lattice[l]) cudaFree(c->d_beam_lattice[l]);
+    if (c->lane_beam[l]) cudaFree(c->lane_beam[l]);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -799,11 +804,18 @@ int svo_beam_conservative(svo_ctx *c, const svo_frame *frame) {
   int rc = check_frame(c, frame);
   if (rc) return rc;
   SVO_CUDA(c, cudaSetDevice(c->device));
-  if (!c->d_beam_lattice) SVO_CUDA(c, cudaMalloc((void **)&c->d_beam_lattice, (size_t)(c->W / 4 + 1) * (size_t)(c->H / 4 + 1) * sizeof(float) + 16));
-  SVO_CUDA(c, join_lanes(c));  // one beam plane and one lattice scratch per context
+  // every lane has its own lattice scratch and beam plane: the pre-pass of frame k+1 may run while frame k is still being drawn
+  const int l = c->render_set;
+  const size_t lat_bytes = (size_t)(c->W / 4 + 1) * (size_t)(c->H / 4 + 1) * sizeof(float) + 16;
+  if (!c->d_beam_lattice[l]) SVO_CUDA(c, cudaMalloc((void **)&c->d_beam_lattice[l], lat_bytes));
+  if (l >= 1 && !c->lane_beam[l]) {
+    const size_t bytes = plane_elems(c, SVO_PLANE_BEAM) * sizeof(float);
+    SVO_CUDA(c, cudaMalloc((void **)&c->lane_beam[l], bytes ? bytes : 16));
+    SVO_CUDA(c, cudaMemsetAsync(c->lane_beam[l], 0, bytes, c->stream));
+  }
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
-  SVO_CUDA(c, launch_beam_conservative(scene_view(c), fp, c->d_beam_lattice, (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
+  SVO_CUDA(c, launch_beam_conservative(scene_view(c), fp, c->d_beam_lattice[l], (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
   c->launches += 2;
   return SVO_OK;
 }

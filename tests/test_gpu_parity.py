@@ -299,6 +299,17 @@ def test_two_lanes_overlap_frames_without_mixing_them(svo, oracle, terrain512):
                 c.select_lane(lane)
                 assert np.array_equal(c.read_color_rgba8(), want[i]["rgba8"]), (kernel, lane)
                 assert np.array_equal(c.read_depth().view(np.uint32), want[i]["depth"].view(np.uint32)), (kernel, lane)
+            # three lanes, each frame preceded by its own conservative beam pre-pass (per-lane beam planes): nothing mixes
+            for i, cam in enumerate(cams[:6]):
+                c.select_lane(i % 3)
+                fb = svo.camera_frame(cam, frame_number=i + 1, render_mode=0, flags=2)
+                c.beam_conservative(fb)
+                c.render(fb)
+            for lane, i in ((0, 3), (1, 4), (2, 5)):
+                c.select_lane(lane)
+                assert np.array_equal(c.read_color_rgba8(), want[i]["rgba8"]), (kernel, "beam", lane)
+                assert np.array_equal(c.read_depth().view(np.uint32), want[i]["depth"].view(np.uint32)), (kernel, "beam", lane)
+            c.select_lane(0)
             # pipelined read-back: every frame lands in its host buffer
             import torch
             bufs = [(torch.empty((H, W, 4), dtype=torch.uint8).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory()) for _ in cams]
