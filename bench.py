@@ -77,7 +77,7 @@ def parse():
     ap.add_argument("--accumulate", type=int, default=0, help="1: progressive running mean (svo_frame.flags bit 0), frameNumber = step + 1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..6; 0 = 2 on one GPU, 6 in the tile partition)")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..6; 0 = 3 on one GPU, 6 in the tile partition)")
     ap.add_argument("--beam", type=int, default=-1, help="conservative beam pre-pass per frame (svo_beam_conservative + SVO_FRAME_BEAM_FLOOR; the frame does not "
                                                          "change): -1 = on for one GPU / replica mode in render modes 0 and 3, off in the tile partition")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
@@ -432,7 +432,7 @@ def main():
     total = a.warmup + a.steps
     # frames in flight per GPU: a frame's kernel ends with the critical path of its longest rays (~0.1 ms whatever share of the
     # frame the GPU renders); the next frames' tiles fill the SMs meanwhile (lanes = stream + plane set each)
-    LANES = max(1, min(6, a.lanes if a.lanes > 0 else (6 if tiles else 2)))
+    LANES = max(1, min(6, a.lanes if a.lanes > 0 else (6 if tiles else 3)))
     if a.accumulate:
         LANES = 1  # a running mean lives in ONE plane set
     PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
@@ -628,6 +628,60 @@ def main():
         e2e_s = timed(e2e_step_pipelined, ctx.read_wait)
     e2e_value = all_rays / e2e_s / 1e6
 
+    # ---- tiles: end to end with the frame assembled in HOST memory ----------------------------------------------------
+    # Through GPU 0 (above) every frame crosses ONE PCIe link (16.6 MB per 1080p frame: ~0.4 ms, more than the 8-GPU render
+    # time).  Here every rank renders its bands into its own planes and copies them over ITS link straight to their place in
+    # frame buffers that live in host memory shared by the ranks (pinned by each): svo_read_interleaved_async.
+    e2e_host_value, got_host = None, {}
+    if tiles and a.fence == "p2p":
+        for plane in PL:
+            ctx.bind_plane(plane, None)
+        set_bytes = W * H * 8
+        shm_path = "/dev/shm/svo_bench_frames_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            with open(shm_path, "wb") as fh:
+                fh.truncate(LANES * set_bytes)
+        dist.barrier()
+        shm = torch.from_file(shm_path, shared=True, size=LANES * set_bytes, dtype=torch.uint8)
+        rc = torch.cuda.cudart().cudaHostRegister(shm.data_ptr(), shm.numel(), 0)
+        ok = torch.tensor([1 if int(rc) == 0 else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            base = shm.data_ptr()
+            cptr = [base + l * set_bytes for l in range(LANES)]
+            dptr = [base + l * set_bytes + W * H * 4 for l in range(LANES)]
+            hstate = {"k": 0}
+
+            def e2e_host_step(s):
+                l = hstate["k"] % LANES
+                hstate["k"] += 1
+                ctx.select_lane(l)  # (waits, on the device, until this lane's previous copy has left its planes)
+                ctx.render_interleaved(frames[s], rank, world_size)
+                ctx.read_interleaved_async(rank, world_size, cptr[l], dptr[l])
+            e2e_host_s = timed(e2e_host_step, ctx.read_wait)
+            e2e_host_value = all_rays / e2e_host_s / 1e6
+            for ci in range(len(set(CAM_CYCLE))):  # the assembled host frames, for the parity check
+                s = a.warmup + ci
+                if s >= total:
+                    break
+                ctx.select_lane(0)
+                ctx.render_interleaved(frames[s], rank, world_size)
+                ctx.read_interleaved_async(rank, world_size, cptr[0], dptr[0])
+                ctx.read_wait()
+                barrier()
+                if rank == 0:
+                    hv = shm[:set_bytes].numpy()
+                    got_host[s] = (hv[:W * H * 4].reshape(H, W, 4).copy(), hv[W * H * 4:].view(np.float32).reshape(H, W).copy())
+                barrier()
+            torch.cuda.cudart().cudaHostUnregister(shm.data_ptr())
+        del shm
+        barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
+
     # ---- the frames just timed, kept for the parity check (outside the timed region) ------------------------------
     got_frames = {}
     if not a.accumulate:
@@ -719,8 +773,14 @@ def main():
             bad_c += int((gc != wc).any(axis=-1).sum())
             bad_d += int((gd.view(np.uint32) != wd.view(np.uint32)).sum())
             px += W * H
-        parity = {"against": "the same frames rendered by GPU 0 alone", "frames": len(got_frames), "pixels": px, "rgba8_mismatch": bad_c,
-                  "depth_mismatch": bad_d}
+        for s, (gc, gd) in got_host.items():  # ... and the frames assembled in host memory from every rank's own read-back
+            ctx.render(frames[s])
+            wc, wd = ctx.read_color_rgba8(), ctx.read_depth()
+            bad_c += int((gc != wc).any(axis=-1).sum())
+            bad_d += int((gd.view(np.uint32) != wd.view(np.uint32)).sum())
+            px += W * H
+        parity = {"against": "the same frames rendered by GPU 0 alone", "frames": len(got_frames) + len(got_host), "pixels": px, "rgba8_mismatch": bad_c,
+                  "depth_mismatch": bad_d, "assembled": "in GPU 0's planes over NVLink (%d frames) and in shared host memory (%d frames)" % (len(got_frames), len(got_host))}
 
     # ---- roofline ----------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -800,11 +860,16 @@ def main():
                                    "frame-complete fence = %s" % (a.band_rows, "remote atomics over NVLink, bumped by the render kernel's last CTA" if a.fence == "p2p" else "NCCL all-reduce")) if tiles else
                                   ("rank r renders progressive sample s*N+r of each view; no data-path exchange" if world_size > 1 else "one GPU renders every frame")},
         "clocks": clk, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
-                "ms_per_step": e2e_s / a.steps * 1e3,
+        "e2e": {"value": e2e_host_value if e2e_host_value is not None else e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
+                "ms_per_step": (all_rays / (e2e_host_value * 1e6) if e2e_host_value is not None else e2e_s) / a.steps * 1e3,
                 "how": "svo_render + svo_read_planes_async + svo_swap_buffers per frame (read-back of frame s overlaps the render of "
                        "frame s+1), svo_read_wait inside the timed region" if not tiles else
-                       "rank 0 reads the assembled frame back after every frame-complete fence (16.6 MB per frame over GPU 0's PCIe link bounds it)",
+                       ("every rank renders its bands and copies them over its own PCIe link to their place in frame buffers in host memory shared by "
+                        "the ranks (svo_render_interleaved + svo_read_interleaved_async, %d frames in flight); every frame is in host memory when the "
+                        "clock stops" % LANES if e2e_host_value is not None else
+                        "rank 0 reads the assembled frame back after every frame-complete fence"),
+                "via_gpu0_value": e2e_value if tiles else None,
+                "via_gpu0_note": "frame gathered in GPU 0's planes over NVLink, then read back over GPU 0's PCIe link alone (16.6 MB per 1080p frame bounds it)" if tiles else None,
                 "blocking_value": all_rays / e2e_sync_s / 1e6},
         "roofline": roofline,
     }

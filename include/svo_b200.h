@@ -208,6 +208,12 @@ int svo_read_radiance_f32(svo_ctx *ctx, float *dst);
  * blocks the host until all enqueued copies have landed.  Per frame: svo_render; svo_read_planes_async;
  * svo_swap_buffers -- frame s+1 renders while frame s crosses PCIe. */
 int svo_read_planes_async(svo_ctx *ctx, uint8_t *rgba8_dst, float *depth_dst);
+/* The multi-GPU variant of svo_read_planes_async: copies the rows of bands part, part + parts, ... (what
+ * svo_render_interleaved(part, parts) drew into this context's current set) into FULL-FRAME host buffers, each row at its
+ * place in the frame -- one strided copy per plane.  With the frame buffers in host memory shared by the ranks (pinned by
+ * each), every GPU delivers its bands over its own PCIe link and the frame assembles in host memory: the read-back of
+ * an N-GPU frame is not bounded by GPU 0's link (16.6 MB per 1080p frame).  Completion: svo_read_wait. */
+int svo_read_interleaved_async(svo_ctx *ctx, int part, int parts, uint8_t *rgba8_frame, float *depth_frame);
 int svo_swap_buffers(svo_ctx *ctx);
 int svo_read_wait(svo_ctx *ctx);
 /* device address of a plane (for CUDA/NCCL/peer interop); NULL if absent */

@@ -74,6 +74,7 @@ SYMBOLS = {
     "svo_read_primary_t": (_i, [_vp, _vp]),
     "svo_read_radiance_f32": (_i, [_vp, _vp]),
     "svo_read_planes_async": (_i, [_vp, _vp, _vp]),
+    "svo_read_interleaved_async": (_i, [_vp, _i, _i, _vp, _vp]),
     "svo_swap_buffers": (_i, [_vp]),
     "svo_select_lane": (_i, [_vp, _i]),
     "svo_read_wait": (_i, [_vp]),

@@ -885,6 +885,37 @@ int svo_read_planes_async(svo_ctx *c, uint8_t *rgba8_dst, float *depth_dst) {
   return SVO_OK;
 }
 
+// The rows of bands part, part + parts, ... (what svo_render_interleaved(part, parts) draws) from the current lane's
+// colour / depth set into FULL-FRAME host buffers, at their place in the frame: one strided copy per plane.
+int svo_read_interleaved_async(svo_ctx *c, int part, int parts, uint8_t *rgba8_frame, float *depth_frame) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (parts < 1 || part < 0 || part >= parts) return fail(c, SVO_ERR_INVALID, "part must be in [0, parts)");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure_pipeline(c, 0);
+  if (rc) return rc;
+  SVO_CUDA(c, cudaEventRecord(c->ev_rendered, c->stream));
+  SVO_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered, 0));
+  const int band = c->opt_band_rows, nbands = (c->H + band - 1) / band;
+  const int mine = nbands > part ? (nbands - part + parts - 1) / parts : 0;  // bands part, part + parts, ...
+  for (int p = 0; p < 2; p++) {
+    char *dst = p == 0 ? (char *)rgba8_frame : (char *)depth_frame;
+    if (!dst || mine == 0) continue;
+    const char *src = (const char *)plane_ptr(c, p);
+    const size_t row = (size_t)c->W * 4u, band_bytes = row * (size_t)band, pitch = band_bytes * (size_t)parts, off = band_bytes * (size_t)part;
+    // all of this part's bands but the last are whole; the last one may be cut by the image's bottom edge
+    const int last = part + (mine - 1) * parts;
+    const int last_rows = (last + 1) * band <= c->H ? band : c->H - last * band;
+    const int whole = last_rows == band ? mine : mine - 1;
+    if (whole > 0) SVO_CUDA(c, cudaMemcpy2DAsync(dst + off, pitch, src + off, pitch, band_bytes, (size_t)whole, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (whole < mine) {
+      const size_t o = band_bytes * (size_t)last;
+      SVO_CUDA(c, cudaMemcpyAsync(dst + o, src + o, row * (size_t)last_rows, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+  }
+  SVO_CUDA(c, cudaEventRecord(c->ev_copied[c->render_set], c->copy_stream));
+  return SVO_OK;
+}
+
 int svo_swap_buffers(svo_ctx *c) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));

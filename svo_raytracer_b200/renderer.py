@@ -222,6 +222,10 @@ class SvoContext:
         """Enqueue the read-back of the current colour/depth set into (pinned) host memory; see svo_read_planes_async."""
         self._check(self._lib.svo_read_planes_async(self._h, C.c_void_p(rgba8_ptr or 0), C.c_void_p(depth_ptr or 0)))
 
+    def read_interleaved_async(self, part: int, parts: int, rgba8_ptr: int, depth_ptr: int):
+        """This rank's bands of the current set into full-frame host buffers (svo_read_interleaved_async)."""
+        self._check(self._lib.svo_read_interleaved_async(self._h, int(part), int(parts), C.c_void_p(rgba8_ptr), C.c_void_p(depth_ptr)))
+
     def swap_buffers(self):
         self._check(self._lib.svo_swap_buffers(self._h))
 
