@@ -420,7 +420,7 @@ def main():
 
 
     tiles = world_size > 1 and partition == "tiles"
-    BEAM = (a.beam == 1 or (a.beam < 0 and not tiles)) and MODE in (0, 3) and not a.accumulate
+    BEAM = (a.beam == 1 or (a.beam < 0 and not tiles)) and MODE in (0, 3) and not a.accumulate and not (tiles and a.fence == "nccl")
 
     def frame_for(s):
         fp = frame_params(s, a.size, a)
@@ -499,6 +499,8 @@ def main():
                 k = state["k"]
                 state["k"] = k + 1
                 ctx.select_lane(k % LANES)
+                if BEAM:
+                    ctx.beam_conservative(frames[s])  # every rank computes the (small) beam plane of the whole frame for itself
                 if rank == 0:
                     bind(k)
                     ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=2 + (k % LANES))
@@ -615,16 +617,16 @@ def main():
         # the public pipelined path: two colour/depth sets on the device and two pinned sets on the host, frame s+1
         # renders while frame s crosses PCIe (svo_read_planes_async / svo_swap_buffers); every frame still lands in
         # host memory inside the timed region (svo_read_wait before the clock stops)
-        color_h2, depth_h2 = torch.empty_like(color_h).pin_memory(), torch.empty_like(depth_h).pin_memory()
-        host_sets = ((color_h, depth_h), (color_h2, depth_h2))
+        host_sets = [(color_h, depth_h)] + [(torch.empty_like(color_h).pin_memory(), torch.empty_like(depth_h).pin_memory()) for _ in range(max(LANES, 2) - 1)]
 
         def e2e_step_pipelined(s):
+            l = s % len(host_sets)
+            ctx.select_lane(l)  # (waits, on the device, until this lane's previous read-back has left its planes)
             if BEAM:
                 ctx.beam_conservative(frames[s])
             ctx.render(frames[s])
-            ch, dh = host_sets[s & 1]
+            ch, dh = host_sets[l]
             ctx.read_planes_async(ch.data_ptr(), dh.data_ptr())
-            ctx.swap_buffers()
         e2e_s = timed(e2e_step_pipelined, ctx.read_wait)
     e2e_value = all_rays / e2e_s / 1e6
 
@@ -656,6 +658,8 @@ def main():
                 l = hstate["k"] % LANES
                 hstate["k"] += 1
                 ctx.select_lane(l)  # (waits, on the device, until this lane's previous copy has left its planes)
+                if BEAM:
+                    ctx.beam_conservative(frames[s])
                 ctx.render_interleaved(frames[s], rank, world_size)
                 ctx.read_interleaved_async(rank, world_size, cptr[l], dptr[l])
             e2e_host_s = timed(e2e_host_step, ctx.read_wait)
@@ -665,6 +669,8 @@ def main():
                 if s >= total:
                     break
                 ctx.select_lane(0)
+                if BEAM:
+                    ctx.beam_conservative(frames[s])
                 ctx.render_interleaved(frames[s], rank, world_size)
                 ctx.read_interleaved_async(rank, world_size, cptr[0], dptr[0])
                 ctx.read_wait()
@@ -701,6 +707,8 @@ def main():
         barrier()
         per_rank = []
         for ci in range(3):  # this rank's share of each camera's frame, alone on its stream (no fences)
+            if BEAM:
+                ctx.beam_conservative(frames[ci])
             ctx.render_interleaved(frames[ci], rank, world_size)
             ctx.sync()
             ctx.timer_begin()
@@ -717,6 +725,8 @@ def main():
             for plane in PL:
                 ctx.bind_plane(plane, None)
             for ci in range(3):
+                if BEAM:
+                    ctx.beam_conservative(frames[ci])
                 ctx.render_interleaved(frames[ci], 0, 1)
                 ctx.sync()
                 ctx.timer_begin()
@@ -767,15 +777,18 @@ def main():
         for plane in PL:
             ctx.bind_plane(plane, None)
         px = bad_c = bad_d = 0
+        def alone(s):  # the whole frame on GPU 0, without the beam floor
+            f = frame_for(s)
+            f.flags = 0
+            ctx.render(f)
+            return ctx.read_color_rgba8(), ctx.read_depth()
         for s, (gc, gd) in got_frames.items():
-            ctx.render(frames[s])
-            wc, wd = ctx.read_color_rgba8(), ctx.read_depth()
+            wc, wd = alone(s)
             bad_c += int((gc != wc).any(axis=-1).sum())
             bad_d += int((gd.view(np.uint32) != wd.view(np.uint32)).sum())
             px += W * H
         for s, (gc, gd) in got_host.items():  # ... and the frames assembled in host memory from every rank's own read-back
-            ctx.render(frames[s])
-            wc, wd = ctx.read_color_rgba8(), ctx.read_depth()
+            wc, wd = alone(s)
             bad_c += int((gc != wc).any(axis=-1).sum())
             bad_d += int((gd.view(np.uint32) != wd.view(np.uint32)).sum())
             px += W * H
@@ -862,8 +875,8 @@ def main():
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_host_value if e2e_host_value is not None else e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": W * H * 8,
                 "ms_per_step": (all_rays / (e2e_host_value * 1e6) if e2e_host_value is not None else e2e_s) / a.steps * 1e3,
-                "how": "svo_render + svo_read_planes_async + svo_swap_buffers per frame (read-back of frame s overlaps the render of "
-                       "frame s+1), svo_read_wait inside the timed region" if not tiles else
+                "how": "svo_select_lane + svo_render + svo_read_planes_async per frame (the read-back of frame s overlaps the render of "
+                       "the next frames), svo_read_wait inside the timed region" if not tiles else
                        ("every rank renders its bands and copies them over its own PCIe link to their place in frame buffers in host memory shared by "
                         "the ranks (svo_render_interleaved + svo_read_interleaved_async, %d frames in flight); every frame is in host memory when the "
                         "clock stops" % LANES if e2e_host_value is not None else
