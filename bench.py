@@ -77,7 +77,7 @@ def parse():
     ap.add_argument("--accumulate", type=int, default=0, help="1: progressive running mean (svo_frame.flags bit 0), frameNumber = step + 1")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..6; 0 = 3 on one GPU, 6 in the tile partition)")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..7; 0 = 3 on one GPU, 6 in the tile partition)")
     ap.add_argument("--beam", type=int, default=-1, help="conservative beam pre-pass per frame (svo_beam_conservative + SVO_FRAME_BEAM_FLOOR; the frame does not "
                                                          "change): -1 = on for one GPU / replica mode in render modes 0 and 3, off in the tile partition")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
@@ -432,7 +432,7 @@ def main():
     total = a.warmup + a.steps
     # frames in flight per GPU: a frame's kernel ends with the critical path of its longest rays (~0.1 ms whatever share of the
     # frame the GPU renders); the next frames' tiles fill the SMs meanwhile (lanes = stream + plane set each)
-    LANES = max(1, min(6, a.lanes if a.lanes > 0 else (6 if tiles else 3)))
+    LANES = max(1, min(7, a.lanes if a.lanes > 0 else (6 if tiles else 3)))
     if a.accumulate:
         LANES = 1  # a running mean lives in ONE plane set
     PL = (L.PLANE_COLOR_RGBA8, L.PLANE_DEPTH)
@@ -462,7 +462,7 @@ def main():
         else:
             # No collective in the data path.  Rank 0 owns LANES colour/depth sets; frame k goes to set k % LANES, so LANES
             # frames are in flight.  Fences are counters in GPU memory bumped by remote atomics over NVLink:
-            # slot 2+(k%LANES) of rank 0's counter = "bands of frame k stored" (complete at (k//LANES+1)*N) -- bumped by the
+            # slot 1+(k%LANES) of rank 0's counter = "bands of frame k stored" (complete at (k//LANES+1)*N) -- bumped by the
             # LAST CTA of each rank's render kernel (svo_render_interleaved_signal: one launch per rank and frame) --
             # slot 0 of every peer's counter = "frames consumed by rank 0".
             handles = [ctx.ipc_export(p | (l << 8)) for l in range(LANES) for p in PL] if rank == 0 else [None] * (2 * LANES)
@@ -488,9 +488,9 @@ def main():
             def finish(j, consume):
                 ctx.select_lane(j % LANES)
                 if consume is None:  # device-resident loop: "every GPU has stored frame j" -> "frame j consumed" in one launch
-                    ctx.fence_wait_signal((j // LANES + 1) * world_size, 2 + (j % LANES), peer_fences, 0)
+                    ctx.fence_wait_signal((j // LANES + 1) * world_size, 1 + (j % LANES), peer_fences, 0)
                     return
-                ctx.fence_wait((j // LANES + 1) * world_size, slot=2 + (j % LANES))  # every GPU has stored its bands of frame j
+                ctx.fence_wait((j // LANES + 1) * world_size, slot=1 + (j % LANES))  # every GPU has stored its bands of frame j
                 bind(j)
                 consume()
                 ctx.fence_signal(peer_fences, slot=0)  # frame j consumed: its plane set may be overwritten
@@ -503,14 +503,14 @@ def main():
                     ctx.beam_conservative(frames[s])  # every rank computes the (small) beam plane of the whole frame for itself
                 if rank == 0:
                     bind(k)
-                    ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=2 + (k % LANES))
+                    ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=1 + (k % LANES))
                     if state["pending"] is not None:
                         finish(*state["pending"])
                     state["pending"] = (k, consume)
                 else:
                     ctx.fence_wait(max(k - LANES + 1, 0), slot=0)  # rank 0 has consumed frames 0..k-LANES: this lane's set is free
                     bind(k)
-                    ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=2 + (k % LANES))
+                    ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=1 + (k % LANES))
 
             def drain():
                 if rank == 0 and state["pending"] is not None:

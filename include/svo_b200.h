@@ -78,7 +78,7 @@ enum svo_plane {
   SVO_PLANE_RADIANCE = 6,    /* new: finalcolor before the rgba8 store, float4 */
   SVO_PLANE_BACK = 0x100     /* OR-ed to COLOR_RGBA8 / DEPTH in svo_device_ptr and svo_ipc_export: the second set
                               * (svo_swap_buffers, lane 1); without it they name the first set.  In general
-                              * plane | (lane << 8) names the set of lane 1..5 (svo_select_lane) */
+                              * plane | (lane << 8) names the set of lane 1..6 (svo_select_lane) */
 };
 
 enum svo_option {
@@ -180,8 +180,8 @@ int svo_beam(svo_ctx *ctx, const svo_frame *frame);
  * svotrace.comp:616-619) and with SVO_OPT_AUX_PLANES. */
 int svo_beam_conservative(svo_ctx *ctx, const svo_frame *frame);
 int svo_sync(svo_ctx *ctx);
-/* Six lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
- * `lane` (0..5) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
+/* Seven lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
+ * `lane` (0..6) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
  * Work on different lanes may overlap on the GPU: rendering frame k+1 on the other lane lets its first tiles fill the SMs
  * that frame k's last, longest tiles leave idle (measured: a 1080p frame carries ~0.13 ms of such tail -- the critical
  * path of its longest rays -- whatever share of the frame a GPU renders, so the 8-GPU tile partition keeps several frames in

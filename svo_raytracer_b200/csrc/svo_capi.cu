@@ -25,7 +25,7 @@ static_assert(sizeof(svo_ray) == 24 && sizeof(svo_hit) == 16, "ray-stream record
 
 static thread_local std::string g_error;
 
-constexpr int kLanes = 6;  // svo_select_lane: streams + colour/depth plane sets that may be in flight together
+constexpr int kLanes = 7;  // svo_select_lane: streams + colour/depth plane sets that may be in flight together
 
 struct svo_ctx {
   int device = 0;
@@ -60,7 +60,7 @@ struct svo_ctx {
   void *own[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *bound[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // second colour/depth set for pipelined read-back (svo_swap_buffers / svo_read_planes_async)
-  void *back[kLanes][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // sets 1..3 ([0] unused: set 0 = own[])
+  void *back[kLanes][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // sets of lanes 1.. ([0] unused: set 0 = own[])
   int render_set = 0;  // which colour/depth set renders draw into and reads take from: 0 = own[], s = back[s]
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_rendered = nullptr, ev_copied[kLanes] = {nullptr, nullptr, nullptr, nullptr};
@@ -931,7 +931,7 @@ int svo_swap_buffers(svo_ctx *c) {
 
 int svo_select_lane(svo_ctx *c, int lane) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
-  if (lane < 0 || lane >= kLanes) return fail(c, SVO_ERR_INVALID, "lane must be in [0, 6)");
+  if (lane < 0 || lane >= kLanes) return fail(c, SVO_ERR_INVALID, "lane must be in [0, 7)");
   if (lane == c->lane) return SVO_OK;
   SVO_CUDA(c, cudaSetDevice(c->device));
   int rc = ensure_pipeline(c, lane);
