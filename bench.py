@@ -215,18 +215,46 @@ def config_of(a, world_size: int, tree_bytes: int, partition: str) -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled from a thread every ~4 ms so
+    that even a 15 ms timed region (the driver's --steps 20) yields several samples; `nvidia-smi -lms 20` is the fallback."""
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
         self.t0 = self.t1 = None
+        self.samples = []  # (time, sm MHz, reasons bitmask)
+        self.nvml = None
+        self.p = None
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = False
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+        except Exception:
+            self.nvml = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                           "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            except OSError:
+                self.p = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                clk = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else \
+                    int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.time(), clk, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def begin(self):
         self.t0 = time.time()
@@ -235,6 +263,15 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            inside = [x for x in self.samples if self.t0 is not None and self.t0 - 0.002 <= x[0] <= self.t1 + 0.002]
+            use = inside if inside else self.samples[-3:]
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            reasons = sorted({nm for _, _, rs in use for bit, nm in names.items() if rs & bit})
+            return {"sm_mhz": float(np.median([c for _, c, _ in use])) if use else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(inside), "source": "nvml, polled every ~4 ms"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -269,7 +306,7 @@ class ClockSampler:
         self.f.close()
         os.unlink(self.f.name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # ---- CPU arm ----------------------------------------------------------------------------------------------------

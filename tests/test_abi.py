@@ -71,3 +71,36 @@ def test_argument_validation_without_device(svo):
     assert lib.svo_build_terrain(hm.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), 8, 8, None, 0, C.byref(need), 1) == 0
     assert need.value > 7
     assert lib.svo_build_terrain(hm.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), 6, 8, None, 0, C.byref(need), 1) == svo._lib.ERR_INVALID
+
+
+def _build_c_client(tmp_path):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "engine_loop")
+    libdir = os.path.join(root, "svo_raytracer_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_client", "engine_loop.c"), "-o", exe, "-L", libdir, "-lsvo_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_client_compiles_links_and_refuses_to_run_without_a_device(tmp_path):
+    """include/svo_b200.h bound by a C compiler (the Java binding of INTEGRATION.md cannot be compiled here): the engine's
+    frame-loop call sequence (tests/c_client/engine_loop.c) compiles as C11 with -Werror and links every entry point it
+    needs; without a CUDA device it exits 77 -- svo_create fails loudly, there is no CPU path."""
+    import subprocess
+    import svo_raytracer_b200 as svo
+    import ctypes as C
+    exe = _build_c_client(tmp_path)
+    n = C.c_int(0)
+    svo._lib.lib().svo_device_count(C.byref(n))
+    rc = subprocess.run([exe], capture_output=True, text=True)
+    assert rc.returncode == (0 if n.value > 0 else 77), (rc.returncode, rc.stdout, rc.stderr)
+
+
+@pytest.mark.gpu
+def test_c_client_runs_the_engine_loop(tmp_path):
+    import subprocess
+    rc = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
+    assert rc.returncode == 0 and "engine loop ok" in rc.stdout, (rc.returncode, rc.stdout, rc.stderr)
