@@ -361,6 +361,41 @@ def test_conservative_beam_full_size(svo, oracle):
                     assert st1["iters"] == st0["iters"], (cam, mode, st0, st1)
 
 
+@pytest.mark.parametrize("band_rows,parts", [(8, 3), (16, 2), (8, 8), (64, 3)])
+def test_read_interleaved_assembles_the_frame_in_host_memory(svo, oracle, terrain128, band_rows, parts):
+    """svo_read_interleaved_async: each part's bands go from the context's planes to their place in full-frame HOST buffers
+    (one strided copy per plane; the last band is cut by the image's bottom edge: H = 117).  Parts rendered and read one
+    after the other, on rotating lanes, assemble the oracle's frame; rows of other parts are not touched."""
+    import torch
+    W, H = 200, 117
+    pos, l1, l2, r1, r2 = svo.CAMERAS["B"]
+    want, _ = oracle.render(terrain128, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=2, render_mode=0, max_depth=7), W, H, nthreads=4,
+                            planes=("rgba8", "depth"))
+    f = svo.camera_frame("B", frame_number=2, render_mode=0, max_depth=7)
+    color = torch.full((H, W, 4), 7, dtype=torch.uint8).pin_memory()
+    depth = torch.full((H, W), -5.0, dtype=torch.float32).pin_memory()
+    with svo.SvoContext(W, H) as c:
+        c.upload(terrain128)
+        c.set_option(svo._lib.OPT_BAND_ROWS, band_rows)
+        for part in range(parts):
+            c.select_lane(part % 7)
+            c.render_interleaved(f, part, parts)
+            c.read_interleaved_async(part, parts, color.data_ptr(), depth.data_ptr())
+            if part == 0:  # only part 0's bands have arrived
+                c.read_wait()
+                rows = np.zeros(H, bool)
+                for b in range(0, (H + band_rows - 1) // band_rows, parts):
+                    rows[b * band_rows:(b + 1) * band_rows] = True
+                assert np.array_equal(color.numpy()[rows], want["rgba8"][rows])
+                if parts > 1:
+                    assert (color.numpy()[~rows] == 7).all() and (depth.numpy()[~rows] == -5.0).all()
+        c.read_wait()
+        assert np.array_equal(color.numpy(), want["rgba8"])
+        assert np.array_equal(depth.numpy().view(np.uint32), want["depth"].view(np.uint32))
+        with pytest.raises(svo.SvoError):
+            c.select_lane(7)
+
+
 def test_fence_watchdog_is_reported(svo, terrain128):
     """A wait nobody signals gives up after ~2 s; svo_sync reports it (the latch was invisible to the host)."""
     with svo.SvoContext(64, 64) as c:
