@@ -79,7 +79,8 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..7; 0 = 3 on one GPU, 6 in the tile partition)")
     ap.add_argument("--beam", type=int, default=-1, help="conservative beam pre-pass per frame (svo_beam_conservative + SVO_FRAME_BEAM_FLOOR; the frame does not "
-                                                         "change): -1 = on for one GPU / replica mode in render modes 0 and 3, off in the tile partition")
+                                                         "change): -1 = on for one GPU / replica mode in render modes 0 and 3, off in the tile partition; "
+                                                         "2 = tile partition with the lattice shared between the ranks")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
@@ -457,7 +458,8 @@ def main():
 
 
     tiles = world_size > 1 and partition == "tiles"
-    BEAM = (a.beam == 1 or (a.beam < 0 and not tiles)) and MODE in (0, 3) and not a.accumulate and not (tiles and a.fence == "nccl")
+    BEAM = (a.beam >= 1 or (a.beam < 0 and not tiles)) and MODE in (0, 3) and not a.accumulate and not (tiles and a.fence == "nccl")
+    BEAM_SHARED = BEAM and tiles and a.beam == 2  # every rank traces 1/N of the lattice for everybody (svo_beam_lattice_rows)
 
     def frame_for(s):
         fp = frame_params(s, a.size, a)
@@ -516,6 +518,25 @@ def main():
             else:
                 owner_fence = [ctx.ipc_import(fh[0])]
             state = {"k": 0, "pending": None}
+            if BEAM_SHARED:
+                lat_h = [None] * world_size
+                dist.all_gather_object(lat_h, [ctx.ipc_export(L.PLANE_BEAM_LATTICE | (l << 8)) for l in range(LANES)])
+                lat_ptrs = [[ctx.device_ptr(L.PLANE_BEAM_LATTICE | (l << 8)) if r == rank else ctx.ipc_import(lat_h[r][l]) for r in range(world_size)]
+                            for l in range(LANES)]
+                all_fences = [ctx.fence_device_ptr() if r == rank else ctx.ipc_import(fh[r]) for r in range(world_size)]
+                lat_rows = H // 4 + 1
+                my_rows = (rank * lat_rows // world_size, (rank + 1) * lat_rows // world_size)
+
+            def beam_for(s, k):
+                if not BEAM:
+                    return
+                if not BEAM_SHARED:
+                    ctx.beam_conservative(frames[s])  # every rank computes the (small) beam plane of the whole frame for itself
+                    return
+                l = k % LANES
+                ctx.beam_lattice_rows(frames[s], my_rows[0], my_rows[1], lat_ptrs[l], all_fences, slot=8 + l)
+                ctx.fence_wait((k // LANES + 1) * world_size, slot=8 + l)  # every rank's rows of this frame's lattice have arrived
+                ctx.beam_filter()
 
             def bind(k):
                 for plane, ptr in zip(PL, sets[k % LANES]):
@@ -536,9 +557,8 @@ def main():
                 k = state["k"]
                 state["k"] = k + 1
                 ctx.select_lane(k % LANES)
-                if BEAM:
-                    ctx.beam_conservative(frames[s])  # every rank computes the (small) beam plane of the whole frame for itself
                 if rank == 0:
+                    beam_for(s, k)
                     bind(k)
                     ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=1 + (k % LANES))
                     if state["pending"] is not None:
@@ -546,6 +566,7 @@ def main():
                     state["pending"] = (k, consume)
                 else:
                     ctx.fence_wait(max(k - LANES + 1, 0), slot=0)  # rank 0 has consumed frames 0..k-LANES: this lane's set is free
+                    beam_for(s, k)
                     bind(k)
                     ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=1 + (k % LANES))
 
@@ -903,7 +924,7 @@ def main():
         "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_of(a, world_size, tree_bytes, partition),
-        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "conservative_beam_prepass": bool(BEAM), "descriptors": info["descriptors"], "levels": info["levels"],
+        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "conservative_beam_prepass": ("lattice shared between the ranks" if BEAM_SHARED else bool(BEAM)), "descriptors": info["descriptors"], "levels": info["levels"],
                          "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
                          "world": {"how": world_how, "seconds": round(build_s, 2), "maps_s": round(maps_s, 2)}, "build_and_transcode_s": round(upload_s, 3),
                          "units": ("one frame per step, interleaved %d-row bands per rank, peers store into rank 0's planes over NVLink, "

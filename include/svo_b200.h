@@ -76,6 +76,8 @@ enum svo_plane {
   SVO_PLANE_ITER = 4,        /* new: primary loop iterations (render mode 1 shows it as a heat map, :428) */
   SVO_PLANE_PRIMARY_T = 5,   /* new: primary res.t */
   SVO_PLANE_RADIANCE = 6,    /* new: finalcolor before the rgba8 store, float4 */
+  SVO_PLANE_BEAM_LATTICE = 7,/* svo_device_ptr / svo_ipc_export only: the (W/4+1) x (H/4+1) lattice buffer of the conservative beam
+                              * pre-pass of lane `plane >> 8` (shared between the GPUs of the tile partition, svo_beam_lattice_rows) */
   SVO_PLANE_BACK = 0x100     /* OR-ed to COLOR_RGBA8 / DEPTH in svo_device_ptr and svo_ipc_export: the second set
                               * (svo_swap_buffers, lane 1); without it they name the first set.  In general
                               * plane | (lane << 8) names the set of lane 1..6 (svo_select_lane) */
@@ -179,6 +181,14 @@ int svo_beam(svo_ctx *ctx, const svo_frame *frame);
  * observable: mode 1 (heat map), mode 2 (the penumbra term reads the primary's stale count when the shadow ray misses,
  * svotrace.comp:616-619) and with SVO_OPT_AUX_PLANES. */
 int svo_beam_conservative(svo_ctx *ctx, const svo_frame *frame);
+/* The same pre-pass in two halves, for the multi-GPU tile partition, where every rank needs the whole beam plane but should not
+ * trace the whole lattice: svo_beam_lattice_rows traces lattice rows [row0, row1) only and stores them into the ndst lattice
+ * buffers of dst_ptrs (its own and, over NVLink, its peers': svo_device_ptr / svo_ipc_import of SVO_PLANE_BEAM_LATTICE |
+ * lane << 8; ndst = 0: its own), and the launch's last CTA bumps slot `slot` of the nsig fences; after svo_fence_wait for all
+ * ranks' rows, svo_beam_filter turns the current lane's lattice into its beam plane (min filter + margin). */
+int svo_beam_lattice_rows(svo_ctx *ctx, const svo_frame *frame, int row0, int row1, void *const *dst_ptrs, int ndst,
+                          void *const *fence_ptrs, int nsig, int slot);
+int svo_beam_filter(svo_ctx *ctx);
 int svo_sync(svo_ctx *ctx);
 /* Seven lanes -- a CUDA stream and a colour/depth plane set each (set 1 = the SVO_PLANE_BACK set).  svo_select_lane makes
  * `lane` (0..6) current: later calls enqueue on its stream, svo_render draws into its set, reads take it from there.
@@ -237,9 +247,10 @@ int svo_ipc_close(svo_ctx *ctx, void *device_ptr);
  * svo_fence_signal(ctx, ptrs, n) enqueues one kernel that, after everything already in the stream, adds 1 to each
  * of the n counters (n = 0: the context's own counter); svo_fence_wait(ctx, target) enqueues a kernel that waits
  * until the context's own counter has reached `target` (modulo 2^32; gives up after ~2 s so that a dead peer
- * cannot hang the GPU).  Protocol of bench.py --partition tiles: peers signal the frame owner when their bands
+ * cannot hang the GPU).  Every counter has 16 slots.  Protocol of bench.py --partition tiles: peers signal the frame owner when their bands
  * are stored ("frame complete" = frames * n_gpus), the owner signals the peers when it has consumed the frame. */
 int svo_fence_export(svo_ctx *ctx, uint8_t handle[SVO_IPC_HANDLE_BYTES]);
+void *svo_fence_device_ptr(svo_ctx *ctx); /* this context's own counter, for fence lists that include the caller itself */
 int svo_fence_signal(svo_ctx *ctx, void *const *fence_ptrs, int n, int slot);
 int svo_fence_wait(svo_ctx *ctx, int slot, uint32_t target);
 /* svo_fence_wait(slot, target) followed by svo_fence_signal(fence_ptrs, n, signal_slot) in ONE launch: what the frame's

@@ -17,7 +17,7 @@ NO_HIT = 0xFFFFFFFF
 # enum svo_status
 OK, ERR_INVALID, ERR_OOM, ERR_NO_DEVICE, ERR_CUDA, ERR_FORMAT, ERR_NO_SCENE, ERR_FENCE = 0, 1, 2, 100, 999, 1000, 1001, 1002
 # enum svo_plane
-PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIMARY_T, PLANE_RADIANCE = range(7)
+PLANE_COLOR_RGBA8, PLANE_DEPTH, PLANE_BEAM, PLANE_HIT_ID, PLANE_ITER, PLANE_PRIMARY_T, PLANE_RADIANCE, PLANE_BEAM_LATTICE = range(8)
 PLANE_BACK = 0x100
 # enum svo_option
 OPT_AUX_PLANES, OPT_FAST_MATH, OPT_KERNEL, OPT_L2_PERSIST, OPT_RAY_SORT, OPT_CONTENT_BOUNDS, OPT_BAND_ROWS, OPT_GPU_TRANSCODE = 1, 2, 3, 4, 5, 6, 7, 8
@@ -63,6 +63,8 @@ SYMBOLS = {
     "svo_render_interleaved_signal": (_i, [_vp, C.POINTER(Frame), _i, _i, C.POINTER(_vp), _i, _i]),
     "svo_beam": (_i, [_vp, C.POINTER(Frame)]),
     "svo_beam_conservative": (_i, [_vp, C.POINTER(Frame)]),
+    "svo_beam_lattice_rows": (_i, [_vp, C.POINTER(Frame), _i, _i, C.POINTER(_vp), _i, C.POINTER(_vp), _i, _i]),
+    "svo_beam_filter": (_i, [_vp]),
     "svo_sync": (_i, [_vp]),
     "svo_read_plane": (_i, [_vp, _i, _vp, _u64]),
     "svo_read_plane_rows": (_i, [_vp, _i, _i, _i, _vp, _u64]),
@@ -84,6 +86,7 @@ SYMBOLS = {
     "svo_ipc_import": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "svo_ipc_close": (_i, [_vp, _vp]),
     "svo_fence_export": (_i, [_vp, _vp]),
+    "svo_fence_device_ptr": (_vp, [_vp]),
     "svo_fence_signal": (_i, [_vp, C.POINTER(_vp), _i, _i]),
     "svo_fence_wait": (_i, [_vp, _i, C.c_uint32]),
     "svo_fence_wait_signal": (_i, [_vp, _i, C.c_uint32, C.POINTER(_vp), _i, _i]),

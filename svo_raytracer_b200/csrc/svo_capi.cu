@@ -461,10 +461,10 @@ int svo_create(svo_ctx **out, int device, int width, int height) {
       if ((e = cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming)) != cudaSuccess) break;
     if (e != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaEventCreate"); break; }
-    if ((e = cudaMalloc((void **)&c->d_tile_counter, 64)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(counter)"); break; }
-    cudaMemsetAsync(c->d_tile_counter, 0, 64, c->stream);
-    if ((e = cudaMalloc((void **)&c->d_fence, 256)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(fence)"); break; }
-    cudaMemsetAsync(c->d_fence, 0, 256, c->stream);
+    if ((e = cudaMalloc((void **)&c->d_tile_counter, 256)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(counter)"); break; }
+    cudaMemsetAsync(c->d_tile_counter, 0, 256, c->stream);
+    if ((e = cudaMalloc((void **)&c->d_fence, 512)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(fence)"); break; }
+    cudaMemsetAsync(c->d_fence, 0, 512, c->stream);
     for (int p = SVO_PLANE_COLOR_RGBA8; p <= SVO_PLANE_BEAM; p++) {
       size_t bytes = plane_elems(c, p) * plane_elem_bytes(p);
       if ((e = cudaMalloc(&c->own[p], bytes ? bytes : 16)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "cudaMalloc(plane)"); break; }
@@ -751,7 +751,7 @@ int svo_render_interleaved_signal(svo_ctx *c, const svo_frame *frame, int part, 
   if (rc) return rc;
   if (parts < 1 || part < 0 || part >= parts) return fail(c, SVO_ERR_INVALID, "part must be in [0, parts)");
   if (n < -1 || n > 16 || (n > 0 && !fence_ptrs)) return fail(c, SVO_ERR_INVALID, "bad fence list (at most 16)");
-  if (n >= 0 && (slot < 0 || slot >= 8)) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
+  if (n >= 0 && (slot < 0 || slot >= 16)) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,16)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   if (c->opt_aux && (rc = ensure_aux(c)) != SVO_OK) return rc;
   FrameParams fp;
@@ -798,6 +798,58 @@ int svo_beam(svo_ctx *c, const svo_frame *frame) {
   return SVO_OK;
 }
 
+static int ensure_lattice(svo_ctx *c, int l) {
+  const size_t lat_bytes = (size_t)(c->W / 4 + 1) * (size_t)(c->H / 4 + 1) * sizeof(float) + 16;
+  if (!c->d_beam_lattice[l]) {
+    SVO_CUDA(c, cudaMalloc((void **)&c->d_beam_lattice[l], lat_bytes));
+    SVO_CUDA(c, cudaMemsetAsync(c->d_beam_lattice[l], 0, lat_bytes, c->stream));
+  }
+  if (l >= 1 && !c->lane_beam[l]) {
+    const size_t bytes = plane_elems(c, SVO_PLANE_BEAM) * sizeof(float);
+    SVO_CUDA(c, cudaMalloc((void **)&c->lane_beam[l], bytes ? bytes : 16));
+    SVO_CUDA(c, cudaMemsetAsync(c->lane_beam[l], 0, bytes, c->stream));
+  }
+  return SVO_OK;
+}
+
+// The conservative beam pre-pass in two halves, for the tile partition: every rank traces 1/N of the lattice and stores it
+// into every rank's lattice buffer over NVLink (dst_ptrs: svo_device_ptr / svo_ipc_import of SVO_PLANE_BEAM_LATTICE of the
+// frame's lane), the launch's last CTA bumps fence_ptrs[*] + slot; after waiting for N such bumps every rank filters locally.
+int svo_beam_lattice_rows(svo_ctx *c, const svo_frame *frame, int row0, int row1, void *const *dst_ptrs, int ndst, void *const *fence_ptrs, int nsig,
+                          int slot) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_beam_lattice_rows before svo_upload");
+  int rc = check_frame(c, frame);
+  if (rc) return rc;
+  if (ndst < 0 || ndst > 16 || nsig < 0 || nsig > 16 || (ndst > 0 && !dst_ptrs) || (nsig > 0 && !fence_ptrs)) return fail(c, SVO_ERR_INVALID, "bad pointer list (at most 16)");
+  if (slot < 0 || slot >= 16) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,16)");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  const int l = c->render_set;
+  if ((rc = ensure_lattice(c, l)) != SVO_OK) return rc;
+  FenceList dst, sig;
+  dst.n = ndst;
+  sig.n = nsig;
+  for (int i = 0; i < 16; i++) {
+    dst.p[i] = i < ndst ? (unsigned int *)dst_ptrs[i] : nullptr;
+    sig.p[i] = i < nsig ? (unsigned int *)fence_ptrs[i] + 8 * slot : nullptr;
+  }
+  FrameParams fp;
+  memcpy(&fp, frame, sizeof fp);
+  SVO_CUDA(c, launch_beam_lattice_rows(scene_view(c), fp, c->d_beam_lattice[l], c->W, c->H, row0, row1, dst, sig, c->d_tile_counter + 32 + 2 * l, c->stream));
+  c->launches++;
+  return SVO_OK;
+}
+int svo_beam_filter(svo_ctx *c) {
+  if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
+  SVO_CUDA(c, cudaSetDevice(c->device));
+  const int l = c->render_set;
+  int rc = ensure_lattice(c, l);
+  if (rc) return rc;
+  SVO_CUDA(c, launch_beam_filter(c->d_beam_lattice[l], (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
+  c->launches++;
+  return SVO_OK;
+}
+
 int svo_beam_conservative(svo_ctx *c, const svo_frame *frame) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (!c->have_scene) return fail(c, SVO_ERR_NO_SCENE, "svo_beam_conservative before svo_upload");
@@ -806,13 +858,7 @@ int svo_beam_conservative(svo_ctx *c, const svo_frame *frame) {
   SVO_CUDA(c, cudaSetDevice(c->device));
   // every lane has its own lattice scratch and beam plane: the pre-pass of frame k+1 may run while frame k is still being drawn
   const int l = c->render_set;
-  const size_t lat_bytes = (size_t)(c->W / 4 + 1) * (size_t)(c->H / 4 + 1) * sizeof(float) + 16;
-  if (!c->d_beam_lattice[l]) SVO_CUDA(c, cudaMalloc((void **)&c->d_beam_lattice[l], lat_bytes));
-  if (l >= 1 && !c->lane_beam[l]) {
-    const size_t bytes = plane_elems(c, SVO_PLANE_BEAM) * sizeof(float);
-    SVO_CUDA(c, cudaMalloc((void **)&c->lane_beam[l], bytes ? bytes : 16));
-    SVO_CUDA(c, cudaMemsetAsync(c->lane_beam[l], 0, bytes, c->stream));
-  }
+  if ((rc = ensure_lattice(c, l)) != SVO_OK) return rc;
   FrameParams fp;
   memcpy(&fp, frame, sizeof fp);
   SVO_CUDA(c, launch_beam_conservative(scene_view(c), fp, c->d_beam_lattice[l], (float *)plane_ptr(c, SVO_PLANE_BEAM), c->W, c->H, c->stream));
@@ -951,6 +997,10 @@ int svo_read_wait(svo_ctx *c) {
 }
 
 void *svo_device_ptr(svo_ctx *c, int plane) {
+  if (c && (plane & 0xFF) == SVO_PLANE_BEAM_LATTICE && (plane >> 8) >= 0 && (plane >> 8) < kLanes) {
+    cudaSetDevice(c->device);
+    return ensure_lattice(c, plane >> 8) == SVO_OK ? (void *)c->d_beam_lattice[plane >> 8] : nullptr;
+  }
   if (c && (plane >> 8) >= 1 && (plane >> 8) < kLanes && (plane & 0xFF) <= SVO_PLANE_DEPTH) {  // plane | (set << 8): the sets of lanes 1..3
     cudaSetDevice(c->device);
     return ensure_pipeline(c, plane >> 8) == SVO_OK ? c->back[plane >> 8][plane & 0xFF] : nullptr;
@@ -973,6 +1023,13 @@ int svo_bind_plane(svo_ctx *c, int plane, void *device_ptr) {
 
 int svo_ipc_export(svo_ctx *c, int plane, uint8_t handle[72]) {
   if (!c || !handle) return fail(nullptr, SVO_ERR_INVALID, "NULL argument");
+  if ((plane & 0xFF) == SVO_PLANE_BEAM_LATTICE && (plane >> 8) >= 0 && (plane >> 8) < kLanes) {
+    SVO_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_lattice(c, plane >> 8);
+    if (rc) return rc;
+    SVO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return export_handle(c, c->d_beam_lattice[plane >> 8], handle);
+  }
   if ((plane >> 8) >= 1 && (plane >> 8) < kLanes && (plane & 0xFF) <= SVO_PLANE_DEPTH) {
     SVO_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_pipeline(c, plane >> 8);
@@ -994,10 +1051,11 @@ int svo_fence_export(svo_ctx *c, uint8_t handle[72]) {
   SVO_CUDA(c, cudaSetDevice(c->device));
   return export_handle(c, c->d_fence, handle);
 }
+void *svo_fence_device_ptr(svo_ctx *c) { return c ? (void *)c->d_fence : nullptr; }
 int svo_fence_signal(svo_ctx *c, void *const *fence_ptrs, int n, int slot) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   if (n < 0 || n > 16 || (n > 0 && !fence_ptrs)) return fail(c, SVO_ERR_INVALID, "bad fence list (at most 16)");
-  if (slot < 0 || slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
+  if (slot < 0 || slot >= 16) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,16)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   FenceList fl;
   fl.n = n > 0 ? n : 1;
@@ -1010,7 +1068,7 @@ int svo_fence_signal(svo_ctx *c, void *const *fence_ptrs, int n, int slot) {
 }
 int svo_fence_wait(svo_ctx *c, int slot, uint32_t target) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
-  if (slot < 0 || slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
+  if (slot < 0 || slot >= 16) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,16)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, launch_fence_wait(c->d_fence + 8 * slot, c->d_fence + 7, target, c->stream));
   c->fence_waits_unchecked = true;
@@ -1019,7 +1077,7 @@ int svo_fence_wait(svo_ctx *c, int slot, uint32_t target) {
 }
 int svo_fence_wait_signal(svo_ctx *c, int slot, uint32_t target, void *const *fence_ptrs, int n, int signal_slot) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
-  if (slot < 0 || slot >= 8 || signal_slot < 0 || signal_slot >= 8) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,8)");
+  if (slot < 0 || slot >= 16 || signal_slot < 0 || signal_slot >= 16) return fail(c, SVO_ERR_INVALID, "fence slot must be in [0,16)");
   if (n < 1 || n > 16 || !fence_ptrs) return fail(c, SVO_ERR_INVALID, "bad fence list (1..16)");
   SVO_CUDA(c, cudaSetDevice(c->device));
   FenceList fl;
@@ -1034,7 +1092,7 @@ int svo_fence_reset(svo_ctx *c) {
   if (!c) return fail(nullptr, SVO_ERR_INVALID, "ctx is NULL");
   SVO_CUDA(c, cudaSetDevice(c->device));
   SVO_CUDA(c, sync_lanes(c));
-  SVO_CUDA(c, cudaMemsetAsync(c->d_fence, 0, 256, c->stream));
+  SVO_CUDA(c, cudaMemsetAsync(c->d_fence, 0, 512, c->stream));
   SVO_CUDA(c, cudaStreamSynchronize(c->stream));
   return SVO_OK;
 }

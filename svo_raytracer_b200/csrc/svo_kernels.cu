@@ -885,12 +885,18 @@ __device__ __forceinline__ vec3 beam_lattice_dir(const FrameParams &f, int gx, i
   return normalize3(d);
 }
 
-__global__ void __launch_bounds__(128) k_beam_lattice(SceneView sc, FrameParams f, float *__restrict__ lattice, int W, int H) {
-  const int lw = (W >> 2) + 1, lh = (H >> 2) + 1;
+// Lattice rows [row0, row1) only, every value stored into the dst.n lattice buffers of `dst` (this GPU's and, over NVLink, its
+// peers': in the tile partition every rank traces 1/N of the lattice for everybody); the last CTA to leave bumps the fences
+// of `sig` ("this rank's rows of the frame's lattice are stored").  `ticket`: two words, zero between launches.
+__global__ void __launch_bounds__(128) k_beam_lattice(SceneView sc, FrameParams f, float *__restrict__ lattice, int W, int H, int row0, int row1,
+                                                      FenceList dst, FenceList sig, unsigned int *__restrict__ ticket) {
+  const int lw = (W >> 2) + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-  const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-  if (gx >= lw || gy >= lh) return;
+  const int gy = row0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+  const bool live = gx < lw && gy < row1;
+  float out_value = 0.0f;
+  if (live) {
   const vec3 d0 = beam_lattice_dir(f, gx, gy, W, H), dx = beam_lattice_dir(f, gx + 1, gy, W, H), dy = beam_lattice_dir(f, gx, gy + 1, W, H);
   const vec3 ex = mk3(dx.x - d0.x, dx.y - d0.y, dx.z - d0.z), ey = mk3(dy.x - d0.x, dy.y - d0.y, dy.z - d0.z);
   // lattice spacing per unit distance around this ray, with slack for its variation over the filter window
@@ -919,7 +925,25 @@ __global__ void __launch_bounds__(128) k_beam_lattice(SceneView sc, FrameParams 
   } else {
     out = 0.0f;
   }
-  lattice[(size_t)gy * (size_t)lw + (size_t)gx] = fmaxf(out, 0.0f);
+  out_value = fmaxf(out, 0.0f);
+  }
+  if (live) {
+    const size_t at = (size_t)gy * (size_t)lw + (size_t)gx;
+    if (dst.n == 0) lattice[at] = out_value;
+    for (int i = 0; i < dst.n; i++) ((float *)dst.p[i])[at] = out_value;
+  }
+  if (sig.n > 0) {  // last CTA out: everything this launch stored is visible system-wide before the bumps
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned t = atomicAdd(ticket, 1u);
+      if (t == gridDim.x * gridDim.y - 1u) {
+        ticket[0] = 0u;
+        __threadfence_system();
+        for (int i = 0; i < sig.n; i++) atomicAdd_system(sig.p[i], 1u);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(128) k_beam_minfilter(const float *__restrict__ lattice, float *__restrict__ beam, int W, int H) {
@@ -1187,14 +1211,34 @@ cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FramePa
   return cudaGetLastError();
 }
 
-cudaError_t launch_beam_conservative(const SceneView &sc, const FrameParams &f, float *lattice, float *beam, int W, int H, cudaStream_t stream) {
+cudaError_t launch_beam_lattice_rows(const SceneView &sc, const FrameParams &f, float *lattice, int W, int H, int row0, int row1,
+                                     const FenceList &dst, const FenceList &sig, unsigned int *ticket, cudaStream_t stream) {
   const int bw = W >> 2, bh = H >> 2;
   if (bw == 0 || bh == 0) return cudaSuccess;
-  const dim3 lgrid((bw + 1 + 15) / 16, (bh + 1 + 7) / 8);
-  SVO_LAUNCH(lgrid, 128, stream, k_beam_lattice)(sc, f, lattice, W, H);
+  if (row1 > bh + 1) row1 = bh + 1;
+  if (row0 < 0) row0 = 0;
+  if (row0 >= row1) {  // nothing to trace: the fences of the frame are still owed
+    if (sig.n > 0) SVO_LAUNCH(1, 32, stream, k_fence_signal)(sig);
+    return cudaGetLastError();
+  }
+  const dim3 lgrid((bw + 1 + 15) / 16, (row1 - row0 + 7) / 8);
+  SVO_LAUNCH(lgrid, 128, stream, k_beam_lattice)(sc, f, lattice, W, H, row0, row1, dst, sig, ticket);
+  return cudaGetLastError();
+}
+cudaError_t launch_beam_filter(const float *lattice, float *beam, int W, int H, cudaStream_t stream) {
+  const int bw = W >> 2, bh = H >> 2;
+  if (bw == 0 || bh == 0) return cudaSuccess;
   const dim3 fgrid((bw + 127) / 128, bh);
   SVO_LAUNCH(fgrid, 128, stream, k_beam_minfilter)(lattice, beam, W, H);
   return cudaGetLastError();
+}
+cudaError_t launch_beam_conservative(const SceneView &sc, const FrameParams &f, float *lattice, float *beam, int W, int H, cudaStream_t stream) {
+  FenceList none;
+  none.n = 0;
+  for (int i = 0; i < 16; i++) none.p[i] = nullptr;
+  cudaError_t e = launch_beam_lattice_rows(sc, f, lattice, W, H, 0, (H >> 2) + 1, none, none, nullptr, stream);
+  if (e != cudaSuccess) return e;
+  return launch_beam_filter(lattice, beam, W, H, stream);
 }
 
 cudaError_t launch_math_probe(int fn, const float *x, const float *y, float *out, uint64_t n, cudaStream_t stream) {

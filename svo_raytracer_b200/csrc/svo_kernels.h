@@ -91,6 +91,9 @@ cudaError_t launch_cast(const LaunchCfg &cfg, const SceneView &sc, const void *d
 cudaError_t launch_beam(const LaunchCfg &cfg, const SceneView &sc, const FrameParams &f, float *beam, int W, int H,
                         cudaStream_t stream);
 // conservative beam pre-pass: lattice = scratch of (W/4+1) x (H/4+1) floats, beam = the (W/4) x (H/4) beam plane
+cudaError_t launch_beam_lattice_rows(const SceneView &sc, const FrameParams &f, float *lattice, int W, int H, int row0, int row1,
+                                     const FenceList &dst, const FenceList &sig, unsigned int *ticket, cudaStream_t stream);
+cudaError_t launch_beam_filter(const float *lattice, float *beam, int W, int H, cudaStream_t stream);
 cudaError_t launch_beam_conservative(const SceneView &sc, const FrameParams &f, float *lattice, float *beam, int W, int H, cudaStream_t stream);
 struct CellBox;
 cudaError_t gpu_transcode(const uint8_t *d_raw, uint64_t nbytes, uint2 *desc, uint32_t *refbase, uint2 *meta, uint64_t cap, uint64_t *ndesc,

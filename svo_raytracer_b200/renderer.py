@@ -174,6 +174,16 @@ class SvoContext:
         """Fill the beam plane with proven per-block lower bounds on the primary hit distance (svo_beam_conservative)."""
         self._check(self._lib.svo_beam_conservative(self._h, C.byref(frame)))
 
+    def beam_lattice_rows(self, frame: Frame, row0: int, row1: int, dst_ptrs: Sequence[int] = (), fence_ptrs: Sequence[int] = (), slot: int = 0):
+        """Lattice rows [row0, row1) of the conservative beam pre-pass into the given lattice buffers (own + peers'), then the fences."""
+        d = (C.c_void_p * max(1, len(dst_ptrs)))(*[C.c_void_p(p) for p in dst_ptrs])
+        f = (C.c_void_p * max(1, len(fence_ptrs)))(*[C.c_void_p(p) for p in fence_ptrs])
+        self._check(self._lib.svo_beam_lattice_rows(self._h, C.byref(frame), int(row0), int(row1), d, len(dst_ptrs), f, len(fence_ptrs), int(slot)))
+
+    def beam_filter(self):
+        """Current lane's lattice -> its beam plane (min filter + margin)."""
+        self._check(self._lib.svo_beam_filter(self._h))
+
     def sync(self):
         self._check(self._lib.svo_sync(self._h))
 
@@ -274,6 +284,9 @@ class SvoContext:
         """fence_wait(target, slot) then fence_signal(fence_ptrs, signal_slot) in one launch."""
         arr = (C.c_void_p * len(fence_ptrs))(*[C.c_void_p(p) for p in fence_ptrs])
         self._check(self._lib.svo_fence_wait_signal(self._h, int(slot), target & 0xFFFFFFFF, arr, len(fence_ptrs), int(signal_slot)))
+
+    def fence_device_ptr(self) -> int:
+        return int(self._lib.svo_fence_device_ptr(self._h) or 0)
 
     def fence_reset(self):
         self._check(self._lib.svo_fence_reset(self._h))

@@ -361,6 +361,36 @@ def test_conservative_beam_full_size(svo, oracle):
                     assert st1["iters"] == st0["iters"], (cam, mode, st0, st1)
 
 
+def test_beam_lattice_in_row_parts_equals_the_whole_prepass(svo, oracle, terrain128):
+    """svo_beam_lattice_rows + svo_beam_filter (the tile partition's shared pre-pass: every rank traces a slice of the lattice)
+    produce the beam plane of svo_beam_conservative bit for bit, whatever the slicing; the launch's last CTA bumps the fences."""
+    W, H = 256, 144
+    L = svo._lib
+    with svo.SvoContext(W, H) as c:
+        c.upload(terrain128)
+        f = svo.camera_frame("A", frame_number=1, render_mode=0, max_depth=7, scale=128)
+        c.beam_conservative(f)
+        want = c.read_plane(L.PLANE_BEAM).copy()
+        lh = H // 4 + 1
+        own = c.device_ptr(L.PLANE_BEAM_LATTICE)
+        fence = c.fence_device_ptr()
+        assert own and fence
+        for parts in (1, 2, 3, 8):
+            c.beam_lattice_rows(f, 0, lh, (), (), 0)  # overwritten below part by part
+            c.fence_reset()
+            for r in reversed(range(parts)):
+                c.beam_lattice_rows(f, r * lh // parts, (r + 1) * lh // parts, (own,), (fence,), slot=9)
+            c.fence_wait(parts, slot=9)
+            c.beam_filter()
+            c.sync()
+            got = c.read_plane(L.PLANE_BEAM)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), parts
+        c.fence_reset()
+        c.beam_lattice_rows(f, 5, 3, (), (fence,), slot=9)  # an empty slice still owes its bump
+        c.fence_wait(1, slot=9)
+        c.sync()
+
+
 @pytest.mark.parametrize("band_rows,parts", [(8, 3), (16, 2), (8, 8), (64, 3)])
 def test_read_interleaved_assembles_the_frame_in_host_memory(svo, oracle, terrain128, band_rows, parts):
     """svo_read_interleaved_async: each part's bands go from the context's planes to their place in full-frame HOST buffers
