@@ -368,7 +368,7 @@ def test_beam_lattice_in_row_parts_equals_the_whole_prepass(svo, oracle, terrain
     L = svo._lib
     with svo.SvoContext(W, H) as c:
         c.upload(terrain128)
-        f = svo.camera_frame("A", frame_number=1, render_mode=0, max_depth=7, scale=128)
+        f = svo.camera_frame("A", frame_number=1, render_mode=0, max_depth=7)
         c.beam_conservative(f)
         want = c.read_plane(L.PLANE_BEAM).copy()
         lh = H // 4 + 1
