@@ -79,8 +79,9 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (svo_select_lane; 1..7; 0 = 3 on one GPU, 6 in the tile partition)")
     ap.add_argument("--beam", type=int, default=-1, help="conservative beam pre-pass per frame (svo_beam_conservative + SVO_FRAME_BEAM_FLOOR; the frame does not "
-                                                         "change): -1 = on for one GPU / replica mode in render modes 0 and 3, off in the tile partition; "
-                                                         "2 = tile partition with the lattice shared between the ranks")
+                                                         "change): -1 = on for one GPU / replica mode in render modes 0 and 3, in the tile partition 2 while a rank "
+                                                         "draws >= 500k pixels of the frame, else 0; 1 = every rank computes the whole lattice; "
+                                                         "2 = tile partition with the lattice shared between the ranks (svo_beam_lattice_rows)")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
@@ -458,7 +459,12 @@ def main():
 
 
     tiles = world_size > 1 and partition == "tiles"
-    BEAM = (a.beam >= 1 or (a.beam < 0 and not tiles)) and MODE in (0, 3) and not a.accumulate and not (tiles and a.fence == "nccl")
+    if a.beam < 0:
+        # one GPU / replicas: on.  Tile partition: the lattice is shared between the ranks (each traces 1/N of it for
+        # everybody, one more fence per frame) while a rank's share of the frame is large enough to pay for that fence:
+        # measured on 8 B200s (profiles/r02_sharedbeam_*.json) +7 % at N=2, +3 % at N=4 and at N=8 4K, -9 % at N=8 1080p.
+        a.beam = (2 if W * H // world_size >= 500_000 and a.fence == "p2p" else 0) if tiles else 1
+    BEAM = a.beam >= 1 and MODE in (0, 3) and not a.accumulate and not (tiles and a.fence == "nccl")
     BEAM_SHARED = BEAM and tiles and a.beam == 2  # every rank traces 1/N of the lattice for everybody (svo_beam_lattice_rows)
 
     def frame_for(s):
