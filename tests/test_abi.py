@@ -104,3 +104,40 @@ def test_c_client_runs_the_engine_loop(tmp_path):
     import subprocess
     rc = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
     assert rc.returncode == 0 and "engine loop ok" in rc.stdout, (rc.returncode, rc.stdout, rc.stderr)
+
+
+def _build_cpp_client(tmp_path):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "engine_main")
+    libdir = os.path.join(root, "svo_raytracer_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp_client", "engine_main.cpp"), "-o", exe, "-L", libdir, "-lsvo_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_renderer_mirror_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """include/svo_renderer.hpp -- Renderer.java's interface (addShader / addSSBO / updateSSBO / dispatchCompute /
+    printGLErrors, Renderer.java:43-165) restated in C++ over the C ABI -- compiles with -Werror together with the engine's
+    frame loop written against it (tests/cpp_client/engine_main.cpp).  Without a CUDA device createImages queues
+    SVO_ERR_NO_DEVICE and the process stays alive (exit 77): no exception, no abort, no CPU path."""
+    import subprocess
+    import svo_raytracer_b200 as svo
+    import ctypes as C
+    exe = _build_cpp_client(tmp_path)
+    n = C.c_int(0)
+    svo._lib.lib().svo_device_count(C.byref(n))
+    rc = subprocess.run([exe], capture_output=True, text=True)
+    assert rc.returncode == (0 if n.value > 0 else 77), (rc.returncode, rc.stdout, rc.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_renderer_mirror_draws_the_frames_of_the_bare_abi(tmp_path):
+    """The engine loop through svo::Renderer (modes 2, 0, 3, 1, both beam pre-passes, an edit pushed as two updateSSBO
+    ranges) equals the same frames drawn through the bare C ABI byte for byte; its error queue behaves like glGetError."""
+    import subprocess
+    rc = subprocess.run([_build_cpp_client(tmp_path)], capture_output=True, text=True)
+    assert rc.returncode == 0 and "engine main ok" in rc.stdout, (rc.returncode, rc.stdout, rc.stderr)
+    assert "Update SSBO error: Invalid parameters." in rc.stdout
