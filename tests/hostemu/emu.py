@@ -48,6 +48,8 @@ def lib():
         L.emu_gpu_build_terrain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
         L.emu_beam_conservative.restype = C.c_int
         L.emu_beam_conservative.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.emu_beam_in_parts.restype = C.c_int
+        L.emu_beam_in_parts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.emu_gpu_transcode_check.restype = C.c_int
         L.emu_gpu_transcode_check.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
         L.emu_patch_check.restype = C.c_int
@@ -162,6 +164,13 @@ class Scene:
         """svo_beam_conservative on the emulator: per 4x4 block a lower bound on the primary hit distance (+inf = all miss)."""
         out = np.zeros((height // 4, width // 4), np.float32)
         rc = lib().emu_beam_conservative(self._h, C.byref(frame), width, height, _ptr(out), nthreads)
+        assert rc == 0, rc
+        return out
+
+    def beam_in_parts(self, frame, width, height, parts, nthreads=8):
+        """svo_beam_lattice_rows per part (each storing into two lattices and bumping two fences) + svo_beam_filter."""
+        out = np.zeros((height // 4, width // 4), np.float32)
+        rc = lib().emu_beam_in_parts(self._h, C.byref(frame), width, height, parts, _ptr(out), nthreads)
         assert rc == 0, rc
         return out
 

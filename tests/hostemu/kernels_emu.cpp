@@ -87,6 +87,33 @@ int emu_beam_conservative(const emu_scene *s, const FrameParams *f, int W, int H
   return (int)launch_beam_conservative(sc, *f, lattice.data(), beam, W, H, nullptr);
 }
 
+// svo_beam_lattice_rows x parts + svo_beam_filter (the tile partition's shared pre-pass): part r traces lattice rows
+// [r*lh/parts, (r+1)*lh/parts) into TWO lattice buffers (its own and a "peer's") and bumps two fence words from its last CTA.
+// Returns 0 if both lattices are complete and equal, every fence counted `parts`, and the ticket word is back at zero.
+int emu_beam_in_parts(const emu_scene *s, const FrameParams *f, int W, int H, int parts, float *beam, int nthreads) {
+  const SceneView sc = emu_view_of(s, nullptr);
+  const size_t n = (size_t)(W / 4 + 1) * (size_t)(H / 4 + 1);
+  const float poison = -7.0f;
+  std::vector<float> own(n + 4, poison), peer(n + 4, poison);
+  unsigned int fences[2 * 8 * 16] = {0}, ticket[2] = {0, 0};
+  const int lh = H / 4 + 1, slot = 9;
+  simt::g_os_threads = nthreads;
+  for (int r = parts - 1; r >= 0; r--) {
+    FenceList dst, sig;
+    dst.n = 2;
+    dst.p[0] = (unsigned int *)own.data();
+    dst.p[1] = (unsigned int *)peer.data();
+    sig.n = 2;
+    sig.p[0] = fences + 8 * slot;
+    sig.p[1] = fences + 8 * 16 + 8 * slot;
+    if (launch_beam_lattice_rows(sc, *f, own.data(), W, H, r * lh / parts, (r + 1) * lh / parts, dst, sig, ticket, nullptr) != cudaSuccess) return 1;
+  }
+  if (fences[8 * slot] != (unsigned)parts || fences[8 * 16 + 8 * slot] != (unsigned)parts || ticket[0] != 0u) return 2;
+  for (size_t i = 0; i < n; i++)
+    if (own[i] == poison || memcmp(&own[i], &peer[i], 4) != 0) return 3;
+  return (int)launch_beam_filter(peer.data(), beam, W, H, nullptr);
+}
+
 // svo_cast through the product's launch_cast on the emulator.  kernel 0 = grid-stride kernel, 1 = persistent threads with
 // warp-level ray fetch; order = optional permutation (the binned order of SVO_OPT_RAY_SORT).
 int emu_launch_cast(const emu_scene *s, const void *rays, const uint32_t *order, uint64_t n, void *out, int maxDepth, int kernel, int ctas,

@@ -371,6 +371,8 @@ def test_conservative_beam_prepass_on_simt_emulator(svo, oracle, terrain128, sce
     hit_blocks = np.isfinite(tmin)
     if hit_blocks.any():
         assert (beam[hit_blocks] > 0).mean() > 0.5 and np.median(beam[hit_blocks] / tmin[hit_blocks]) > 0.3  # a useful bound even at this tiny resolution (the margins are in lattice spacings)
+    for parts in (1, 2, 3, 8, 40):  # the tile partition's shared pre-pass: lattice rows traced part by part (40 > rows: empty parts still signal)
+        assert np.array_equal(scene128.beam_in_parts(f0, W, H, parts).view(np.uint32), beam.view(np.uint32)), parts
     f1 = oracle.make_frame(pos, l1, l2, r1, r2, flags=2, **kw)
     for kernel in (13, 17, 0):
         got = scene128.launch_render(f1, W, H, kernel=kernel, aux=False, box=True, beam=beam)
