@@ -444,6 +444,7 @@ def _ipc_worker(rank, world, port, q):
     import os, sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import numpy as np
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -497,7 +498,44 @@ def _ipc_worker(rank, world, port, q):
                 ctx.render(svo.camera_frame("A", frame_number=1, render_mode=3, max_depth=7))
                 ctx.sync()
             dist.barrier()
+        # 3) the conservative beam pre-pass with the lattice shared between the GPUs: every rank traces its rows of the lattice
+        # and stores them into both lattices over NVLink (svo_beam_lattice_rows), waits for everybody's rows, filters
+        # locally (svo_beam_filter) and draws its bands with SVO_FRAME_BEAM_FLOOR: same frame, and the same beam plane as
+        # svo_beam_conservative computes alone.
+        ctx.set_option(L.OPT_KERNEL, 17)
+        f0 = svo.camera_frame("B", frame_number=1, render_mode=0, max_depth=7)
+        ctx.beam_conservative(f0)
+        beam_alone = ctx.read_plane(L.PLANE_BEAM).copy()
+        lat_h = [None] * world
+        dist.all_gather_object(lat_h, ctx.ipc_export(L.PLANE_BEAM_LATTICE))
+        lattices = [ctx.device_ptr(L.PLANE_BEAM_LATTICE) if r == rank else ctx.ipc_import(lat_h[r]) for r in range(world)]
+        fences = [ctx.fence_device_ptr()] + (peers if rank == 0 else owner)  # (any order: every listed counter gets the bump)
+        lh = H // 4 + 1
+        ctx.beam_lattice_rows(f0, 0, lh, (), (), 0)
         ctx.sync()
+        dist.barrier()
+        fb = svo.camera_frame("B", frame_number=1, render_mode=0, max_depth=7, flags=2)
+        same = True
+        for i in range(3):
+            if rank != 0:
+                ctx.fence_wait(k)
+            ctx.beam_lattice_rows(fb, rank * lh // world, (rank + 1) * lh // world, lattices, fences, slot=9)
+            ctx.fence_wait((i + 1) * world, slot=9)
+            ctx.beam_filter()
+            if rank == 0:
+                ctx.render_interleaved_signal(fb, 0, world)
+                ctx.fence_wait((k + 1) * world)
+                out["sharedbeam"] = (ctx.read_color_rgba8(), ctx.read_depth())
+                same = same and np.array_equal(ctx.read_plane(L.PLANE_BEAM).view(np.uint32), beam_alone.view(np.uint32))
+                ctx.fence_signal(peers)
+            else:
+                ctx.render_interleaved_signal(fb, rank, world, owner)
+                same = same and np.array_equal(ctx.read_plane(L.PLANE_BEAM).view(np.uint32), beam_alone.view(np.uint32))
+            k += 1
+        ctx.sync()
+        ok = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        out["beam_planes_equal"] = bool(int(ok.item()))
         if rank == 0:
             q.put(out)
         dist.barrier()
@@ -532,6 +570,10 @@ def test_two_gpu_tiles_over_nvlink(svo, oracle):
     for tag in ("separate", "fused"):
         rgba, depth = out[tag]
         assert np.array_equal(rgba, want["rgba8"]) and np.array_equal(depth.view(np.uint32), want["depth"].view(np.uint32)), tag
+    want0, _ = oracle.render(nodes, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=1, render_mode=0, max_depth=7), 320, 200, nthreads=4)
+    rgba, depth = out["sharedbeam"]
+    assert out["beam_planes_equal"], "shared lattice: beam plane differs from svo_beam_conservative's"
+    assert np.array_equal(rgba, want0["rgba8"]) and np.array_equal(depth.view(np.uint32), want0["depth"].view(np.uint32)), "sharedbeam"
 
 
 @pytest.mark.parametrize("kernel", [0, 4, 6])
