@@ -538,7 +538,7 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
       return SVO_OK;
     case SVO_OPT_FAST_MATH: c->opt_fast = value != 0; return SVO_OK;
     case SVO_OPT_KERNEL:
-      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 24)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
+      if (value != 0 && value != 1 && value != 2 && (value < 4 || value > 26)) return fail(c, SVO_ERR_INVALID, "unknown kernel variant");
       if (cudaSetDevice(c->device) == cudaSuccess) sync_lanes(c);
       c->opt_kernel = (int)value;
       refresh_stream(c);

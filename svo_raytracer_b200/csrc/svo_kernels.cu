@@ -1039,7 +1039,7 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
 #undef SVO_LAUNCH_BINNED
     return cudaGetLastError();
   }
-  if (cfg.kernel >= 18 && cfg.kernel <= 24 && !cfg.fast && !cfg.aux && cfg.band_stride == 0) {  // ablations of variant 13's parts (production instance only)
+  if (cfg.kernel >= 18 && cfg.kernel <= 26 && !cfg.fast && !cfg.aux && cfg.band_stride == 0) {  // ablations of variant 13's parts (production instance only)
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
 #define SVO_LAUNCH_BALMASK(B, M) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, M>)(sc, f, pl, W, H, y0, y1)
@@ -1051,14 +1051,16 @@ cudaError_t launch_render(const LaunchCfg &cfg_in, const SceneView &sc, const Fr
     else if (cfg.kernel == 21) SVO_LAUNCH_BALMASK(B, 5);   \
     else if (cfg.kernel == 22) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 7>)(sc, f, pl, W, H, y0, y1); \
     else if (cfg.kernel == 23) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 1, 7>)(sc, f, pl, W, H, y0, y1);  \
-    else SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 6>)(sc, f, pl, W, H, y0, y1);                       \
+    else if (cfg.kernel == 24) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 6>)(sc, f, pl, W, H, y0, y1); \
+    else if (cfg.kernel == 25) SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 9>)(sc, f, pl, W, H, y0, y1); \
+    else SVO_LAUNCH(grid, 128, stream, k_render_tile_balanced<false, B, 15, 10>)(sc, f, pl, W, H, y0, y1);                      \
   } while (0)
     if (cfg.box) SVO_LAUNCH_BAL(true); else SVO_LAUNCH_BAL(false);
 #undef SVO_LAUNCH_BAL
 #undef SVO_LAUNCH_BALMASK
     return cudaGetLastError();
   }
-  if (cfg.kernel >= 18 && cfg.kernel <= 24) cfg.kernel = 13;
+  if (cfg.kernel >= 18 && cfg.kernel <= 26) cfg.kernel = 13;
   if (cfg.kernel == 9 && !smem_stack_fits(cfg, f)) cfg.kernel = 13;
   if (cfg.kernel >= 9 && cfg.kernel <= 13 && !cfg.fast && cfg.band_stride == 0 && (cfg.kernel != 9 || smem_stack_fits(cfg, f))) {
     const dim3 grid((W + 15) / 16, (y1 - y0 + 7) / 8);

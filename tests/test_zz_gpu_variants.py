@@ -28,7 +28,8 @@ VARIANTS = {7: "refill4", 8: "refill2", 9: "smemstack", 10: "widestack", 11: "re
             15: "split",  # aux planes on: falls back to the default kernel; its own path is the production instance below
             16: "split_presetup",
             17: "tile_queue",  # variant 13 as persistent warps that take whole tiles from a queue
-            19: "balanced_mask7"}  # aux planes on: runs variant 13; the production instance is the ablation
+            19: "balanced_mask7",  # aux planes on: runs variant 13; the production instance is the ablation
+            25: "balanced_9ctas", 26: "balanced_10ctas"}  # 56 / 48 registers (aux planes on: variant 13)
 
 
 @pytest.mark.parametrize("kernel", list(VARIANTS), ids=list(VARIANTS.values()))
