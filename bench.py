@@ -83,6 +83,8 @@ def parse():
                                                          "draws >= 500k pixels of the frame, else 0; 1 = every rank computes the whole lattice; "
                                                          "2 = tile partition with the lattice shared between the ranks (svo_beam_lattice_rows)")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
+    ap.add_argument("--rotate", type=int, default=1, help="tiles: 1 = rank r draws bands (r + k) mod N of frame k, so that with several frames in "
+                                                          "flight every GPU sees the average band load instead of always the same bands")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
                     help="N>1: tiles (default) = ONE frame per step split in interleaved bands, peers store straight into rank 0's "
@@ -465,6 +467,7 @@ def main():
         # measured on 8 B200s (profiles/r02_sharedbeam_*.json) +7 % at N=2, +3 % at N=4 and at N=8 4K, -9 % at N=8 1080p.
         a.beam = (2 if W * H // world_size >= 500_000 and a.fence == "p2p" else 0) if tiles else 1
     BEAM = a.beam >= 1 and MODE in (0, 3) and not a.accumulate and not (tiles and a.fence == "nccl")
+    ROTATE = bool(a.rotate) and tiles and not a.accumulate  # (the running mean of --accumulate lives in the planes a rank drew last time)
     BEAM_SHARED = BEAM and tiles and a.beam == 2  # every rank traces 1/N of the lattice for everybody (svo_beam_lattice_rows)
 
     def frame_for(s):
@@ -563,10 +566,11 @@ def main():
                 k = state["k"]
                 state["k"] = k + 1
                 ctx.select_lane(k % LANES)
+                part = (rank + k) % world_size if ROTATE else rank
                 if rank == 0:
                     beam_for(s, k)
                     bind(k)
-                    ctx.render_interleaved_signal(frames[s], 0, world_size, (), slot=1 + (k % LANES))
+                    ctx.render_interleaved_signal(frames[s], part, world_size, (), slot=1 + (k % LANES))
                     if state["pending"] is not None:
                         finish(*state["pending"])
                     state["pending"] = (k, consume)
@@ -574,7 +578,7 @@ def main():
                     ctx.fence_wait(max(k - LANES + 1, 0), slot=0)  # rank 0 has consumed frames 0..k-LANES: this lane's set is free
                     beam_for(s, k)
                     bind(k)
-                    ctx.render_interleaved_signal(frames[s], rank, world_size, owner_fence, slot=1 + (k % LANES))
+                    ctx.render_interleaved_signal(frames[s], part, world_size, owner_fence, slot=1 + (k % LANES))
 
             def drain():
                 if rank == 0 and state["pending"] is not None:
@@ -722,10 +726,11 @@ def main():
                 l = hstate["k"] % LANES
                 hstate["k"] += 1
                 ctx.select_lane(l)  # (waits, on the device, until this lane's previous copy has left its planes)
+                part = (rank + hstate["k"]) % world_size if ROTATE else rank
                 if BEAM:
                     ctx.beam_conservative(frames[s])
-                ctx.render_interleaved(frames[s], rank, world_size)
-                ctx.read_interleaved_async(rank, world_size, cptr[l], dptr[l])
+                ctx.render_interleaved(frames[s], part, world_size)
+                ctx.read_interleaved_async(part, world_size, cptr[l], dptr[l])
             e2e_host_s = timed(e2e_host_step, ctx.read_wait)
             e2e_host_value = all_rays / e2e_host_s / 1e6
             for ci in range(len(set(CAM_CYCLE))):  # the assembled host frames, for the parity check
@@ -930,7 +935,7 @@ def main():
         "warmup": a.warmup, "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "strong" if tiles else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_of(a, world_size, tree_bytes, partition),
-        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "conservative_beam_prepass": ("lattice shared between the ranks" if BEAM_SHARED else bool(BEAM)), "descriptors": info["descriptors"], "levels": info["levels"],
+        "impl_details": {"kernel": kernel_id, "fast_math": a.fast_math, "frames_in_flight": LANES, "band_rotation": ROTATE, "conservative_beam_prepass": ("lattice shared between the ranks" if BEAM_SHARED else bool(BEAM)), "descriptors": info["descriptors"], "levels": info["levels"],
                          "rays_per_step": {c: per_cam[c]["casts"] for c in CAM_CYCLE},
                          "world": {"how": world_how, "seconds": round(build_s, 2), "maps_s": round(maps_s, 2)}, "build_and_transcode_s": round(upload_s, 3),
                          "units": ("one frame per step, interleaved %d-row bands per rank, peers store into rank 0's planes over NVLink, "
