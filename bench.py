@@ -83,8 +83,10 @@ def parse():
                                                          "draws >= 500k pixels of the frame, else 0; 1 = every rank computes the whole lattice; "
                                                          "2 = tile partition with the lattice shared between the ranks (svo_beam_lattice_rows)")
     ap.add_argument("--band-rows", type=int, default=8, help="tiles: image rows per interleaved band (multiple of 8)")
-    ap.add_argument("--rotate", type=int, default=1, help="tiles: 1 = rank r draws bands (r + k) mod N of frame k, so that with several frames in "
-                                                          "flight every GPU sees the average band load instead of always the same bands")
+    ap.add_argument("--rotate", type=int, default=0, help="tiles: 1 = rank r draws bands (r + k) mod N of frame k, so that with several frames in "
+                                                          "flight every GPU sees the average band load instead of always the same bands "
+                                                          "(measured at N = 8: +1.7 %% on the device, but the host-memory gather drops 10x when the "
+                                                          "pages a rank writes change every frame: off)")
     ap.add_argument("--fence", default="p2p", choices=["p2p", "nccl"], help="tiles: frame-complete fence = NVLink atomics or NCCL all-reduce")
     ap.add_argument("--partition", default="auto", choices=["auto", "frames", "tiles"],
                     help="N>1: tiles (default) = ONE frame per step split in interleaved bands, peers store straight into rank 0's "
