@@ -4,8 +4,11 @@
  * (a) make reference-format node streams for the traversal oracle and
  * (b) check the product's fast builder byte-for-byte.
  *
- * PARITY UNPINNED: no .svo level file ships with the reference (README.md:10)
- * and its Java cannot run here; correspondence is line-by-line.
+ * PINNED: no .svo level file ships with the reference (README.md:10) and no JVM
+ * exists here, but the builder's Java text compiles as C++ after a mechanical
+ * rewrite (oracle/build_ref_java.py -> oracle/_ref/libsvo_ref_java.so);
+ * tests/test_builder_ref.py demands byte-equal streams from that library and
+ * from this file (dense volumes, heightmap worlds with chunk splices).
  *
  * Follows: record writers Octree.java:119-176, fillEmptyChildren :481-502,
  * constructInnerOctree :511-608, genSurfaceNormal :620-649,

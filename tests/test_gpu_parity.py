@@ -838,6 +838,49 @@ def test_incremental_upload_range_equals_whole_upload(svo, oracle, terrain128):
         assert c.upload_stats() == {"dirty": 0, "roots": 0, "appended": 0, "whole_transcode": False}
 
 
+def test_incremental_upload_range_absorbs_the_reference_brush_session(svo, oracle, terrain128):
+    """tests/golden/sdf_edits.npz: a session of the REFERENCE'S OWN brush (Octree.useSDFBrush / subdivideNode compiled from its
+    Java text, tests/golden/make_sdf_edits.py) -- additive and subtractive spheres, a box, a stroke that changes nothing --
+    pushed the way Main.placeSDF pushes it: two svo_upload_range calls per stroke with the ChangeBounds the engine computed.
+    After every stroke the scene equals a whole upload of the same bytes and renders the oracle's frames."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdf_edits.npz"))
+    assert int(g["n"]) == 128 and int(g["chunk"]) == 64 and int(g["base_bytes"]) == terrain128.size
+    W, H = 200, 120
+    cur = terrain128
+    incremental = 0
+    with svo.SvoContext(W, H) as c, svo.SvoContext(64, 64) as fresh:
+        c.upload(cur)
+        for k in range(int(g["steps"])):
+            s0, e0, s1, e1 = (int(v) for v in g["s%d_bounds" % k])
+            tail = g["s%d_tail" % k]
+            nxt = np.zeros(cur.size + tail.size, np.uint8)
+            nxt[:cur.size] = cur
+            nxt[g["s%d_idx" % k]] = g["s%d_val" % k]
+            nxt[cur.size:] = tail
+            if s0 < e0:
+                c.upload_range(nxt, s0, e0)    # renderer.updateSSBO(7, buf, cb.start0, cb.end0)
+                incremental += not c.upload_stats()["whole_transcode"]
+            else:
+                with pytest.raises(svo.SvoError):  # "Update SSBO error: Invalid parameters." (Renderer.java:137-140)
+                    c.upload_range(nxt, s0, e0)
+            if s1 < e1:
+                c.upload_range(nxt, s1, e1)    # renderer.updateSSBO(7, buf, cb.start1, cb.end1)
+            assert c.scene_info()["stream_bytes"] == nxt.size
+            fresh.upload(nxt)
+            a, b = c.scene_canonical(), fresh.scene_canonical()
+            assert (a["reachable"], a["hash"], a["depth"]) == (b["reachable"], b["hash"], b["depth"]), k
+            for cam, mode in (("B", 0), ("C", 2), ("A", 3)):
+                pos, l1, l2, r1, r2 = svo.CAMERAS[cam]
+                want, _ = oracle.render(nxt, oracle.make_frame(pos, l1, l2, r1, r2, frame_number=k + 1, render_mode=mode, max_depth=7), W, H,
+                                        nthreads=8, planes=("rgba8", "depth"))
+                c.render(svo.camera_frame(cam, frame_number=k + 1, render_mode=mode, max_depth=7))
+                assert np.array_equal(c.read_color_rgba8(), want["rgba8"]), (k, cam)
+                assert np.array_equal(c.read_depth().view(np.uint32), want["depth"].view(np.uint32)), (k, cam)
+            cur = nxt
+    assert incremental >= 3
+
+
 def test_incremental_upload_range_on_the_bench_world_is_fast(svo):
     """A 1 KB in-place edit of the 8192^3 world (1.95 GB stream, 87 M descriptors): absorbed without a whole transcode, in
     about a millisecond (the whole transcode takes ~0.1 s), with the same descriptor tree as a whole upload."""
