@@ -20,6 +20,8 @@ What is taken (member names; everything else of the classes -- GL, PNG and file 
     and lines `int[] startPos = ...` to the end of the splice loop of constructCompleteOctree(shader, voxelTexture,
     heightmapTexture, materialTexture) (Octree.java:285-338) as the body of a method buildChunk(chunk, voxelBuffer, maxLOD).
   OctreeThread, Util, sdf/SignedDistanceField, sdf/Sphere, sdf/Box: whole classes.  Constants: the integer constants.
+  src/shaders/chunkgen-heightmap.comp (the voxeliser the builder reads its voxels from): whole, through oracle/build_ref.py's
+    rules R1-R3 and oracle/glsl_voxel_shim.h (generate_voxeliser below).
 
 The rewrite, in full (regular expressions over the comment-stripped text unless noted):
   J1  `byte short long boolean` -> `jbyte jshort jlong bool`; `null` -> `nullptr`; `public private protected final
@@ -55,6 +57,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
 REF = "/root/reference/src/engine"
 OUT = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT, "libsvo_ref_java.so")
@@ -294,9 +298,37 @@ def generate() -> str:
     return "\n\n".join(parts) + "\n"
 
 
+def generate_voxeliser() -> str:
+    """src/shaders/chunkgen-heightmap.comp through rules R1-R3 of oracle/build_ref.py (layout/uniform lines become variables,
+    the rest becomes the body of `struct Invocation`, float literals get `f`), plus: the literal `2048` (= WORLD_SIZE / 4 of the
+    shipped 8192^3 world) becomes `ref_height_scale`, default 2048 (J9)."""
+    from build_ref import rewrite_common, split_items
+    path = os.path.join(os.path.dirname(REF), "shaders", "chunkgen-heightmap.comp")
+    src = strip_comments(open(path, encoding="utf-8", errors="replace").read())
+    hoisted, body = [], []
+    for it in split_items(src):
+        if it.startswith("#version"):
+            continue
+        m = re.match(r"layout\s*\(([^)]*)\)\s*(.*)$", it, flags=re.S)
+        rest = m.group(2) if m else it
+        if m and re.match(r"in\s*;", rest):
+            continue
+        if rest.startswith("uniform"):
+            hoisted.append(re.sub(r"^uniform\s+", "", rest))
+            continue
+        assert not m, "unhandled layout item: " + it[:60]
+        body.append(rewrite_common(it))
+    text = "\n".join(body)
+    assert len(re.findall(r"\* 2048\b", text)) == 1
+    text = re.sub(r"\* 2048\b", "* ref_height_scale", text)
+    return ("// GENERATED by oracle/build_ref_java.py from %s -- do not commit (oracle/_ref/ is git-ignored)\n"
+            "namespace glslv { namespace ref_chunkgen {\nint ref_height_scale = 2048;\n%s\nstruct Invocation : invocation_base {\n%s\n};\n} }\n"
+            % (path, "\n".join(hoisted), text))
+
+
 def build(force: bool = False) -> str | None:
     """Returns the library path, or None when neither /root/reference nor a prebuilt library is there."""
-    srcs = [os.path.join(HERE, f) for f in ("java_shim.h", "ref_java_harness.cpp", "build_ref_java.py")]
+    srcs = [os.path.join(HERE, f) for f in ("java_shim.h", "glsl_voxel_shim.h", "ref_java_harness.cpp", "build_ref_java.py", "build_ref.py")]
     java = [os.path.join(REF, f) for f in ("Octree.java", "OctreeThread.java", "Util.java", "Constants.java", "sdf/Sphere.java",
                                            "sdf/Box.java", "sdf/SignedDistanceField.java")]
     if not os.path.isfile(java[0]):
@@ -306,6 +338,8 @@ def build(force: bool = False) -> str | None:
     os.makedirs(OUT, exist_ok=True)
     with open(GEN, "w") as f:
         f.write(generate())
+    with open(os.path.join(OUT, "ref_chunkgen_gen.inc"), "w") as f:
+        f.write(generate_voxeliser())
     subprocess.check_call(["g++", *CXXFLAGS, "-I", HERE, "-I", OUT, "-o", LIB, os.path.join(HERE, "ref_java_harness.cpp"), "-lm"])
     return LIB
 

@@ -3,9 +3,9 @@
 // restates is only what surrounds those methods in the engine:
 //   * Octree.constructCompleteOctree's frame (Octree.java:244-262): root = createInteriorNode(1), fillEmptyChildren(0,
 //     chunkLevel, rootPos, chunks), then per chunk the voxel volume and the (extracted) thread-and-splice block;
-//   * the voxel volume of a chunk, which the engine gets from a GL compute shader (chunkgen-heightmap.comp:13-31:
-//     `y <= h ? (h - y <= 4 ? material : 1) : 0`, read back with glGetTexImage into a ByteBuffer indexed
-//     x | y << 10 | z << 20, Octree.java:110-112) -- here filled on the CPU with the same rule and the same indexing;
+//   * the dispatch of the voxeliser per chunk (Octree.java:270-282): the shader itself, chunkgen-heightmap.comp, is compiled
+//     from its text too (oracle/glsl_voxel_shim.h) and run per voxel; its image is read back by the engine into a ByteBuffer
+//     indexed x | y << 10 | z << 20 (Octree.java:110-112), which is where the invocations store here;
 //   * Main.placeSDF (Main.java:338-353): `new Sphere(pos, r)`, `octree.useSDFBrush(sdf, value)`, the two ranges.
 // Settable constants (defaults = shipped): Octree::CHUNK_SIZE, Constants::SUB_OCTREE_SIZE, Constants::WORLD_SIZE,
 // Constants::SDF_MAX_LOD -- see rule J9 of the generator.
@@ -13,11 +13,13 @@
 #include <cstdio>
 #include <cstring>
 
+#include "glsl_voxel_shim.h"
 #include "java_shim.h"
 
 namespace javaref {
 #include "ref_java_gen.inc"
 }  // namespace javaref
+#include "ref_chunkgen_gen.inc"  // namespace glslv::ref_chunkgen: chunkgen-heightmap.comp
 
 using namespace javaref;
 
@@ -95,20 +97,31 @@ uint64_t svo_refj_build_terrain(const uint16_t *height, const uint8_t *mat, int 
   ArrayList<Octree::Chunk *> *chunks = new ArrayList<Octree::Chunk *>();
   o->fillEmptyChildren(0, levels, rootPos, chunks);                  // :257
   ByteBuffer *vox = BufferUtils::createByteBuffer(1 << 30);          // :296 (CHUNK_SIZE^3 upstream: the 1024 pitch is getVoxel's)
+  {
+    namespace cg = glslv::ref_chunkgen;
+    cg::ref_height_scale = n / 4;                                    // the shader's literal 2048 = 8192 / 4
+    cg::heightImage.texels = height; cg::heightImage.width = cg::heightImage.height = n;          // image unit 4 (Octree.java:214)
+    cg::matImage.texels = (const int8_t *)mat; cg::matImage.width = cg::matImage.height = n;      // image unit 5 (:226)
+    cg::voxelImage.texels = (int8_t *)vox->data;                                                  // image unit 3
+    cg::voxelImage.width = cg::voxelImage.height = cg::voxelImage.depth = chunk;
+    cg::voxelImage.row_pitch = 1u << 10; cg::voxelImage.slice_pitch = 1u << 20;
+  }
   for (Octree::Chunk *c : *chunks) {
     const size_t mark = BufferUtils::mark();
+    // Octree.java:270-282: offsets = chunk origin, glDispatchCompute over the chunk, glGetTexImage into the voxel buffer.
+    // The dispatch runs the reference's voxeliser itself (chunkgen-heightmap.comp compiled from its text), one invocation
+    // per voxel, storing into the 1024-pitch layout getVoxel reads.
+    namespace cg = glslv::ref_chunkgen;
+    cg::offsetX = c->origin[0];
+    cg::offsetY = c->origin[1];
+    cg::offsetZ = c->origin[2];
+    cg::Invocation inv;
     for (int z = 0; z < chunk; z++)
-      for (int x = 0; x < chunk; x++) {
-        const size_t hm = (size_t)(c->origin[2] + z) * (size_t)n + (size_t)(c->origin[0] + x);
-        const int hs = (int)(((uint32_t)height[hm] * (uint32_t)(n / 4)) >> 16);
-        const uint8_t ms = mat[hm];
-        for (int y = 0; y < chunk; y++) {
-          const int posY = y + c->origin[1];
-          uint8_t v = 0;
-          if (posY <= hs) v = (hs - posY <= 4) ? ms : 1;              // chunkgen-heightmap.comp:13-31
-          vox->data[(size_t)x | (size_t)y << 10 | (size_t)z << 20] = v;
+      for (int y = 0; y < chunk; y++)
+        for (int x = 0; x < chunk; x++) {
+          inv.gl_GlobalInvocationID.set((uint32_t)x, (uint32_t)y, (uint32_t)z);
+          inv.main();
         }
-      }
     o->buildChunk(c, vox, ilog2(chunk / 2));                          // :285-338 (maxLOD = 9 upstream)
     BufferUtils::release_to(mark);                                    // the eight sub-octree buffers
   }
