@@ -151,3 +151,38 @@ def test_incremental_transcode_absorbs_the_reference_brush_session():
             assert np.array_equal(cur, nxt)
         cur = nxt
     assert patched_steps >= 4
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_brush_sessions_through_the_incremental_transcode(refj, oracle, svo, seed):
+    """Random strokes of the reference's brush (spheres and boxes, additive and subtractive, on / under / above the surface),
+    each pushed as the engine pushes it: the GPU copy is the old bytes with the two ranges overwritten, the patched
+    descriptor tree equals a whole transcode of those bytes (SIMT emulator), and it decodes to the engine's own voxels."""
+    from hostemu import emu as E
+    n = 128
+    hm, mm = svo.terrain_inputs(n)
+    base, _ = oracle.build_terrain(hm, mm, n, 64)
+    hs = (hm.astype(np.uint32) * (n // 4)) >> 16
+    rng = np.random.default_rng(seed)
+    engine, gpu = base.copy(), base.copy()
+    incremental = 0
+    for k in range(6):
+        x, z = int(rng.integers(4, n - 4)), int(rng.integers(4, n - 4))
+        y = int(hs[z, x]) + int(rng.integers(-6, 10))
+        kind = "box" if rng.random() < 0.25 else "sphere"
+        params = tuple(int(v) for v in rng.integers(1, 7, 3)) if kind == "box" else (int(rng.integers(1, 10)),)
+        value = int(rng.integers(0, 4))
+        new, ranges, _ = refj.sdf_brush(engine, n, 7, (x, y, z), params, value, kind=kind)
+        nxt = np.zeros(new.size, np.uint8)
+        nxt[:gpu.size] = gpu
+        for a, b in ranges:
+            nxt[a:b] = new[a:b]
+        if ranges:
+            r = E.patch_check(gpu, nxt, ranges)
+            assert r["status"] == 0, (seed, k, kind, value, (x, y, z), params, r)
+            incremental += r["fell_back"] == 0
+        else:
+            assert np.array_equal(nxt, gpu)
+        assert np.array_equal(S.decode_voxels(nxt, n), S.decode_voxels(new, n)), (seed, k)
+        engine, gpu = new, nxt
+    assert incremental >= 3
