@@ -16,7 +16,7 @@ if os.environ.get("SVO_SANITIZE_CHILD") != "1":
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
                            "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-Wno-unknown-pragmas",
                            "-I" + os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include", "-o", LIB] +
-                          [os.path.join(he, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "simt_emu.cpp")] +
+                          [os.path.join(he, f) for f in ("emu.cpp", "kernels_emu.cpp", "wavefront_emu.cpp", "gpu_build_emu.cpp", "transcode_emu.cpp", "simt_emu.cpp")] +
                           [os.path.join(cs, "svo_transcode.cpp"), "-lpthread"])
     asan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"]).decode().strip()
     env = dict(os.environ, SVO_SANITIZE_CHILD="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
@@ -53,4 +53,21 @@ if len(sys.argv)>1:
         print("emulated kernel",k,"ok",flush=True)
     for k in (0,1,2):
         sc.launch_cast(rays,7,kernel=k,nthreads=1)
-    print("emulated stream kernels ok")
+    print("emulated stream kernels ok",flush=True)
+    for k in (17,19):
+        sc.launch_render(f,W,H,kernel=k,aux=False,box=True,nthreads=1)
+    beam=sc.beam_conservative(f,W,H,nthreads=1)
+    assert np.array_equal(sc.beam_in_parts(f,W,H,3,nthreads=1).view(np.uint32),beam.view(np.uint32))
+    print("tile queue, conservative beam (whole and in parts) ok",flush=True)
+    # device world builder, whole and incremental transcode
+    hm64,mm64=svo.terrain_inputs(64)
+    assert np.array_equal(E.gpu_build_terrain(hm64,mm64,64,32),svo.build_terrain(hm64,mm64,64,32))
+    assert E.gpu_transcode_check(nodes)==0
+    import svo_stream as S
+    ed=S.StreamEditor(nodes)
+    p=ed.find_leaf(2,False,rng,min_depth=3)
+    ed.subdivide(p,[0,2,0,0,3,0,0,1])
+    ed.set_value(ed.find_leaf(1,True,rng),0)
+    r=E.patch_check(nodes,ed.stream(),ed.ranges())
+    assert r["status"]==0 and r["fell_back"]==0,r
+    print("device builder, whole and incremental transcode ok")
