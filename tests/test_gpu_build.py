@@ -25,6 +25,23 @@ def test_device_builder_equals_host_builder(svo, n, chunk):
             assert c.scene_probe() == probe_built  # same descriptors, reference offsets and content boxes
 
 
+def test_device_builder_reproduces_the_reference_builders_streams(svo):
+    """tests/golden/builder_golden.json: SHA-256 of the streams the reference's OWN builder produces (Octree.java, OctreeThread.java
+    and the voxeliser shader compiled from their text, tests/golden/make_builder_golden.py) -- 8^3 ... 1024^3, the last with
+    the constants as shipped.  The device builder's bytes have those digests."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "builder_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 8
+    with svo.SvoContext(64, 64) as c:
+        for case in cases:
+            hm, mm = svo.terrain_inputs(case["n"], seed=case["seed"])
+            assert c.build_terrain_device(hm, mm, case["n"], case["chunk"]) == case["bytes"], case
+            assert hashlib.sha256(c.download().tobytes()).hexdigest() == case["sha256"], case
+
+
 def test_device_builder_adversarial_maps(svo):
     from test_builder import _adversarial_maps
     n, chunk = 64, 32
