@@ -99,7 +99,8 @@ enum svo_option {
                                * svo_render_interleaved runs unless 0 or 14 is selected).  All bit-exact; the others are measured ablations */
   SVO_OPT_L2_PERSIST = 4,     /* 0/1: L2 access-policy window (persisting) over the upper octree levels, applied at the next
                                * upload; default 0 (measured: no effect, the path is not memory bound) */
-  SVO_OPT_RAY_SORT = 5,       /* 0/1: trace ray streams of >= 65536 rays in (direction octant, origin Morton code) order; default 1 */
+  SVO_OPT_RAY_SORT = 5,       /* trace ray streams of >= 65536 rays in binned order (results stay in the caller's order): 0 off; 1 = (direction
+                               * octant, origin Morton code); 2 = (octant, 64^3 origin cell, direction bin, finer origin bits); default 2 */
   SVO_OPT_CONTENT_BOUNDS = 6, /* 0/1: end casts that cannot hit anything once they are outside the bounding box of the octree's
                                * non-empty leaves (computed at upload).  Outputs are unchanged; only the iteration count of
                                * MISSING casts differs, so it is ignored in render mode 1 and with SVO_OPT_AUX_PLANES.  default 1 */

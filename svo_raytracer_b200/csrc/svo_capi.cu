@@ -72,7 +72,7 @@ struct svo_ctx {
   uint64_t sort_cap = 0;
   size_t sort_temp_bytes = 0;
   // options
-  int opt_aux = 0, opt_fast = 0, opt_kernel = 13, opt_l2 = 0, opt_sort = 1, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1, opt_stream_kernel = 0;
+  int opt_aux = 0, opt_fast = 0, opt_kernel = 13, opt_l2 = 0, opt_sort = 2, opt_bounds = 1, opt_band_rows = 8, opt_gpu_transcode = 1, opt_stream_kernel = 0;
   CellBox leaf_box, depth_box[24];  // where casts can end in a hit (svo_transcode.h)
   unsigned int *d_tile_counter = nullptr;
   unsigned int *d_fence = nullptr;  // frame-complete counter peers signal over NVLink (svo_fence_*)
@@ -544,7 +544,10 @@ int svo_set_option(svo_ctx *c, int option, int64_t value) {
       refresh_stream(c);
       return SVO_OK;
     case SVO_OPT_L2_PERSIST: c->opt_l2 = value != 0; return SVO_OK;
-    case SVO_OPT_RAY_SORT: c->opt_sort = value != 0; return SVO_OK;
+    case SVO_OPT_RAY_SORT:
+      if (value < 0 || value > 2) return fail(c, SVO_ERR_INVALID, "SVO_OPT_RAY_SORT is 0, 1 or 2");
+      c->opt_sort = (int)value;
+      return SVO_OK;
     case SVO_OPT_CONTENT_BOUNDS: c->opt_bounds = value != 0; return SVO_OK;
     case SVO_OPT_GPU_TRANSCODE: c->opt_gpu_transcode = value != 0; return SVO_OK;
     case SVO_OPT_STREAM_KERNEL:
@@ -1153,7 +1156,7 @@ int svo_cast_device(svo_ctx *c, const void *d_rays, uint64_t n, void *d_out, int
       c->sort_cap = n;
     }
     uint32_t *keys = c->d_sort, *keys_alt = keys + c->sort_cap, *idx = keys_alt + c->sort_cap, *ord = idx + c->sort_cap;
-    SVO_CUDA(c, launch_ray_sort(d_rays, n, keys, keys_alt, idx, ord, c->d_sort_temp, c->sort_temp_bytes, c->stream));
+    SVO_CUDA(c, launch_ray_sort(d_rays, n, keys, keys_alt, idx, ord, c->d_sort_temp, c->sort_temp_bytes, c->opt_sort, c->stream));
     c->launches += 2;
     order = ord;
   }

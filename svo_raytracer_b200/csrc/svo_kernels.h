@@ -106,7 +106,7 @@ cudaError_t gpu_patch(const uint8_t *d_raw, uint64_t nbytes, const uint8_t *d_bi
                       CellBox *depth_box, bool *fallback, uint64_t stats[3], void *arena, size_t arena_bytes, cudaStream_t stream);
 size_t ray_sort_temp_bytes(uint64_t n);
 cudaError_t launch_ray_sort(const void *d_rays, uint64_t n, uint32_t *keys, uint32_t *keys_alt, uint32_t *idx, uint32_t *order_out,
-                            void *temp, size_t temp_bytes, cudaStream_t stream);
+                            void *temp, size_t temp_bytes, int mode, cudaStream_t stream);
 cudaError_t launch_math_probe(int fn, const float *x, const float *y, float *out, uint64_t n, cudaStream_t stream);
 
 }  // namespace svo

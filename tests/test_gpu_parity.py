@@ -677,8 +677,9 @@ def test_progressive_accumulation(svo, oracle, terrain128):
 
 
 def test_ray_binning_keeps_results(svo, oracle, terrain512):
-    """SVO_OPT_RAY_SORT: rays are traced in (octant, origin Morton) order; every hit record lands in the caller's
-    slot, so the output equals the unsorted run and the oracle."""
+    """SVO_OPT_RAY_SORT: rays are traced in binned order -- 1 = (octant, origin Morton code), 2 = (octant, 64^3 origin cell,
+    direction bin, finer origin bits; the default) -- and every hit record lands in the caller's slot, so the output equals the
+    unsorted run and the oracle."""
     rng = np.random.default_rng(9)
     n = 100003
     rays = np.zeros(n, dtype=svo.RAY_DTYPE)
@@ -688,10 +689,16 @@ def test_ray_binning_keeps_results(svo, oracle, terrain512):
     rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     rays["d"][:7] = np.nan
     rays["o"][7:14] = np.nan
+    rays["d"][14:21] = 0.0
+    rays["d"][21:28] = np.inf
+    rays["d"][28:35, 0] = 0.0
     want, _ = oracle.cast_rays(terrain512, rays, max_depth=9, nthreads=8)
     with svo.SvoContext(64, 64) as c:
         c.upload(terrain512)
-        for sort in (1, 0):
+        assert c.get_option(svo._lib.OPT_RAY_SORT) == 2
+        with pytest.raises(svo.SvoError):
+            c.set_option(svo._lib.OPT_RAY_SORT, 3)
+        for sort in (2, 1, 0):
             c.set_option(svo._lib.OPT_RAY_SORT, sort)
             got = c.cast(rays, max_depth=9)
             for k in ("id", "value", "iter"):

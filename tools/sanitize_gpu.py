@@ -106,7 +106,7 @@ rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
 rays["d"][:8] = 0.0
 rays["d"][8:16] = np.nan
 first = None
-for sk, sort in ((0, 0), (0, 1), (1, 1), (2, 1)):
+for sk, sort in ((0, 0), (0, 1), (0, 2), (1, 2), (2, 1)):
     ctx.set_option(L.OPT_STREAM_KERNEL, sk)
     ctx.set_option(L.OPT_RAY_SORT, sort)
     got = ctx.cast(rays, DEPTH)
