@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """SVO_OPT_RAY_SORT 0 / 1 / 2 on a dense-origin incoherent stream (BASELINE configs[3] in spirit: many random directions from
-every surface point of a patch), numpy only.  Times whole svo_cast calls (host buffers: the copies are the same for every mode,
-the difference is binning + traversal).   usage: python tools/sortkey_bench.py [size=2048] [patch=1024] [dirs=8]"""
+every surface point of a patch), numpy + the CUDA runtime through ctypes only.  Times svo_cast_device on device-resident buffers.   usage: python tools/sortkey_bench.py [size=2048] [patch=1024] [dirs=8]"""
 import os
 import sys
 import time
@@ -32,17 +31,26 @@ d = rng.normal(size=(n, 3)).astype(np.float32)
 rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True)
 perm = rng.permutation(n)
 rays = rays[perm]  # the caller's order is arbitrary
+# device-resident buffers through the CUDA runtime (ctypes; no torch): the timed region is binning + traversal only
+import ctypes as C  # noqa: E402
+rt = C.CDLL("libcudart.so.12")
+rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+d_rays, d_hits = C.c_void_p(), C.c_void_p()
+assert rt.cudaMalloc(C.byref(d_rays), rays.nbytes) == 0 and rt.cudaMalloc(C.byref(d_hits), n * 16) == 0
+assert rt.cudaMemcpy(d_rays, rays.ctypes.data_as(C.c_void_p), rays.nbytes, 1) == 0
+hits = np.zeros(n, dtype=svo.HIT_DTYPE)
 ref = None
 for sort in (0, 1, 2, 1, 2):
     ctx.set_option(L.OPT_RAY_SORT, sort)
-    got = ctx.cast(rays, depth)
-    best = 1e9
-    for _ in range(3):
-        t0 = time.perf_counter()
-        got = ctx.cast(rays, depth)
-        best = min(best, time.perf_counter() - t0)
+    ctx.cast_device(d_rays.value, n, d_hits.value, depth)
+    ctx.sync()
+    ctx.timer_begin()
+    for _ in range(5):
+        ctx.cast_device(d_rays.value, n, d_hits.value, depth)
+    ms = ctx.timer_end() / 5
+    assert rt.cudaMemcpy(hits.ctypes.data_as(C.c_void_p), d_hits, n * 16, 2) == 0
     if ref is None:
-        ref = got
-    same = bool(np.array_equal(got, ref))
-    print("size %d, %d rays, SVO_OPT_RAY_SORT %d: %.1f ms per svo_cast (copies included), hit %.2f, mean iter %.1f, identical %s"
-          % (size, n, sort, 1e3 * best, float((got["id"] != 0xFFFFFFFF).mean()), float(got["iter"].mean()), same), flush=True)
+        ref = hits.copy()
+    print("size %d, %d rays, SVO_OPT_RAY_SORT %d: %.3f ms = %.0f Mrays/s (device-resident, binning included), hit %.2f, mean iter %.1f, identical %s"
+          % (size, n, sort, ms, n / ms / 1e3, float((hits["id"] != 0xFFFFFFFF).mean()), float(hits["iter"].mean()), bool(np.array_equal(hits, ref))), flush=True)
